@@ -1,0 +1,115 @@
+/* liblocr - B200-native detect-then-recognize path of lightly-ocr behind a C ABI.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class contract of ocr/net.py
+ * (CRAFT :37-113, CRNN :116-193) as driven by ocr/pipeline.py:47-87.  Each entry point below names the reference
+ * code it replaces; the Python module lightly_ocr_b200/net.py binds them with ctypes and re-exposes the reference's
+ * CRAFT / CRNN classes unchanged.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative locr_status and
+ * never throws; outputs are caller-allocated host buffers; one handle = one GPU = one CUDA stream; a handle is not
+ * thread-safe, distinct handles are.  All calls are synchronous on return.  There is no CPU fallback: without a
+ * CUDA device locr_create fails.
+ */
+#ifndef LOCR_H_
+#define LOCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LOCR_API __attribute__((visibility("default")))
+#else
+#define LOCR_API
+#endif
+
+typedef struct locr_handle locr_handle;
+
+typedef enum {
+    LOCR_OK = 0,
+    LOCR_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+    LOCR_ERR_CUDA = -2,      /* CUDA runtime or driver error (message in locr_last_error) */
+    LOCR_ERR_STATE = -3,     /* weights missing / not finalized */
+    LOCR_ERR_CAPACITY = -4   /* caller-provided output capacity too small */
+} locr_status;
+
+enum { LOCR_MODEL_CRAFT = 0, LOCR_MODEL_CRNN = 1 };
+enum { LOCR_HEAD_CTC = 0, LOCR_HEAD_ATTN = 1 };
+enum { LOCR_ACT_F16 = 0, LOCR_ACT_BF16 = 1 };
+
+/* Mirrors the knobs of CRAFT.__init__ (ocr/net.py:45-50) and the config.yml keys read by CRNN (ocr/config.yml:27-45). */
+typedef struct {
+    int device_id;
+    int act_dtype;        /* LOCR_ACT_*: storage type of activations and weights; accumulation is always fp32 */
+    int head;             /* LOCR_HEAD_* (config.yml `prediction`) */
+    int num_classes;      /* 37 for CTC, 38 for Attention (config.yml `num_classes`) */
+    int canvas_size;      /* 1280  (net.py:45) */
+    float mag_ratio;      /* 1.5   (net.py:46) */
+    float text_threshold; /* 0.7   (net.py:47) */
+    float link_threshold; /* 0.4   (net.py:48) */
+    float low_text;       /* 0.4   (net.py:49) */
+} locr_config;
+
+LOCR_API const char* locr_version(void);
+/* Error text of the last failing call on this thread (handle may be NULL for create/test hooks). */
+LOCR_API const char* locr_last_error(const locr_handle* h);
+
+/* CRAFT.__init__/CRNN.__init__ (net.py:38-51, :117-126): create the per-GPU engine. */
+LOCR_API int locr_create(const locr_config* cfg, locr_handle** out);
+LOCR_API void locr_destroy(locr_handle* h);
+
+/* CRAFT.load / CRNN.load (net.py:59-69, :134-150): one call per state-dict entry, host fp32 data, reference key names
+ * (an optional leading "module." is stripped like copyStateDict, net.py:24-34). */
+LOCR_API int locr_load_tensor(locr_handle* h, int model, const char* key, const float* data, const int64_t* shape,
+                              int ndim);
+/* Folds BatchNorm into the convolutions, converts/lays out weights on the device.  Must follow the loads. */
+LOCR_API int locr_finalize(locr_handle* h, int model);
+
+/* CRAFT.process up to the rect list (net.py:100-107 = preproc :71-80, VGG_UNet forward model.py:39-61,
+ * getDetBoxes det_utils.py:248-256, adjustResultCoordinates :259-265, getCoords net.py:82-98) for n images.
+ *   bgr[i]     : uint8 HxWx3 (cv2.imread layout), row stride strides[i] bytes
+ *   rects      : [max_boxes_total][4] = (min_y, min_x, max_y, max_x) in image pixels, label order (unsorted; the
+ *                reading-order sort compare_rects stays on the host), images concatenated
+ *   boxes      : [max_boxes_total][4][2] float32 score-map-space corners as det_boxes_core returns them (may be NULL)
+ *   box_counts : [n] number of boxes of each image
+ *   score_maps : optional [sum over images of (H/2 * W/2 * 2)] fp32 (text, link interleaved like y[0,:,:,c]) */
+LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
+                         const int* strides, int n, int max_boxes_total, int32_t* rects, float* boxes,
+                         int32_t* box_counts, float* score_maps);
+
+/* pipeline.py:74-79 + CRNN.getPreds/process (net.py:152-193) for n crops at once.
+ *   img[i] : uint8 crop, channels[i] = 3 (BGR, converted like cv2.cvtColor BGR2GRAY) or 1 (gray)
+ *   logits : [n][26][num_classes] fp32 (`preds`) or NULL; token_ids [n][26]; text [n][32] NUL-terminated decoded
+ *   string (CTC: collapsed; Attention: characters before the first [s], has_eos says whether one was found);
+ *   conf   : [n] cumulative product of per-step max softmax probabilities (net.py:190). */
+LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,
+                            const int* strides, const int* channels, int n, float* logits, int32_t* token_ids,
+                            char* text, int32_t* has_eos, float* conf);
+
+/* Fused throughput path = getText (pipeline.py:65-87) for a batch of images, crops never leave the GPU.
+ *   rects come back sorted in the reference's reading order per image. */
+LOCR_API int locr_ocr_batch(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
+                            const int* strides, int n, int max_boxes_total, int32_t* rects, int32_t* box_counts,
+                            char* text, int32_t* has_eos, float* conf);
+
+/* Kernel launches issued by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
+LOCR_API int64_t locr_launch_count(const locr_handle* h);
+
+/* ---- kernel-level test hooks (used by tests/ only; same kernels as the product path) ---- */
+typedef struct {
+    int B, H, W, Cin, Cout;
+    int KH, KW, dil_h, dil_w, pad_h, pad_w, stride_h;
+    int x_pitch, y_pitch;      /* elements per pixel of the input / output buffers (>= Cin / Cout) */
+    int relu, out_fp32, act_dtype, n_tile;
+} locr_conv_desc;
+/* x [B,H,W,x_pitch] fp32 NHWC, w [Cout,KH,KW,Cin] fp32, bias [Cout] or NULL, residual [B,OH,OW,Cout] or NULL,
+ * y [B,OH,OW,y_pitch] fp32.  Inputs are rounded to the 16-bit activation type on the way in. */
+LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
+                            const float* residual, float* y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCR_H_ */

@@ -1,0 +1,478 @@
+// Implicit-GEMM convolution for sm_100a.
+//
+//   GEMM view:  D[M = output pixels, N = Cout] = sum over (tap, channel chunk) of A[M, 64ch] * W[N, 64ch]^T
+//   A operand : one TMA box per (tap, channel chunk): a bw x bh x bb patch of NHWC pixels (128 rows of the M
+//               tile) shifted by the tap offset; out-of-bounds pixels are zero-filled by the TMA unit, which IS the
+//               convolution's zero padding - no im2col buffer, no halo copies, no boundary branches.
+//   B operand : K-major weight slab [n_tile][64] from a 2-D tensor map.
+//   MMA       : tcgen05.mma cta_group::1 kind::f16, M=128, N=n_tile (16..256), K=16; fp32 accumulators in TMEM,
+//               double-buffered so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   Epilogue  : tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit NHWC (or fp32) stores.
+//   Roles     : warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+//   Grid      : persistent, one CTA per SM, static round-robin over (m_tile, n_tile) with n fastest so the
+//               activation patch is reused out of L2 by consecutive CTAs.
+//
+// Replaces the cuDNN conv + separate BN/ReLU kernels behind nn.Conv2d/nn.BatchNorm2d/nn.ReLU in
+// reference ocr/modules/vgg_bn.py:23-55, ocr/model.py:21-31, ocr/modules/resnet50v1.py:55-82,
+// ocr/modules/TPS_STN.py:38-58 and the nn.Linear GEMMs of ocr/modules/biLSTM.py:18-20.
+#include "conv_tc.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include "ptx.cuh"
+
+namespace locr {
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+
+struct ConvParams {
+    int B, OH, OW, Cout;
+    int bw, bh, bb;
+    int tiles_w, tiles_h, tiles_n, num_tiles;
+    int n_tile, n_tile_alloc, tmem_cols;
+    int cin_chunks, KW, dil_h, dil_w, pad_h, pad_w, stride2;
+    int num_kblocks, stages;
+    uint32_t a_stage_bytes, b_stage_bytes;
+    uint32_t idesc;
+    void* y;
+    long y_pitch;
+    int out_fp32;
+    const void* res;
+    long res_pitch;
+    const float* bias;
+    int relu, is_f16;
+};
+
+struct TileCoord {
+    int n0, ow0, oh0, b0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+    TileCoord t;
+    int n_idx = tile % p.tiles_n;
+    int m_idx = tile / p.tiles_n;
+    int tw = m_idx % p.tiles_w;
+    int rest = m_idx / p.tiles_w;
+    int th = rest % p.tiles_h;
+    int tb = rest / p.tiles_h;
+    t.n0 = n_idx * p.n_tile;
+    t.ow0 = tw * p.bw;
+    t.oh0 = th * p.bh;
+    t.b0 = tb * p.bb;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
+    if (is_f16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
+    if (is_f16) {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    } else {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    }
+}
+
+template <int SWZ>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const ConvParams p) {
+    constexpr int BLOCK_K = SWZ / 2;      // 16-bit elements per swizzled row
+    constexpr int MMAS_PER_STAGE = BLOCK_K / 16;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::tma_prefetch_desc(&tmap_x);
+        ptx::tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tfull_bar[a], 1);
+            ptx::mbar_init(&tempty_bar[a], 4);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    const int tap = kb / p.cin_chunks;
+                    const int cc = kb - tap * p.cin_chunks;
+                    const int kh = tap / p.KW;
+                    const int kw = tap - kh * p.KW;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    const int iw0 = t.ow0 + kw * p.dil_w - p.pad_w;
+                    int c2, c3;
+                    if (p.stride2) {  // input row = 2*oh + kh : dim2 selects kh, dim3 walks oh
+                        c2 = kh;
+                        c3 = t.oh0;
+                    } else {
+                        c2 = 0;
+                        c3 = t.oh0 + kh * p.dil_h - p.pad_h;
+                    }
+                    ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_x, &full_bar[stage],
+                                     cc * BLOCK_K, iw0, c2, c3, t.b0);
+                    ptx::tma_load_2d(smem_b + (size_t)stage * p.b_stage_bytes, &tmap_w, &full_bar[stage],
+                                     kb * BLOCK_K, t.n0);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 200 + acc);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile_alloc);
+                for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
+                    const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * p.b_stage_bytes);
+#pragma unroll
+                    for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                        const uint64_t da = ptx::make_kmajor_desc(a_addr + k * 32, SWZ);
+                        const uint64_t db = ptx::make_kmajor_desc(b_addr + k * 32, SWZ);
+                        ptx::umma_f16(d_tmem, da, db, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        const int rw = row % p.bw;
+        const int rh = (row / p.bw) % p.bh;
+        const int rb = row / (p.bw * p.bh);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int chunks = (p.n_tile + 31) / 32;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const int ow = t.ow0 + rw, oh = t.oh0 + rh, b = t.b0 + rb;
+            const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
+            const long pix = ((long)b * p.OH + oh) * p.OW + ow;
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+            ptx::tc_fence_after();
+            for (int c = 0; c < chunks; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr =
+                    tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile_alloc + c * 32);
+                ptx::tmem_ld_32x32(taddr, r);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    const int nb = t.n0 + c * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(&p.bias[nb + j]);
+                    if (p.res != nullptr) {
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pitch + nb;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (nb + q * 8 < p.Cout) {
+                                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + q * 8));
+                                const float2 f0 = unpack2(u.x, p.is_f16), f1 = unpack2(u.y, p.is_f16);
+                                const float2 f2 = unpack2(u.z, p.is_f16), f3 = unpack2(u.w, p.is_f16);
+                                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y;
+                                v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y;
+                                v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    if (p.out_fp32) {
+                        float* yp = reinterpret_cast<float*>(p.y) + pix * p.y_pitch + nb;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.Cout) yp[j] = v[j];
+                    } else {
+                        uint16_t* yp = reinterpret_cast<uint16_t*>(p.y) + pix * p.y_pitch + nb;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (nb + q * 8 < p.Cout) {
+                                uint4 u;
+                                u.x = pack2(v[q * 8 + 0], v[q * 8 + 1], p.is_f16);
+                                u.y = pack2(v[q * 8 + 2], v[q * 8 + 3], p.is_f16);
+                                u.z = pack2(v[q * 8 + 4], v[q * 8 + 5], p.is_f16);
+                                u.w = pack2(v[q * 8 + 6], v[q * 8 + 7], p.is_f16);
+                                *reinterpret_cast<uint4*>(yp + q * 8) = u;
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    }
+    return fn;
+}
+
+void set_err(char* err, int errlen, const char* msg) {
+    if (err != nullptr && errlen > 0) {
+        strncpy(err, msg, errlen - 1);
+        err[errlen - 1] = 0;
+    }
+}
+
+template <int SWZ>
+cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, int grid, size_t smem,
+                       cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_tc_kernel<SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    conv_tc_kernel<SWZ><<<grid, kThreads, smem, stream>>>(mx, mw, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int device_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, int errlen) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) {
+        set_err(err, errlen, "cuTensorMapEncodeTiled entry point not available");
+        return cudaErrorNotSupported;
+    }
+    int swz = 0;
+    if (c.Cin % 64 == 0) swz = 128;
+    else if (c.Cin % 32 == 0) swz = 64;
+    else if (c.Cin % 16 == 0) swz = 32;
+    else {
+        set_err(err, errlen, "conv_tc: Cin must be a multiple of 16");
+        return cudaErrorInvalidValue;
+    }
+    const int block_k = swz / 2;
+    if (c.stride_h != 1 && !(c.stride_h == 2 && c.KH == 2 && c.pad_h == 0 && c.dil_h == 1 && c.H % 2 == 0)) {
+        set_err(err, errlen, "conv_tc: unsupported vertical stride configuration");
+        return cudaErrorInvalidValue;
+    }
+    if (c.Cout_pad % 16 != 0 || c.x_pitch % 8 != 0 || (!c.out_fp32 && (c.y_pitch % 8 != 0 || c.Cout % 8 != 0))) {
+        set_err(err, errlen, "conv_tc: channel counts / pitches must keep 16-byte alignment");
+        return cudaErrorInvalidValue;
+    }
+    int n_tile = c.n_tile;
+    if (n_tile == 0) {
+        if (c.Cout_pad % 256 == 0) n_tile = 256;
+        else if (c.Cout_pad % 128 == 0) n_tile = 128;
+        else if (c.Cout_pad <= 256) n_tile = c.Cout_pad;
+        else if (c.Cout_pad % 64 == 0) n_tile = 64;
+        else n_tile = 16;
+    }
+    if (n_tile < 16 || n_tile > 256 || n_tile % 16 != 0 || c.Cout_pad % n_tile != 0) {
+        set_err(err, errlen, "conv_tc: invalid n_tile");
+        return cudaErrorInvalidValue;
+    }
+
+    // Pick the 128-pixel patch shape (bw x bh x bb, all powers of two) that covers the output with fewest tiles.
+    int best_bw = 0, best_bh = 0, best_bb = 0;
+    long best_tiles = -1;
+    for (int bw = 128; bw >= 1; bw >>= 1) {
+        for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+            const int bb = 128 / (bw * bh);
+            const long tiles = (long)((c.OW + bw - 1) / bw) * ((c.OH + bh - 1) / bh) * ((c.B + bb - 1) / bb);
+            if (best_tiles < 0 || tiles < best_tiles) {
+                best_tiles = tiles;
+                best_bw = bw;
+                best_bh = bh;
+                best_bb = bb;
+            }
+        }
+    }
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = c.B; p.OH = c.OH; p.OW = c.OW; p.Cout = c.Cout;
+    p.bw = best_bw; p.bh = best_bh; p.bb = best_bb;
+    p.tiles_w = (c.OW + p.bw - 1) / p.bw;
+    p.tiles_h = (c.OH + p.bh - 1) / p.bh;
+    const int tiles_b = (c.B + p.bb - 1) / p.bb;
+    p.tiles_n = c.Cout_pad / n_tile;
+    const long num_tiles = (long)p.tiles_w * p.tiles_h * tiles_b * p.tiles_n;
+    if (num_tiles <= 0 || num_tiles > 0x7fffffffL) {
+        set_err(err, errlen, "conv_tc: empty or oversized problem");
+        return cudaErrorInvalidValue;
+    }
+    p.num_tiles = (int)num_tiles;
+    p.n_tile = n_tile;
+    p.n_tile_alloc = (n_tile + 31) / 32 * 32;
+    int cols = 32;
+    while (cols < 2 * p.n_tile_alloc) cols <<= 1;
+    p.tmem_cols = cols;
+    p.cin_chunks = c.Cin / block_k;
+    p.KW = c.KW; p.dil_h = c.dil_h; p.dil_w = c.dil_w; p.pad_h = c.pad_h; p.pad_w = c.pad_w;
+    p.stride2 = (c.stride_h == 2) ? 1 : 0;
+    p.num_kblocks = c.KH * c.KW * p.cin_chunks;
+    p.a_stage_bytes = (uint32_t)(kTileM * swz);
+    p.b_stage_bytes = (uint32_t)((n_tile * swz + 1023) / 1024 * 1024);
+    const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, kTileM, n_tile);
+    p.y = c.y; p.y_pitch = c.y_pitch; p.out_fp32 = c.out_fp32;
+    p.res = c.residual; p.res_pitch = c.res_pitch;
+    p.bias = c.bias; p.relu = c.relu; p.is_f16 = (c.dtype == ACT_F16) ? 1 : 0;
+
+    const CUtensorMapDataType dt =
+        (c.dtype == ACT_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw =
+        swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+
+    CUtensorMap mx, mw;
+    {
+        const int S = p.stride2 ? 2 : 1;
+        cuuint64_t dims[5] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)S, (cuuint64_t)(c.H / S),
+                              (cuuint64_t)c.B};
+        const cuuint64_t pb = (cuuint64_t)c.x_pitch * 2;
+        cuuint64_t strides[4] = {pb, pb * c.W, pb * c.W * S, pb * c.W * c.H};
+        cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&mx, dt, 5, const_cast<void*>(c.x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "conv_tc: activation tensor map encode failed (CUresult %d)", (int)r);
+            set_err(err, errlen, msg);
+            return cudaErrorInvalidValue;
+        }
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)c.KH * c.KW * c.Cin;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)c.Cout_pad};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&mw, dt, 2, const_cast<void*>(c.w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "conv_tc: weight tensor map encode failed (CUresult %d)", (int)r);
+            set_err(err, errlen, msg);
+            return cudaErrorInvalidValue;
+        }
+    }
+
+    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
+    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    cudaError_t e;
+    if (swz == 128) e = launch_swz<128>(mx, mw, p, grid, smem, stream);
+    else if (swz == 64) e = launch_swz<64>(mx, mw, p, grid, smem, stream);
+    else e = launch_swz<32>(mx, mw, p, grid, smem, stream);
+    if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
+    return e;
+}
+
+}  // namespace locr

@@ -1,0 +1,40 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
+// Host-side description of one layer invocation; see conv_tc.cu for the kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace locr {
+
+enum ActDType { ACT_F16 = 0, ACT_BF16 = 1 };
+
+// One convolution call: y = act( conv(x, w) + bias [+ residual] ).  BN scale is folded into w on load.
+//   x : NHWC activation view, 16-bit elements, channel pitch x_pitch (>= Cin; concat buffers are views)
+//   w : [Cout_pad][KH*KW*Cin] K-major, k = (kh*KW + kw)*Cin + c, 16-bit elements (same type as x)
+//   y : NHWC, channel pitch y_pitch, 16-bit (same type as x) or fp32 when out_fp32
+struct ConvCall {
+    const void* x = nullptr;
+    int B = 0, H = 0, W = 0, Cin = 0;
+    long x_pitch = 0;
+    const void* w = nullptr;
+    int Cout = 0, Cout_pad = 0;
+    int KH = 1, KW = 1, dil_h = 1, dil_w = 1, pad_h = 0, pad_w = 0, stride_h = 1;  // stride_w is always 1 on this path
+    void* y = nullptr;
+    int OH = 0, OW = 0;
+    long y_pitch = 0;
+    int out_fp32 = 0;
+    const float* bias = nullptr;   // [Cout_pad] fp32
+    const void* residual = nullptr;  // NHWC at output resolution, 16-bit, pitch res_pitch
+    long res_pitch = 0;
+    int relu = 0;
+    int dtype = ACT_BF16;
+    int n_tile = 0;  // 0 = choose automatically
+};
+
+// Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).
+cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, int errlen);
+
+// Number of SMs used for the persistent grid (queried once).
+int device_sm_count();
+
+}  // namespace locr

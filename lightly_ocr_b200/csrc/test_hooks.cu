@@ -1,0 +1,94 @@
+// Kernel-level test hooks behind the C ABI.  They drive exactly the kernels the product path uses, on host data.
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "util.cuh"
+
+namespace locr {
+
+std::string& tls_error() {
+    static thread_local std::string e;
+    return e;
+}
+int fail(int code, const std::string& msg) {
+    tls_error() = msg;
+    return code;
+}
+
+}  // namespace locr
+
+using namespace locr;
+
+extern "C" {
+
+LOCR_API const char* locr_version(void) { return "liblocr 0.1 (sm_100a)"; }
+LOCR_API const char* locr_last_error(const locr_handle* h) {
+    (void)h;
+    return tls_error().c_str();
+}
+
+LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
+                            const float* residual, float* y) {
+    if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LOCR_ERR_CUDA, "no CUDA device: liblocr has no CPU fallback");
+    const int S = d->stride_h;
+    const int OH = (d->H + 2 * d->pad_h - d->dil_h * (d->KH - 1) - 1) / S + 1;
+    const int OW = (d->W + 2 * d->pad_w - d->dil_w * (d->KW - 1) - 1) + 1;
+    const int cout_pad = (d->Cout + 15) / 16 * 16;
+    const size_t nx = (size_t)d->B * d->H * d->W * d->x_pitch;
+    const size_t ktot = (size_t)d->KH * d->KW * d->Cin;
+    const size_t nw = (size_t)cout_pad * ktot;
+    const size_t npix = (size_t)d->B * OH * OW;
+    const size_t ny = npix * d->y_pitch;
+
+    std::vector<uint16_t> hx(nx), hw(nw, 0);
+    for (size_t i = 0; i < nx; ++i) hx[i] = f32_to_act(x[i], d->act_dtype);
+    for (size_t i = 0; i < (size_t)d->Cout * ktot; ++i) hw[i] = f32_to_act(w[i], d->act_dtype);
+    std::vector<float> hb(cout_pad, 0.f);
+    if (bias) for (int i = 0; i < d->Cout; ++i) hb[i] = bias[i];
+    std::vector<uint16_t> hr;
+    if (residual) {
+        hr.resize(npix * d->Cout);
+        for (size_t i = 0; i < hr.size(); ++i) hr[i] = f32_to_act(residual[i], d->act_dtype);
+    }
+
+    DevBuf dx, dw, db, dr, dy;
+    LOCR_CUDA_OK(dx.alloc(nx * 2));
+    LOCR_CUDA_OK(dw.alloc(nw * 2));
+    LOCR_CUDA_OK(db.alloc(cout_pad * 4));
+    LOCR_CUDA_OK(dy.alloc(ny * (d->out_fp32 ? 4 : 2)));
+    LOCR_CUDA_OK(cudaMemcpy(dx.p, hx.data(), nx * 2, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemcpy(dw.p, hw.data(), nw * 2, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemcpy(db.p, hb.data(), cout_pad * 4, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemset(dy.p, 0, ny * (d->out_fp32 ? 4 : 2)));
+    if (residual) {
+        LOCR_CUDA_OK(dr.alloc(hr.size() * 2));
+        LOCR_CUDA_OK(cudaMemcpy(dr.p, hr.data(), hr.size() * 2, cudaMemcpyHostToDevice));
+    }
+
+    ConvCall c;
+    c.x = dx.p; c.B = d->B; c.H = d->H; c.W = d->W; c.Cin = d->Cin; c.x_pitch = d->x_pitch;
+    c.w = dw.p; c.Cout = d->Cout; c.Cout_pad = cout_pad;
+    c.KH = d->KH; c.KW = d->KW; c.dil_h = d->dil_h; c.dil_w = d->dil_w; c.pad_h = d->pad_h; c.pad_w = d->pad_w;
+    c.stride_h = S;
+    c.y = dy.p; c.OH = OH; c.OW = OW; c.y_pitch = d->y_pitch; c.out_fp32 = d->out_fp32;
+    c.bias = db.as<float>();
+    c.residual = residual ? dr.p : nullptr; c.res_pitch = d->Cout;
+    c.relu = d->relu; c.dtype = d->act_dtype; c.n_tile = d->n_tile;
+    char err[256] = {0};
+    cudaError_t e = conv_tc_launch(c, 0, err, sizeof(err));
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? LOCR_ERR_INVALID : LOCR_ERR_CUDA, err);
+    LOCR_CUDA_OK(cudaDeviceSynchronize());
+    if (d->out_fp32) {
+        LOCR_CUDA_OK(cudaMemcpy(y, dy.p, ny * 4, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<uint16_t> hy(ny);
+        LOCR_CUDA_OK(cudaMemcpy(hy.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ny; ++i) y[i] = act_to_f32(hy[i], d->act_dtype);
+    }
+    return LOCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+"""Parity of the tcgen05 implicit-GEMM convolution against torch's CPU fp32 conv2d on identically rounded operands.
+
+Floating point: the kernel multiplies 16-bit operands exactly and accumulates in fp32, so against an fp32 reference
+on the same rounded inputs the only difference is accumulation order: tolerance 2e-3 * max|y| on fp32 outputs
+(K up to 4608), plus one 16-bit rounding step (2^-8 relative for bf16, 2^-11 for fp16) on 16-bit outputs.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _round(a, act_dtype):
+    t = torch.from_numpy(np.ascontiguousarray(a, np.float32))
+    return t.to(torch.bfloat16 if act_dtype == 1 else torch.float16).float()
+
+
+def _ref(x, w, bias, residual, dil, pad, stride_h, relu, act_dtype):
+    xr = _round(x, act_dtype).permute(0, 3, 1, 2)
+    wr = _round(w, act_dtype).permute(0, 3, 1, 2)
+    y = F.conv2d(xr, wr, None if bias is None else torch.from_numpy(bias), stride=(stride_h, 1), padding=pad,
+                 dilation=dil)
+    if residual is not None:
+        y = y + _round(residual, act_dtype).permute(0, 3, 1, 2)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+CASES = [
+    # name, B, H, W, Cin, Cout, KH, KW, dil, pad, stride_h, relu, residual, out_fp32, act, x_extra, y_extra, n_tile
+    ("3x3_c64", 1, 32, 32, 64, 64, 3, 3, (1, 1), (1, 1), 1, False, False, True, 1, 0, 0, 0),
+    ("3x3_c128_n256_b2", 2, 20, 24, 128, 256, 3, 3, (1, 1), (1, 1), 1, True, False, True, 1, 0, 0, 0),
+    ("1x1_c192", 1, 17, 23, 192, 64, 1, 1, (1, 1), (0, 0), 1, False, False, True, 1, 0, 0, 0),
+    ("dil6", 1, 24, 24, 64, 128, 3, 3, (6, 6), (6, 6), 1, False, False, True, 1, 0, 0, 0),
+    ("k2_s21_p01", 16, 4, 26, 64, 64, 2, 2, (1, 1), (0, 1), 2, True, False, True, 1, 0, 0, 0),
+    ("k2_s1_p0", 16, 2, 27, 64, 64, 2, 2, (1, 1), (0, 0), 1, True, False, True, 1, 0, 0, 0),
+    ("sw64_c32", 1, 40, 36, 32, 32, 3, 3, (1, 1), (1, 1), 1, True, False, True, 1, 0, 0, 0),
+    ("sw32_c16", 1, 40, 36, 16, 16, 3, 3, (1, 1), (1, 1), 1, True, False, True, 1, 0, 0, 0),
+    ("residual_bf16out", 4, 4, 26, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 1, 0, 0, 0),
+    ("fp16", 2, 16, 50, 64, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    ("head_c37", 8, 1, 26, 256, 37, 1, 1, (1, 1), (0, 0), 1, False, False, True, 1, 0, 0, 0),
+    ("views", 1, 30, 28, 64, 64, 3, 3, (1, 1), (1, 1), 1, True, False, False, 1, 64, 32, 0),
+    ("deep_k_multi_tile", 64, 4, 26, 512, 512, 3, 3, (1, 1), (1, 1), 1, True, True, False, 1, 0, 0, 0),
+    ("n_tile_128_of_512", 2, 16, 16, 64, 512, 3, 3, (1, 1), (1, 1), 1, False, False, True, 1, 0, 0, 128),
+    ("big_plane", 1, 160, 120, 64, 64, 3, 3, (1, 1), (1, 1), 1, True, False, False, 1, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_parity(case):
+    from lightly_ocr_b200 import bridge
+    (name, B, H, W, Cin, Cout, KH, KW, dil, pad, stride_h, relu, use_res, out_fp32, act, x_extra, y_extra,
+     n_tile) = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    x = rng.standard_normal((B, H, W, Cin + x_extra)).astype(np.float32)
+    w = (rng.standard_normal((Cout, KH, KW, Cin)) / np.sqrt(KH * KW * Cin)).astype(np.float32)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    OH = (H + 2 * pad[0] - dil[0] * (KH - 1) - 1) // stride_h + 1
+    OW = (W + 2 * pad[1] - dil[1] * (KW - 1) - 1) + 1
+    residual = rng.standard_normal((B, OH, OW, Cout)).astype(np.float32) if use_res else None
+    y = bridge.test_conv(x, w, bias, residual, dil=dil, pad=pad, stride_h=stride_h, relu=relu, out_fp32=out_fp32,
+                         act_dtype=act, n_tile=n_tile, y_pitch=Cout + y_extra)
+    ref = _ref(x[..., :Cin], w, bias, residual, dil, pad, stride_h, relu, act)
+    assert y.shape[:3] == ref.shape[:3]
+    got = y[..., :Cout]
+    scale = float(np.abs(ref).max())
+    tol = 2e-3 * scale
+    if not out_fp32:
+        tol += scale * (2.0 ** -8 if act == 1 else 2.0 ** -11)
+    err = float(np.abs(got - ref).max())
+    assert err <= tol, "%s: max abs err %g > tol %g (scale %g)" % (name, err, tol, scale)
+    if y_extra:
+        assert np.all(y[..., Cout:] == 0), "kernel wrote outside its channel view"
