@@ -109,6 +109,9 @@ typedef struct {
 LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
                             const float* residual, float* y);
 
+/* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
+LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);
+
 #ifdef __cplusplus
 }
 #endif

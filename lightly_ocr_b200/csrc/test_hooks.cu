@@ -91,4 +91,50 @@ LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float
     return LOCR_OK;
 }
 
+/* Times `iters` back-to-back launches of one conv layer on uninitialised (zeroed) device buffers. */
+LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter) {
+    const int S = d->stride_h;
+    const int OH = (d->H + 2 * d->pad_h - d->dil_h * (d->KH - 1) - 1) / S + 1;
+    const int OW = (d->W + 2 * d->pad_w - d->dil_w * (d->KW - 1) - 1) + 1;
+    const int cout_pad = (d->Cout + 15) / 16 * 16;
+    const size_t nx = (size_t)d->B * d->H * d->W * d->x_pitch;
+    const size_t ktot = (size_t)d->KH * d->KW * d->Cin;
+    const size_t nw = (size_t)cout_pad * ktot;
+    const size_t ny = (size_t)d->B * OH * OW * d->y_pitch;
+    DevBuf dx, dw, db, dy;
+    LOCR_CUDA_OK(dx.alloc(nx * 2));
+    LOCR_CUDA_OK(dw.alloc(nw * 2));
+    LOCR_CUDA_OK(db.alloc(cout_pad * 4));
+    LOCR_CUDA_OK(dy.alloc(ny * (d->out_fp32 ? 4 : 2)));
+    LOCR_CUDA_OK(cudaMemset(dx.p, 0x11, nx * 2));
+    LOCR_CUDA_OK(cudaMemset(dw.p, 0x11, nw * 2));
+    LOCR_CUDA_OK(cudaMemset(db.p, 0, cout_pad * 4));
+    ConvCall c;
+    c.x = dx.p; c.B = d->B; c.H = d->H; c.W = d->W; c.Cin = d->Cin; c.x_pitch = d->x_pitch;
+    c.w = dw.p; c.Cout = d->Cout; c.Cout_pad = cout_pad;
+    c.KH = d->KH; c.KW = d->KW; c.dil_h = d->dil_h; c.dil_w = d->dil_w; c.pad_h = d->pad_h; c.pad_w = d->pad_w;
+    c.stride_h = S;
+    c.y = dy.p; c.OH = OH; c.OW = OW; c.y_pitch = d->y_pitch; c.out_fp32 = d->out_fp32;
+    c.bias = db.as<float>();
+    c.relu = d->relu; c.dtype = d->act_dtype; c.n_tile = d->n_tile;
+    char err[256] = {0};
+    for (int i = 0; i < 3; ++i) {
+        cudaError_t e = conv_tc_launch(c, 0, err, sizeof(err));
+        if (e != cudaSuccess) return fail(LOCR_ERR_CUDA, err);
+    }
+    cudaEvent_t e0, e1;
+    LOCR_CUDA_OK(cudaEventCreate(&e0));
+    LOCR_CUDA_OK(cudaEventCreate(&e1));
+    LOCR_CUDA_OK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) conv_tc_launch(c, 0, err, sizeof(err));
+    LOCR_CUDA_OK(cudaEventRecord(e1, 0));
+    LOCR_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    LOCR_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_iter = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return LOCR_OK;
+}
+
 }  // extern "C"
