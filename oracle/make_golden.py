@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.npz by running the REAL reference (this container only).
+
+/root/reference is read-only and absent on the GPU box, so the live reference is imported here once, fed the
+synthetic checkpoints of oracle/weights.py, and its outputs are committed as small fixtures.  The reference sources
+are copied to a scratch directory under /tmp (never into the repository) because ocr/net.py derives its checkpoint
+directory from its own location (net.py:19) and needs a writable save_models/.
+
+Shims, none of them touching reference files:
+  * torchvision.models.vgg.model_urls   (removed from torchvision >= 0.13; vgg_bn.py:6,37 only rewrites a URL)
+  * stub modules lmdb, skimage, skimage.io  (imported by tools/dataset.py:7, tools/imgproc.py:3; unused on the path)
+  * the scratch copy's config.yml gets `prediction` / `num_classes` set per head
+
+Usage:  python -m oracle.make_golden
+"""
+import contextlib
+import io
+import json
+import os
+import shutil
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference/ocr"
+
+
+def load_reference(head, scratch):
+    """Import the reference's net / pipeline modules from a scratch copy configured for `head`."""
+    import yaml
+    dst = os.path.join(scratch, "ocr_" + head)
+    if os.path.exists(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(REF, dst)
+    os.makedirs(os.path.join(dst, "test"), exist_ok=True)
+    cfg_path = os.path.join(dst, "config.yml")
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["prediction"] = head
+    cfg["num_classes"] = 37 if head == "CTC" else 38
+    yaml.safe_dump(cfg, open(cfg_path, "w"))
+    import torchvision.models.vgg as tv_vgg
+    if not hasattr(tv_vgg, "model_urls"):
+        tv_vgg.model_urls = {"vgg16_bn": "https://download.pytorch.org/models/vgg16_bn-6c64b313.pth"}
+    for name in ("lmdb", "skimage", "skimage.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage"].io = sys.modules["skimage.io"]
+    for m in [k for k in sys.modules if k.split(".")[0] in ("net", "model", "modules", "tools", "pipeline")]:
+        del sys.modules[m]
+    sys.path.insert(0, dst)
+    cwd = os.getcwd()
+    os.chdir(dst)  # MODEL_PATH is relative to the cwd (os.path.relpath, net.py:19)
+    return dst, cwd
+
+
+def unload_reference(dst, cwd):
+    os.chdir(cwd)
+    sys.path.remove(dst)
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from oracle import ocr_ref, receipts, weights
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLDEN, exist_ok=True)
+    scratch = "/tmp/locr_ref_scratch"
+    os.makedirs(scratch, exist_ok=True)
+
+    # ---- calibrations of the synthetic checkpoints (committed so every machine loads identical tensors)
+    if "--keep-calib" not in sys.argv:
+        weights.build_calibrations()
+    img0 = receipts.receipt(0)
+    craft_calibrated = weights.craft_calibrated
+
+    for head in ("CTC", "Attention"):
+        dst, cwd = load_reference(head, scratch)
+        try:
+            craft_sd = craft_calibrated(0, ink=True)
+            crnn_sd = weights.crnn_calibrated(1, head=head)
+            os.makedirs("save_models", exist_ok=True)
+            torch.save(craft_sd, os.path.join("save_models", "CRAFT.pth"))
+            torch.save(crnn_sd, os.path.join("save_models", "CRNN.pth"))
+            import net as ref_net
+            import pipeline as ref_pipeline
+            import tools as ref_tools
+            out = {}
+            detector, recognizer = ref_pipeline.prepModel(ref_pipeline.CONFIG, docker=True)
+
+            if head == "CTC":
+                # -- config 2 at reduced size: reference CRAFT on a 256x192 window of receipt(0) (ratio 1.5 resize path)
+                win = np.ascontiguousarray(img0[40:296, 40:232])
+                with torch.no_grad():
+                    xt, rw, rh = detector.preproc(win)
+                    y, feat = detector.net(xt)
+                text = y[0, :, :, 0].numpy().copy()
+                link = y[0, :, :, 1].numpy().copy()
+                rects = detector.getCoords([text, link], rw, rh)
+                out["craft_win"] = win
+                out["craft_x"] = xt.numpy()
+                out["craft_text"] = text
+                out["craft_link"] = link
+                out["craft_feature"] = feat.numpy().astype(np.float16)
+                out["craft_rects"] = np.array(rects, np.int32).reshape(-1, 4)
+                out["craft_ratio"] = np.array([rw, rh], np.float64)
+                roi = detector.process(win)
+                out["craft_roi_shapes"] = np.array([r.shape[:2] for r in roi], np.int32).reshape(-1, 2)
+                # -- second window with native-resolution maps: identity-resize path (target == canvas)
+                # -- post-processing on synthetic score maps (inputs regenerate from the seed; outputs stored)
+                for seed in (1, 2):
+                    t, l = receipts.score_maps(seed)
+                    boxes, polys = ref_tools.getDetBoxes(t, l, 0.7, 0.4, 0.4, False)
+                    out["maps%d_boxes" % seed] = np.array(boxes, np.float32).reshape(-1, 4, 2)
+                    rr = detector.getCoords([t, l], 1.0, 1.0)
+                    out["maps%d_rects" % seed] = np.array(rr, np.int32).reshape(-1, 4)
+                    from functools import cmp_to_key
+                    srt = sorted(rr, key=cmp_to_key(ref_tools.compare_rects))
+                    out["maps%d_sorted" % seed] = np.array(srt, np.int32).reshape(-1, 4)
+                # -- CTC decode known answers of the reference's own unit test (ocr/test/utils_test.py:37-43)
+                import string
+                conv = ref_tools.CTCLabelConverter(string.ascii_lowercase)
+                out["kat_fifa"] = np.array(conv.decode(torch.IntTensor([6, 9, 6, 1]), torch.IntTensor([4])))
+                out["kat_ea"] = np.array(conv.decode(torch.IntTensor([5, 5, 0, 1]), torch.IntTensor([4])))
+
+            # -- recognizer: config 1 crop + ragged crops
+            crop0 = np.random.default_rng(0).integers(0, 256, (32, 100), dtype=np.uint8)
+            crop_list = [crop0] + receipts.crops(15, seed=3)
+            preds_all, raw_all, conf_all, u8_all = [], [], [], []
+            for g in crop_list:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    raw, preds = recognizer.getPreds(g)
+                    res = {}
+                    try:
+                        raw_p, res = recognizer.process(res, g)
+                    except IndexError:      # reference quirk: [s] at position 0 -> cumprod of an empty tensor
+                        res = {-2.0: "IndexError"}
+                preds_all.append(preds.numpy()[0])
+                raw_all.append(raw[0])
+                conf_all.append([float(k) for k in res.keys()] or [-1.0])
+                from PIL import Image
+                tt = recognizer.transformer(Image.fromarray(g).convert("L"))
+                u8_all.append((tt[0] * 0.5 + 0.5).mul(255).round().to(torch.uint8).numpy())
+            out["crnn_preds"] = np.stack(preds_all)
+            out["crnn_raw"] = np.array(raw_all)
+            out["crnn_conf"] = np.array([c[0] for c in conf_all], np.float32)
+            out["crnn_res_text"] = np.array([str(list(r)) for r in [raw_all]])
+            out["crnn_u8"] = np.stack(u8_all)
+            # intermediate taps of the reference network for layer-wise parity (first two crops)
+            with torch.no_grad():
+                xb = torch.cat([recognizer.transformer(Image.fromarray(g).convert("L")).unsqueeze(0)
+                                for g in crop_list[:2]], 0)
+                tr = recognizer.net.Transformation(xb)
+                vf = recognizer.net.FeatureExtraction(tr)
+            out["crnn_rectified"] = tr.numpy()
+            out["crnn_visual"] = vf.numpy().astype(np.float32)
+
+            if head == "CTC":
+                # -- end to end: getText on one full receipt through the reference pipeline (pipeline.py:65-87)
+                import cv2
+                path = os.path.join(scratch, "receipt1.png")
+                cv2.imwrite(path, receipts.receipt(1))
+                with contextlib.redirect_stdout(io.StringIO()):
+                    res = ref_pipeline.getText(path, detector, recognizer, write=False)
+                out["e2e_text"] = np.array([v[0] for v in res.values()])
+                out["e2e_conf"] = np.array([float(k) for k in res.keys()], np.float32)
+            np.savez_compressed(os.path.join(GOLDEN, "ref_%s.npz" % head.lower()), **out)
+            print(head, {k: getattr(v, "shape", None) for k, v in out.items()})
+        finally:
+            unload_reference(dst, cwd)
+
+
+if __name__ == "__main__":
+    main()
