@@ -81,18 +81,24 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
 
 /* pipeline.py:74-79 + CRNN.getPreds/process (net.py:152-193) for n crops at once.
  *   img[i] : uint8 crop, channels[i] = 3 (BGR, converted like cv2.cvtColor BGR2GRAY) or 1 (gray)
- *   logits : [n][26][num_classes] fp32 (`preds`) or NULL; token_ids [n][26]; text [n][32] NUL-terminated decoded
- *   string (CTC: collapsed; Attention: characters before the first [s], has_eos says whether one was found);
+ *   logits : [n][26][num_classes] fp32 (`preds`) or NULL; token_ids [n][26]; text [n][128] NUL-terminated decoded
+ *   string, stride 128 (CTC: collapsed; Attention: characters before the first [s]; has_eos = 1 found, 0 none, -1 [s]
+ *   first = the reference raises IndexError);
  *   conf   : [n] cumulative product of per-step max softmax probabilities (net.py:190). */
 LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,
                             const int* strides, const int* channels, int n, float* logits, int32_t* token_ids,
                             char* text, int32_t* has_eos, float* conf);
 
-/* Fused throughput path = getText (pipeline.py:65-87) for a batch of images, crops never leave the GPU.
- *   rects come back sorted in the reference's reading order per image. */
-LOCR_API int locr_ocr_batch(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
-                            const int* strides, int n, int max_boxes_total, int32_t* rects, int32_t* box_counts,
-                            char* text, int32_t* has_eos, float* conf);
+/* Second half of the fused throughput path (getText, pipeline.py:65-87): recognises boxes of the images of the LAST
+ * locr_detect call without the pixels leaving the GPU.  The caller sorts the rects in between exactly like the
+ * reference does on the host (sorted(rects, key=cmp_to_key(compare_rects)), net.py:108 - the comparator is not a
+ * consistent order, so the result is defined by CPython's sort and stays in Python).
+ *   image_index[i] : index into the image list passed to locr_detect;  rects[i] = (min_y, min_x, max_y, max_x)
+ *   crops follow numpy slicing image[min_y:max_y, min_x:max_x] (net.py:109-111); an empty crop yields has_eos = -2
+ *   (the reference's cv2.cvtColor raises on it).  resized_u8 (optional): [n][32][100] output of the BICUBIC resize. */
+LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, const int32_t* rects, int n,
+                                  float* logits, int32_t* token_ids, char* text, int32_t* has_eos, float* conf,
+                                  uint8_t* resized_u8);
 
 /* Kernel launches issued by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 LOCR_API int64_t locr_launch_count(const locr_handle* h);
@@ -108,6 +114,24 @@ typedef struct {
  * y [B,OH,OW,y_pitch] fp32.  Inputs are rounded to the 16-bit activation type on the way in. */
 LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
                             const float* residual, float* y);
+
+/* CRAFT forward only: bgr uint8 [B][img_h][img_w][3] packed -> score fp32 [B][H32/2][W32/2][2]. */
+LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score);
+/* CRNN forward + decode on already resized crops: u8 [n][32][100] (output of ResizeNormalize's BICUBIC resize). */
+LOCR_API int locr_debug_crnn(locr_handle* h, const uint8_t* u8, int n, float* logits, int32_t* ids, char* text,
+                             int text_stride, int32_t* has_eos, float* conf);
+/* Named intermediate of the last forward pass as dense fp32 (out may be NULL to query the shape only). */
+LOCR_API int locr_debug_read(locr_handle* h, const char* name, float* out, int64_t capacity, int64_t* shape,
+                             int* ndim);
+
+/* det_boxes_core + adjustResultCoordinates + getCoords alone, on host score maps [B][H][W][2]; outputs per image with
+ * capacity max_boxes: boxes [B][max_boxes][8], rects [B][max_boxes][4], box_label [B][max_boxes], counts [B][2]
+ * (boxes kept, components found), labels (optional) [B][H][W] like cv2.connectedComponents. */
+LOCR_API int locr_debug_postproc(locr_handle* h, const float* score, int B, int H, int W, double ratio_w,
+                                 double ratio_h, int max_boxes, float* boxes, int32_t* rects, int32_t* box_label,
+                                 int32_t* counts, int32_t* labels);
+/* cv2.resize(src [sh][sw][3], (dw, dh), INTER_LINEAR) alone. */
+LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
 
 /* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);

@@ -73,3 +73,245 @@ def test_conv(x, w, bias=None, residual=None, *, dil=(1, 1), pad=(0, 0), stride_
         residual = np.ascontiguousarray(residual, np.float32)
     _check(lib().locr_test_conv(C.byref(d), _fptr(x), _fptr(w), _fptr(bias), _fptr(residual), _fptr(y)))
     return y
+
+
+class Config(C.Structure):
+    _fields_ = [("device_id", C.c_int), ("act_dtype", C.c_int), ("head", C.c_int), ("num_classes", C.c_int),
+                ("canvas_size", C.c_int), ("mag_ratio", C.c_float), ("text_threshold", C.c_float),
+                ("link_threshold", C.c_float), ("low_text", C.c_float)]
+
+
+MODEL_CRAFT, MODEL_CRNN = 0, 1
+HEAD_CTC, HEAD_ATTN = 0, 1
+ACT_F16, ACT_BF16 = 0, 1
+TEXT_STRIDE = 128
+
+
+def _bind_engine(L):
+    if getattr(L, "_engine_bound", False):
+        return
+    vp = C.c_void_p
+    L.locr_create.restype = C.c_int
+    L.locr_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.locr_destroy.restype = None
+    L.locr_destroy.argtypes = [vp]
+    L.locr_load_tensor.restype = C.c_int
+    L.locr_load_tensor.argtypes = [vp, C.c_int, C.c_char_p, vp, C.POINTER(C.c_int64), C.c_int]
+    L.locr_finalize.restype = C.c_int
+    L.locr_finalize.argtypes = [vp, C.c_int]
+    L.locr_launch_count.restype = C.c_int64
+    L.locr_launch_count.argtypes = [vp]
+    L.locr_debug_craft_scores.restype = C.c_int
+    L.locr_debug_craft_scores.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.locr_debug_crnn.restype = C.c_int
+    L.locr_debug_crnn.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp]
+    L.locr_debug_read.restype = C.c_int
+    L.locr_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    L._engine_bound = True
+
+
+class Engine:
+    """One liblocr handle = one GPU.  Weights go in as a {name: array-like fp32} mapping with reference key names."""
+
+    def __init__(self, device_id=0, act_dtype=ACT_BF16, head="CTC", num_classes=None, canvas_size=1280,
+                 mag_ratio=1.5, text_threshold=0.7, link_threshold=0.4, low_text=0.4):
+        self.L = lib()
+        _bind_engine(self.L)
+        self.head = HEAD_CTC if head == "CTC" else HEAD_ATTN
+        self.num_classes = num_classes or (37 if self.head == HEAD_CTC else 38)
+        cfg = Config(device_id, act_dtype, self.head, self.num_classes, canvas_size, mag_ratio, text_threshold,
+                     link_threshold, low_text)
+        self.h = C.c_void_p()
+        _check(self.L.locr_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.locr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, model, state_dict):
+        for key, val in state_dict.items():
+            a = val.detach().cpu().numpy() if hasattr(val, "detach") else np.asarray(val)
+            if a.dtype.kind not in "fiu" or key.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(a, np.float32)
+            shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+            _check(self.L.locr_load_tensor(self.h, model, key.encode(), _fptr(a), shape, a.ndim), self.h)
+        _check(self.L.locr_finalize(self.h, model), self.h)
+
+    def launch_count(self):
+        return int(self.L.locr_launch_count(self.h))
+
+    def craft_scores(self, images):
+        """images: uint8 [B,H,W,3] BGR (same size) -> fp32 [B,H32/2,W32/2,2]."""
+        images = np.ascontiguousarray(images, np.uint8)
+        B, H, W, _ = images.shape
+        H32, W32 = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+        out = np.empty((B, H32 // 2, W32 // 2, 2), np.float32)
+        _check(self.L.locr_debug_craft_scores(self.h, _fptr(images), B, H, W, _fptr(out)), self.h)
+        return out
+
+    def crnn_on_resized(self, u8):
+        """u8: uint8 [n,32,100] -> dict(logits, ids, text, has_eos, conf)."""
+        u8 = np.ascontiguousarray(u8, np.uint8)
+        n = u8.shape[0]
+        logits = np.empty((n, 26, self.num_classes), np.float32)
+        ids = np.empty((n, 26), np.int32)
+        text = np.zeros((n, TEXT_STRIDE), np.uint8)
+        eos = np.empty(n, np.int32)
+        conf = np.empty(n, np.float32)
+        _check(self.L.locr_debug_crnn(self.h, _fptr(u8), n, _fptr(logits), _fptr(ids), _fptr(text), TEXT_STRIDE,
+                                      _fptr(eos), _fptr(conf)), self.h)
+        strings = [bytes(row).split(b"\0", 1)[0].decode("ascii") for row in text]
+        return dict(logits=logits, ids=ids, text=strings, has_eos=eos, conf=conf)
+
+    def debug_read(self, name):
+        shape = (C.c_int64 * 8)()
+        nd = C.c_int()
+        _check(self.L.locr_debug_read(self.h, name.encode(), None, 0, shape, C.byref(nd)), self.h)
+        shp = tuple(int(shape[i]) for i in range(nd.value))
+        out = np.empty(shp, np.float32)
+        _check(self.L.locr_debug_read(self.h, name.encode(), _fptr(out), out.size, shape, C.byref(nd)), self.h)
+        return out
+
+
+def _bind_pipeline(L):
+    if getattr(L, "_pipeline_bound", False):
+        return
+    vp = C.c_void_p
+    L.locr_detect.restype = C.c_int
+    L.locr_detect.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.locr_recognize.restype = C.c_int
+    L.locr_recognize.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.locr_recognize_boxes.restype = C.c_int
+    L.locr_recognize_boxes.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.locr_debug_postproc.restype = C.c_int
+    L.locr_debug_postproc.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, vp,
+                                      vp, vp]
+    L.locr_debug_resize.restype = C.c_int
+    L.locr_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+    L._pipeline_bound = True
+
+
+def _ptr_array(arrays):
+    return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+
+def _int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _texts(buf):
+    return [bytes(row).split(b"\0", 1)[0].decode("ascii") for row in buf]
+
+
+class Pipeline(Engine):
+    """Engine + the product entry points (locr_detect / locr_recognize / locr_recognize_boxes)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        _bind_pipeline(self.L)
+
+    def detect(self, images, max_boxes_total=None, want_boxes=False, want_scores=False):
+        """images: list of uint8 BGR HxWx3 arrays.  Returns (rects list per image, boxes per image or None,
+        score maps per image or None); rects are [min_y, min_x, max_y, max_x] in label order (unsorted)."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        cap = max_boxes_total or 4096 * n
+        rects = np.empty((cap, 4), np.int32)
+        boxes = np.empty((cap, 4, 2), np.float32) if want_boxes else None
+        counts = np.zeros(n, np.int32)
+        scores = None
+        sizes = []
+        if want_scores:
+            total = 0
+            for im in imgs:
+                h, w = im.shape[:2]
+                mx = max(h, w)
+                target = min(1.5 * mx, 1280)
+                ratio = target / mx
+                th, tw = int(h * ratio), int(w * ratio)
+                h32 = th if th % 32 == 0 else th + (32 - th % 32)
+                w32 = tw if tw % 32 == 0 else tw + (32 - tw % 32)
+                sizes.append((h32 // 2, w32 // 2))
+                total += (h32 // 2) * (w32 // 2) * 2
+            scores = np.empty(total, np.float32)
+        _check(self.L.locr_detect(self.h, _ptr_array(imgs), _int_array([i.shape[0] for i in imgs]),
+                                  _int_array([i.shape[1] for i in imgs]), None, n, cap, _fptr(rects), _fptr(boxes),
+                                  _fptr(counts), _fptr(scores)), self.h)
+        out_r, out_b, out_s = [], [], []
+        base = 0
+        sbase = 0
+        for i in range(n):
+            k = int(counts[i])
+            out_r.append(rects[base:base + k].copy())
+            if want_boxes:
+                out_b.append(boxes[base:base + k].copy())
+            if want_scores:
+                mh, mw = sizes[i]
+                out_s.append(scores[sbase:sbase + mh * mw * 2].reshape(mh, mw, 2).copy())
+                sbase += mh * mw * 2
+            base += k
+        return out_r, (out_b if want_boxes else None), (out_s if want_scores else None)
+
+    def _outputs(self, n, want_logits):
+        return dict(logits=np.empty((n, 26, self.num_classes), np.float32) if want_logits else None,
+                    ids=np.empty((n, 26), np.int32), text=np.zeros((n, TEXT_STRIDE), np.uint8),
+                    has_eos=np.empty(n, np.int32), conf=np.empty(n, np.float32))
+
+    def recognize(self, crops, want_logits=True):
+        """crops: list of uint8 arrays, HxW (gray) or HxWx3 (BGR)."""
+        cs = [np.ascontiguousarray(c, np.uint8) for c in crops]
+        n = len(cs)
+        o = self._outputs(n, want_logits)
+        ch = [1 if c.ndim == 2 else c.shape[2] for c in cs]
+        _check(self.L.locr_recognize(self.h, _ptr_array(cs), _int_array([c.shape[0] for c in cs]),
+                                     _int_array([c.shape[1] for c in cs]), None, _int_array(ch), n,
+                                     _fptr(o["logits"]), _fptr(o["ids"]), _fptr(o["text"]), _fptr(o["has_eos"]),
+                                     _fptr(o["conf"])), self.h)
+        o["text"] = _texts(o["text"])
+        return o
+
+    def recognize_boxes(self, image_index, rects, want_logits=False, want_u8=False):
+        idx = np.ascontiguousarray(image_index, np.int32)
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        n = len(idx)
+        o = self._outputs(n, want_logits)
+        u8 = np.empty((n, 32, 100), np.uint8) if want_u8 else None
+        _check(self.L.locr_recognize_boxes(self.h, _fptr(idx), _fptr(r), n, _fptr(o["logits"]), _fptr(o["ids"]),
+                                           _fptr(o["text"]), _fptr(o["has_eos"]), _fptr(o["conf"]), _fptr(u8)),
+               self.h)
+        o["text"] = _texts(o["text"])
+        o["u8"] = u8
+        return o
+
+    def postproc(self, score, ratio_w=1.0, ratio_h=1.0, max_boxes=4096, want_labels=True):
+        """score: fp32 [B,H,W,2] -> per image (boxes [k,4,2], rects [k,4], box labels [k], n components, labels)."""
+        score = np.ascontiguousarray(score, np.float32)
+        B, H, W, _ = score.shape
+        boxes = np.empty((B, max_boxes, 4, 2), np.float32)
+        rects = np.empty((B, max_boxes, 4), np.int32)
+        lab = np.empty((B, max_boxes), np.int32)
+        counts = np.empty((B, 2), np.int32)
+        labels = np.empty((B, H, W), np.int32) if want_labels else None
+        _check(self.L.locr_debug_postproc(self.h, _fptr(score), B, H, W, ratio_w, ratio_h, max_boxes, _fptr(boxes),
+                                          _fptr(rects), _fptr(lab), _fptr(counts), _fptr(labels)), self.h)
+        out = []
+        for b in range(B):
+            k = int(counts[b, 0])
+            out.append(dict(boxes=boxes[b, :k].copy(), rects=rects[b, :k].copy(), box_label=lab[b, :k].copy(),
+                            n_components=int(counts[b, 1]), labels=None if labels is None else labels[b]))
+        return out
+
+    def resize_linear(self, img, out_w, out_h):
+        img = np.ascontiguousarray(img, np.uint8)
+        out = np.empty((out_h, out_w, 3), np.uint8)
+        _check(self.L.locr_debug_resize(self.h, _fptr(img), img.shape[0], img.shape[1], _fptr(out), out_h, out_w),
+               self.h)
+        return out

@@ -1,0 +1,538 @@
+#include "engine.cuh"
+
+#include <math.h>
+
+namespace locr {
+
+namespace {
+
+const char* kLoc = "Transformation.LocalizationNetwork.";
+const char* kFe = "FeatureExtraction.ConvNet.";
+
+const HostTensor* find(locr_handle* h, int model, const std::string& key) {
+    auto it = h->host[model].find(key);
+    return it == h->host[model].end() ? nullptr : &it->second;
+}
+
+template <typename T>
+T* dev_upload(locr_handle* h, const std::vector<T>& v) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, v.size() * sizeof(T) + 16) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    h->owned.push_back(p);
+    return reinterpret_cast<T*>(p);
+}
+
+// Conv (+ optional BatchNorm, eval mode, eps 1e-5) -> weights with the BN scale folded in and a single fp32 bias.
+int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct) {
+    const HostTensor* w = find(h, model, prefix + ".weight");
+    if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
+        return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
+    const int cout = (int)w->shape[0], cin = (int)w->shape[1];
+    const int kh = w->shape.size() == 4 ? (int)w->shape[2] : 1, kw = w->shape.size() == 4 ? (int)w->shape[3] : 1;
+    const HostTensor* b = find(h, model, prefix + ".bias");
+    std::vector<double> scale(cout, 1.0), shift(cout, 0.0);
+    for (int n = 0; n < cout; ++n) shift[n] = b ? (double)b->data[n] : 0.0;
+    if (!bn.empty()) {
+        const HostTensor* g = find(h, model, bn + ".weight");
+        const HostTensor* be = find(h, model, bn + ".bias");
+        const HostTensor* mu = find(h, model, bn + ".running_mean");
+        const HostTensor* var = find(h, model, bn + ".running_var");
+        if (!g || !be || !mu || !var || g->numel() != cout)
+            return h->fail(LOCR_ERR_STATE, "missing BatchNorm tensors for " + bn);
+        for (int n = 0; n < cout; ++n) {
+            const double s = (double)g->data[n] / sqrt((double)var->data[n] + 1e-5);
+            scale[n] = s;
+            shift[n] = (shift[n] - (double)mu->data[n]) * s + (double)be->data[n];
+        }
+    }
+    ConvW cw;
+    cw.cin = cin; cw.cout = cout; cw.kh = kh; cw.kw = kw;
+    cw.cout_pad = (cout + 15) / 16 * 16;
+    std::vector<float> bias(cw.cout_pad, 0.f);
+    for (int n = 0; n < cout; ++n) bias[n] = (float)shift[n];
+    cw.bias = dev_upload(h, bias);
+    const int taps = kh * kw;
+    if (direct) {
+        std::vector<float> w32((size_t)taps * cin * cout);
+        for (int n = 0; n < cout; ++n)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < taps; ++t)
+                    w32[((size_t)t * cin + c) * cout + n] = (float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]);
+        cw.w32 = dev_upload(h, w32);
+        if (!cw.w32) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+    } else {
+        if (cin % 16 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": Cin must be a multiple of 16");
+        std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * cin, 0);
+        for (int n = 0; n < cout; ++n)
+            for (int c = 0; c < cin; ++c)
+                for (int t = 0; t < taps; ++t)
+                    w16[((size_t)n * taps + t) * cin + c] =
+                        f32_to_act((float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]), h->cfg.act_dtype);
+        cw.w = dev_upload(h, w16);
+        if (!cw.w) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+    }
+    if (!cw.bias) return h->fail(LOCR_ERR_CUDA, "bias upload failed");
+    h->conv[prefix] = cw;
+    return LOCR_OK;
+}
+
+float* upload_f32(locr_handle* h, const std::string& name, const std::vector<float>& v) {
+    float* p = dev_upload(h, v);
+    h->f32[name] = p;
+    return p;
+}
+
+// [rows][cols] row-major -> [cols][rows]
+std::vector<float> transpose(const std::vector<float>& a, int rows, int cols) {
+    std::vector<float> t((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = a[(size_t)r * cols + c];
+    return t;
+}
+
+void dbg(locr_handle* h, const std::string& name, const void* p, int kind, std::vector<int64_t> shape, long pitch) {
+    DebugTensor d;
+    d.p = p; d.kind = kind; d.shape = std::move(shape); d.pitch = pitch;
+    h->dbg[name] = d;
+}
+
+struct Ctx {
+    locr_handle* h;
+    int rc = LOCR_OK;
+    // y = act(conv(x)) through the tensor-core kernel.  Shapes are those of the INPUT; returns output dims.
+    void tc(const std::string& layer, const void* x, int B, int H, int W, long x_pitch, void* y, long y_pitch, int relu,
+            int pad_h, int pad_w, int dil = 1, int stride_h = 1, int out_fp32 = 0, const void* res = nullptr,
+            long res_pitch = 0) {
+        if (rc != LOCR_OK) return;
+        auto it = h->conv.find(layer);
+        if (it == h->conv.end() || it->second.w == nullptr) {
+            rc = h->fail(LOCR_ERR_STATE, "layer not finalized: " + layer);
+            return;
+        }
+        const ConvW& cw = it->second;
+        ConvCall c;
+        c.x = x; c.B = B; c.H = H; c.W = W; c.Cin = cw.cin; c.x_pitch = x_pitch;
+        c.w = cw.w; c.Cout = cw.cout; c.Cout_pad = cw.cout_pad;
+        c.KH = cw.kh; c.KW = cw.kw; c.dil_h = dil; c.dil_w = dil; c.pad_h = pad_h; c.pad_w = pad_w;
+        c.stride_h = stride_h;
+        c.OH = (H + 2 * pad_h - dil * (cw.kh - 1) - 1) / stride_h + 1;
+        c.OW = (W + 2 * pad_w - dil * (cw.kw - 1) - 1) + 1;
+        c.y = y; c.y_pitch = y_pitch; c.out_fp32 = out_fp32;
+        c.bias = cw.bias; c.residual = res; c.res_pitch = res_pitch; c.relu = relu;
+        c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
+        char err[256] = {0};
+        cudaError_t e = conv_tc_launch(c, h->stream, err, sizeof(err));
+        h->launches++;
+        if (e != cudaSuccess) rc = h->fail(LOCR_ERR_CUDA, layer + ": " + err);
+    }
+    void* buf(const std::string& name, size_t bytes) {
+        void* p = engine_buffer(h, name, bytes);
+        if (p == nullptr && rc == LOCR_OK) rc = h->fail(LOCR_ERR_CUDA, "device allocation failed for " + name);
+        return p;
+    }
+};
+
+}  // namespace
+
+void* engine_buffer(locr_handle* h, const std::string& name, size_t bytes) {
+    auto& e = h->buffers[name];
+    if (e.first != nullptr && e.second >= bytes) return e.first;
+    if (e.first != nullptr) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(e.first);
+        e.first = nullptr;
+    }
+    const size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&e.first, want) != cudaSuccess) {
+        e.first = nullptr;
+        e.second = 0;
+        return nullptr;
+    }
+    e.second = want;
+    return e.first;
+}
+
+// ------------------------------------------------------------------------------------------------ CRAFT
+static const char* kCraftBn[][2] = {
+    {"basenet.slice1.3", "basenet.slice1.4"},   {"basenet.slice1.7", "basenet.slice1.8"},
+    {"basenet.slice1.10", "basenet.slice1.11"}, {"basenet.slice2.14", "basenet.slice2.15"},
+    {"basenet.slice2.17", "basenet.slice2.18"}, {"basenet.slice3.20", "basenet.slice3.21"},
+    {"basenet.slice3.24", "basenet.slice3.25"}, {"basenet.slice3.27", "basenet.slice3.28"},
+    {"basenet.slice4.30", "basenet.slice4.31"}, {"basenet.slice4.34", "basenet.slice4.35"},
+    {"basenet.slice4.37", "basenet.slice4.38"}, {"basenet.slice5.1", ""},
+    {"basenet.slice5.2", ""},                   {"upconv1.conv.0", "upconv1.conv.1"},
+    {"upconv1.conv.3", "upconv1.conv.4"},       {"upconv2.conv.0", "upconv2.conv.1"},
+    {"upconv2.conv.3", "upconv2.conv.4"},       {"upconv3.conv.0", "upconv3.conv.1"},
+    {"upconv3.conv.3", "upconv3.conv.4"},       {"upconv4.conv.0", "upconv4.conv.1"},
+    {"upconv4.conv.3", "upconv4.conv.4"},       {"conv_cls.0", ""},
+    {"conv_cls.2", ""},                         {"conv_cls.4", ""},
+    {"conv_cls.6", ""},                         {"conv_cls.8", ""},
+};
+
+int engine_finalize_craft(locr_handle* h) {
+    int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", true);
+    if (rc != LOCR_OK) return rc;
+    for (auto& e : kCraftBn) {
+        rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false);
+        if (rc != LOCR_OK) return rc;
+    }
+    h->host[LOCR_MODEL_CRAFT].clear();
+    h->ready[LOCR_MODEL_CRAFT] = true;
+    return LOCR_OK;
+}
+
+// VGG_UNet.forward (reference ocr/model.py:39-61) over vgg16_bn.forward (ocr/modules/vgg_bn.py:69-82).
+// Concatenations never materialise: producers write straight into channel slices of the concat buffers.
+int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img_h, int img_w, int H, int W,
+                         float** score) {
+    if (!h->ready[LOCR_MODEL_CRAFT]) return h->fail(LOCR_ERR_STATE, "CRAFT weights not finalized");
+    if (H % 32 != 0 || W % 32 != 0 || img_h > H || img_w > W) return h->fail(LOCR_ERR_INVALID, "bad canvas size");
+    Ctx c{h};
+    const int f16 = h->is_f16();
+    cudaStream_t s = h->stream;
+    const size_t px = (size_t)B * H * W;
+    void* a0 = c.buf("a0", px * 64 * 2);
+    void* a1 = c.buf("a1", px * 64 * 2);
+    void* p1 = c.buf("p1", px / 4 * 64 * 2);
+    void* a2 = c.buf("a2", px / 4 * 128 * 2);
+    uint16_t* cat4 = (uint16_t*)c.buf("cat4", px / 4 * 192 * 2);
+    void* p2 = c.buf("p2", px / 16 * 128 * 2);
+    void* a3 = c.buf("a3", px / 16 * 256 * 2);
+    uint16_t* cat3 = (uint16_t*)c.buf("cat3", px / 16 * 384 * 2);
+    void* a4 = c.buf("a4", px / 16 * 256 * 2);
+    void* p3 = c.buf("p3", px / 64 * 256 * 2);
+    void* a5 = c.buf("a5", px / 64 * 512 * 2);
+    uint16_t* cat2 = (uint16_t*)c.buf("cat2", px / 64 * 768 * 2);
+    void* a6 = c.buf("a6", px / 64 * 512 * 2);
+    void* p4 = c.buf("p4", px / 256 * 512 * 2);
+    void* a7 = c.buf("a7", px / 256 * 512 * 2);
+    uint16_t* cat1 = (uint16_t*)c.buf("cat1", px / 256 * 1536 * 2);
+    void* p5 = c.buf("p5", px / 256 * 512 * 2);
+    void* a8 = c.buf("a8", px / 256 * 1024 * 2);
+    void* u1a = c.buf("u1a", px / 256 * 512 * 2);
+    void* y1 = c.buf("y1", px / 256 * 256 * 2);
+    void* u2a = c.buf("u2a", px / 64 * 256 * 2);
+    void* y2 = c.buf("y2", px / 64 * 128 * 2);
+    void* u3a = c.buf("u3a", px / 16 * 128 * 2);
+    void* y3 = c.buf("y3", px / 16 * 64 * 2);
+    void* u4a = c.buf("u4a", px / 4 * 64 * 2);
+    void* feat = c.buf("feature", px / 4 * 32 * 2);
+    void* c0 = c.buf("c0", px / 4 * 32 * 2);
+    void* c2 = c.buf("c2", px / 4 * 32 * 2);
+    void* c4 = c.buf("c4", px / 4 * 16 * 2);
+    void* c6 = c.buf("c6", px / 4 * 16 * 2);
+    float* sc = (float*)c.buf("score", px / 4 * 2 * 4);
+    if (c.rc != LOCR_OK) return c.rc;
+    const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
+
+    const ConvW& first = h->conv["basenet.slice1.0"];
+    launch_direct_conv3x3(d_images, 1, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, first.w32,
+                          first.bias, 3, 64, a0, 64, 1, f16, s);
+    h->launches++;
+    c.tc("basenet.slice1.3", a0, B, H, W, 64, a1, 64, 1, 1, 1);
+    launch_maxpool(a1, 64, B, H, W, 64, p1, 64, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc("basenet.slice1.7", p1, B, H2, W2, 64, a2, 128, 1, 1, 1);
+    // relu2_2: the reference's slice ends on the BN, the next slice's in-place ReLU rectifies the tap as well
+    c.tc("basenet.slice1.10", a2, B, H2, W2, 128, cat4 + 64, 192, 1, 1, 1);
+    launch_maxpool(cat4 + 64, 192, B, H2, W2, 128, p2, 128, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc("basenet.slice2.14", p2, B, H4, W4, 128, a3, 256, 1, 1, 1);
+    c.tc("basenet.slice2.17", a3, B, H4, W4, 256, cat3 + 128, 384, 1, 1, 1);               // relu3_2
+    c.tc("basenet.slice3.20", cat3 + 128, B, H4, W4, 384, a4, 256, 1, 1, 1);
+    launch_maxpool(a4, 256, B, H4, W4, 256, p3, 256, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc("basenet.slice3.24", p3, B, H8, W8, 256, a5, 512, 1, 1, 1);
+    c.tc("basenet.slice3.27", a5, B, H8, W8, 512, cat2 + 256, 768, 1, 1, 1);               // relu4_3
+    c.tc("basenet.slice4.30", cat2 + 256, B, H8, W8, 768, a6, 512, 1, 1, 1);
+    launch_maxpool(a6, 512, B, H8, W8, 512, p4, 512, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc("basenet.slice4.34", p4, B, H16, W16, 512, a7, 512, 1, 1, 1);
+    // relu5_3 keeps its negatives: slice5 starts with a non-in-place max-pool (vgg_bn.py:54)
+    c.tc("basenet.slice4.37", a7, B, H16, W16, 512, cat1 + 1024, 1536, 0, 1, 1);
+    launch_maxpool(cat1 + 1024, 1536, B, H16, W16, 512, p5, 512, 3, 3, 1, 1, 1, 1, f16, s);
+    c.tc("basenet.slice5.1", p5, B, H16, W16, 512, a8, 1024, 0, 6, 6, 6);
+    c.tc("basenet.slice5.2", a8, B, H16, W16, 1024, cat1, 1536, 0, 0, 0);                  // fc7
+    c.tc("upconv1.conv.0", cat1, B, H16, W16, 1536, u1a, 512, 1, 0, 0);
+    c.tc("upconv1.conv.3", u1a, B, H16, W16, 512, y1, 256, 1, 1, 1);
+    launch_upsample2x(y1, 256, B, H16, W16, 256, cat2, 768, f16, s);
+    c.tc("upconv2.conv.0", cat2, B, H8, W8, 768, u2a, 256, 1, 0, 0);
+    c.tc("upconv2.conv.3", u2a, B, H8, W8, 256, y2, 128, 1, 1, 1);
+    launch_upsample2x(y2, 128, B, H8, W8, 128, cat3, 384, f16, s);
+    c.tc("upconv3.conv.0", cat3, B, H4, W4, 384, u3a, 128, 1, 0, 0);
+    c.tc("upconv3.conv.3", u3a, B, H4, W4, 128, y3, 64, 1, 1, 1);
+    launch_upsample2x(y3, 64, B, H4, W4, 64, cat4, 192, f16, s);
+    c.tc("upconv4.conv.0", cat4, B, H2, W2, 192, u4a, 64, 1, 0, 0);
+    c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat, 32, 1, 1, 1);
+    c.tc("conv_cls.0", feat, B, H2, W2, 32, c0, 32, 1, 1, 1);
+    c.tc("conv_cls.2", c0, B, H2, W2, 32, c2, 32, 1, 1, 1);
+    c.tc("conv_cls.4", c2, B, H2, W2, 32, c4, 16, 1, 1, 1);
+    c.tc("conv_cls.6", c4, B, H2, W2, 16, c6, 16, 1, 0, 0);
+    c.tc("conv_cls.8", c6, B, H2, W2, 16, sc, 2, 0, 0, 0, 1, 1, /*out_fp32=*/1);
+    h->launches += 8;  // 5 max-pools + 3 up-samplings
+    if (c.rc != LOCR_OK) return c.rc;
+    LOCR_CUDA_OK(cudaGetLastError());
+    dbg(h, "slice1.0", a0, 0, {B, H, W, 64}, 64);
+    dbg(h, "relu2_2", cat4 + 64, 0, {B, H2, W2, 128}, 192);
+    dbg(h, "relu3_2", cat3 + 128, 0, {B, H4, W4, 256}, 384);
+    dbg(h, "relu4_3", cat2 + 256, 0, {B, H8, W8, 512}, 768);
+    dbg(h, "relu5_3", cat1 + 1024, 0, {B, H16, W16, 512}, 1536);
+    dbg(h, "fc7", cat1, 0, {B, H16, W16, 1024}, 1536);
+    dbg(h, "feature", feat, 0, {B, H2, W2, 32}, 32);
+    dbg(h, "h16", c6, 0, {B, H2, W2, 16}, 16);
+    dbg(h, "score", sc, 1, {B, H2, W2, 2}, 2);
+    *score = sc;
+    return LOCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CRNN
+int engine_finalize_crnn(locr_handle* h) {
+    const int M = LOCR_MODEL_CRNN;
+    const std::string loc = kLoc, fe = kFe;
+    int rc;
+    auto F = [&](const std::string& p, const std::string& bn, bool direct = false) {
+        return fold_conv(h, M, p, bn, direct);
+    };
+    if ((rc = F(loc + "conv.0", loc + "conv.1", true))) return rc;
+    if ((rc = F(loc + "conv.4", loc + "conv.5"))) return rc;
+    if ((rc = F(loc + "conv.8", loc + "conv.9"))) return rc;
+    if ((rc = F(loc + "conv.12", loc + "conv.13"))) return rc;
+    if ((rc = F(fe + "conv0_1", fe + "bn0_1", true))) return rc;
+    if ((rc = F(fe + "conv0_2", fe + "bn0_2"))) return rc;
+    const int nblocks[5] = {0, 1, 2, 5, 3};
+    for (int l = 1; l <= 4; ++l) {
+        for (int i = 0; i < nblocks[l]; ++i) {
+            const std::string p = fe + "layer" + std::to_string(l) + "." + std::to_string(i) + ".";
+            if ((rc = F(p + "conv1", p + "bn1"))) return rc;
+            if ((rc = F(p + "conv2", p + "bn2"))) return rc;
+            if (find(h, M, p + "downsample.0.weight") != nullptr)
+                if ((rc = F(p + "downsample.0", p + "downsample.1"))) return rc;
+        }
+    }
+    if ((rc = F(fe + "conv1", fe + "bn1"))) return rc;
+    if ((rc = F(fe + "conv2", fe + "bn2"))) return rc;
+    if ((rc = F(fe + "conv3", fe + "bn3"))) return rc;
+    if ((rc = F(fe + "conv4_1", fe + "bn4_1"))) return rc;
+    if ((rc = F(fe + "conv4_2", fe + "bn4_2"))) return rc;
+
+    // localisation FC layers (fp32, transposed for coalesced reads) and the TPS buffers
+    {
+        const HostTensor* w1 = find(h, M, loc + "localization_fc1.0.weight");
+        const HostTensor* b1 = find(h, M, loc + "localization_fc1.0.bias");
+        const HostTensor* w2 = find(h, M, loc + "localization_fc2.weight");
+        const HostTensor* b2 = find(h, M, loc + "localization_fc2.bias");
+        const HostTensor* inv = find(h, M, "Transformation.GridGenerator.inv_delta_C");
+        const HostTensor* ph = find(h, M, "Transformation.GridGenerator.P_hat");
+        if (!w1 || !b1 || !w2 || !b2 || !inv || !ph || w1->numel() != 256 * 512 || w2->numel() != 40 * 256 ||
+            inv->numel() != 23 * 23 || ph->numel() != 3200 * 23)
+            return h->fail(LOCR_ERR_STATE, "missing or malformed TPS tensors");
+        upload_f32(h, "loc.w1t", transpose(w1->data, 256, 512));
+        upload_f32(h, "loc.b1", b1->data);
+        upload_f32(h, "loc.w2t", transpose(w2->data, 40, 256));
+        upload_f32(h, "loc.b2", b2->data);
+        upload_f32(h, "tps.inv", inv->data);
+        upload_f32(h, "tps.phat_t", transpose(ph->data, 3200, 23));
+    }
+    // BiLSTMs: stacked input projections as 1x1 "convs" (N = 2 dirs x 4 gates x 256), recurrent weights transposed
+    for (int l = 0; l < 2; ++l) {
+        const std::string p = "SequenceModeling." + std::to_string(l) + ".rnn.";
+        const HostTensor* wf = find(h, M, p + "weight_ih_l0");
+        const HostTensor* wb = find(h, M, p + "weight_ih_l0_reverse");
+        const HostTensor* hf = find(h, M, p + "weight_hh_l0");
+        const HostTensor* hb = find(h, M, p + "weight_hh_l0_reverse");
+        const HostTensor* bif = find(h, M, p + "bias_ih_l0");
+        const HostTensor* bhf = find(h, M, p + "bias_hh_l0");
+        const HostTensor* bib = find(h, M, p + "bias_ih_l0_reverse");
+        const HostTensor* bhb = find(h, M, p + "bias_hh_l0_reverse");
+        if (!wf || !wb || !hf || !hb || !bif || !bhf || !bib || !bhb) return h->fail(LOCR_ERR_STATE, "missing LSTM tensors");
+        const int nin = (int)wf->shape[1];
+        HostTensor stacked, sbias;
+        stacked.shape = {2048, nin};
+        stacked.data = wf->data;
+        stacked.data.insert(stacked.data.end(), wb->data.begin(), wb->data.end());
+        sbias.shape = {2048};
+        sbias.data.resize(2048);
+        for (int i = 0; i < 1024; ++i) {
+            sbias.data[i] = bif->data[i] + bhf->data[i];
+            sbias.data[1024 + i] = bib->data[i] + bhb->data[i];
+        }
+        const std::string name = "lstm" + std::to_string(l) + ".xproj";
+        h->host[M][name + ".weight"] = stacked;
+        h->host[M][name + ".bias"] = sbias;
+        if ((rc = F(name, ""))) return rc;
+        std::vector<uint16_t> whh((size_t)2 * 256 * 256 * 4);
+        for (int d = 0; d < 2; ++d) {
+            const HostTensor* hh = d == 0 ? hf : hb;
+            for (int k = 0; k < 256; ++k)
+                for (int j = 0; j < 256; ++j)
+                    for (int q = 0; q < 4; ++q)
+                        whh[(((size_t)d * 256 + k) * 256 + j) * 4 + q] =
+                            f32_to_act(hh->data[(size_t)(q * 256 + j) * 256 + k], h->cfg.act_dtype);
+        }
+        h->lstm_whh[l] = dev_upload(h, whh);
+        if ((rc = F("SequenceModeling." + std::to_string(l) + ".linear", ""))) return rc;
+    }
+    if (h->cfg.head == LOCR_HEAD_CTC) {
+        if ((rc = F("Prediction", ""))) return rc;
+        if (h->conv["Prediction"].cout != h->cfg.num_classes) return h->fail(LOCR_ERR_STATE, "num_classes mismatch");
+    } else {
+        const std::string p = "Prediction.attention_cell.";
+        const int C = h->cfg.num_classes;
+        if ((rc = F(p + "i2h", ""))) return rc;
+        const HostTensor* h2h = find(h, M, p + "h2h.weight");
+        const HostTensor* h2hb = find(h, M, p + "h2h.bias");
+        const HostTensor* sw = find(h, M, p + "score.weight");
+        const HostTensor* wih = find(h, M, p + "rnn.weight_ih");
+        const HostTensor* whh = find(h, M, p + "rnn.weight_hh");
+        const HostTensor* bih = find(h, M, p + "rnn.bias_ih");
+        const HostTensor* bhh = find(h, M, p + "rnn.bias_hh");
+        const HostTensor* gw = find(h, M, "Prediction.generator.weight");
+        const HostTensor* gb = find(h, M, "Prediction.generator.bias");
+        if (!h2h || !h2hb || !sw || !wih || !whh || !bih || !bhh || !gw || !gb || wih->shape[1] != 256 + C ||
+            gw->shape[0] != C)
+            return h->fail(LOCR_ERR_STATE, "missing or malformed attention tensors");
+        upload_f32(h, "att.h2h_wt", transpose(h2h->data, 256, 256));
+        upload_f32(h, "att.h2h_b", h2hb->data);
+        upload_f32(h, "att.score", sw->data);
+        const int K = 256 + C;
+        std::vector<float> wih_t((size_t)K * 256 * 4), whh_t((size_t)256 * 256 * 4), gbias(1024);
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < 256; ++j)
+                for (int q = 0; q < 4; ++q) wih_t[((size_t)k * 256 + j) * 4 + q] = wih->data[(size_t)(q * 256 + j) * K + k];
+        for (int k = 0; k < 256; ++k)
+            for (int j = 0; j < 256; ++j)
+                for (int q = 0; q < 4; ++q) whh_t[((size_t)k * 256 + j) * 4 + q] = whh->data[(size_t)(q * 256 + j) * 256 + k];
+        for (int i = 0; i < 1024; ++i) gbias[i] = bih->data[i] + bhh->data[i];
+        upload_f32(h, "att.wih_t", wih_t);
+        upload_f32(h, "att.whh_t", whh_t);
+        upload_f32(h, "att.gate_b", gbias);
+        upload_f32(h, "att.gen_w", gw->data);
+        upload_f32(h, "att.gen_b", gb->data);
+    }
+    for (auto& kv : h->f32)
+        if (kv.second == nullptr) return h->fail(LOCR_ERR_CUDA, "weight upload failed: " + kv.first);
+    h->host[M].clear();
+    h->ready[M] = true;
+    return LOCR_OK;
+}
+
+// CRNNet.forward (reference ocr/model.py:103-118): TPS_STN -> ResNet -> 2x BiLSTM -> CTC / attention head.
+int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits) {
+    if (!h->ready[LOCR_MODEL_CRNN]) return h->fail(LOCR_ERR_STATE, "CRNN weights not finalized");
+    if (B <= 0) return h->fail(LOCR_ERR_INVALID, "empty crop batch");
+    Ctx c{h};
+    const int f16 = h->is_f16();
+    cudaStream_t s = h->stream;
+    const std::string loc = kLoc, fe = kFe;
+    const size_t big = (size_t)B * 32 * 100 * 64 * 2;
+    void* sA = c.buf("crnn.sA", big);
+    void* sB = c.buf("crnn.sB", big);
+    void* sC = c.buf("crnn.sC", big / 2);
+    void* sD = c.buf("crnn.sD", big / 2);
+    float* fid = (float*)c.buf("crnn.fid", (size_t)B * 40 * 4);
+    float* xr = (float*)c.buf("crnn.rectified", (size_t)B * 3200 * 4);
+    float* grid = (float*)c.buf("crnn.grid", (size_t)B * 3200 * 2 * 4);
+    void* vis = c.buf("crnn.visual", (size_t)B * 26 * 512 * 2);
+    float* xproj = (float*)c.buf("crnn.xproj", (size_t)B * 26 * 2048 * 4);
+    void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * 512 * 2);
+    void* s0 = c.buf("crnn.s0", (size_t)B * 26 * 256 * 2);
+    void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * 256 * 2);
+    const int C = h->cfg.num_classes;
+    float* lg = (float*)c.buf("crnn.logits", (size_t)B * 26 * C * 4);
+    if (c.rc != LOCR_OK) return c.rc;
+
+    // ---- TPS localisation network (TPS_STN.py:38-58)
+    const ConvW& l0 = h->conv[loc + "conv.0"];
+    launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 64, 1, f16, s);
+    launch_maxpool(sA, 64, B, 32, 100, 64, sB, 64, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc(loc + "conv.4", sB, B, 16, 50, 64, sA, 128, 1, 1, 1);
+    launch_maxpool(sA, 128, B, 16, 50, 128, sB, 128, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc(loc + "conv.8", sB, B, 8, 25, 128, sA, 256, 1, 1, 1);
+    launch_maxpool(sA, 256, B, 8, 25, 256, sB, 256, 2, 2, 2, 2, 0, 0, f16, s);
+    c.tc(loc + "conv.12", sB, B, 4, 12, 256, sA, 512, 1, 1, 1);
+    launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s);
+    launch_tps_sample(fid, h->f32["tps.inv"], h->f32["tps.phat_t"], d_x, xr, grid, B, s);
+    h->launches += 6;
+
+    // ---- ResNet feature extractor (resnet50v1.py:101-135)
+    const ConvW& r0 = h->conv[fe + "conv0_1"];
+    launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, sA, 32, 1, f16, s);
+    c.tc(fe + "conv0_2", sA, B, 32, 100, 32, sB, 64, 1, 1, 1);
+    launch_maxpool(sB, 64, B, 32, 100, 64, sA, 64, 2, 2, 2, 2, 0, 0, f16, s);
+    h->launches += 2;
+    // x lives in `cur`; BasicBlock (resnet50v1.py:33-48): relu(bn2(conv2(relu(bn1(conv1 x)))) + residual)
+    void* cur = sA;
+    void* other = sB;
+    int Hc = 16, Wc = 50, Cc = 64;
+    const int nblocks[5] = {0, 1, 2, 5, 3};
+    const int planes[5] = {0, 128, 256, 512, 512};
+    for (int l = 1; l <= 4; ++l) {
+        for (int i = 0; i < nblocks[l]; ++i) {
+            const std::string p = fe + "layer" + std::to_string(l) + "." + std::to_string(i) + ".";
+            const int P = planes[l];
+            c.tc(p + "conv1", cur, B, Hc, Wc, Cc, sC, P, 1, 1, 1);
+            const void* res = cur;
+            long res_pitch = Cc;
+            if (h->conv.count(p + "downsample.0")) {
+                c.tc(p + "downsample.0", cur, B, Hc, Wc, Cc, sD, P, 0, 0, 0);
+                res = sD;
+                res_pitch = P;
+            }
+            c.tc(p + "conv2", sC, B, Hc, Wc, P, other, P, 1, 1, 1, 1, 1, 0, res, res_pitch);
+            std::swap(cur, other);
+            Cc = P;
+        }
+        const std::string tail = fe + "conv" + std::to_string(l);
+        if (l <= 3) {
+            c.tc(tail, cur, B, Hc, Wc, Cc, other, Cc, 1, 1, 1);
+            std::swap(cur, other);
+        }
+        if (l == 1 || l == 2) {
+            if (l == 1) {
+                launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 2, 0, 0, f16, s);
+                Hc /= 2; Wc /= 2;
+            } else {
+                launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s);  // k2 s(2,1) p(0,1)
+                Hc = (Hc - 2) / 2 + 1; Wc = Wc + 2 - 2 + 1;
+            }
+            h->launches++;
+            std::swap(cur, other);
+        }
+    }
+    dbg(h, "layer4", cur, 0, {B, Hc, Wc, 512}, 512);
+    c.tc(fe + "conv4_1", cur, B, Hc, Wc, 512, other, 512, 1, 0, 1, 1, 2);                  // k2 s(2,1) p(0,1) -> 2x27
+    c.tc(fe + "conv4_2", other, B, 2, 27, 512, vis, 512, 1, 0, 0);                        // k2 s1 p0     -> 1x26
+
+    // ---- sequence modelling (model.py:107-112; AdaptiveAvgPool over H=1 is the identity) as [B*26, C] GEMMs
+    const int R = B * 26;
+    c.tc("lstm0.xproj", vis, 1, 1, R, 512, xproj, 2048, 0, 0, 0, 1, 1, 1);
+    if (c.rc == LOCR_OK) launch_lstm(xproj, h->lstm_whh[0], hcat, B, 26, f16, s);
+    c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, 256, 0, 0, 0);
+    c.tc("lstm1.xproj", s0, 1, 1, R, 256, xproj, 2048, 0, 0, 0, 1, 1, 1);
+    if (c.rc == LOCR_OK) launch_lstm(xproj, h->lstm_whh[1], hcat, B, 26, f16, s);
+    c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, 256, 0, 0, 0);
+    h->launches += 2;
+    if (h->cfg.head == LOCR_HEAD_CTC) {
+        c.tc("Prediction", s1, 1, 1, R, 256, lg, C, 0, 0, 0, 1, 1, 1);
+    } else {
+        float* fproj = (float*)c.buf("crnn.fproj", (size_t)R * 256 * 4);
+        c.tc("Prediction.attention_cell.i2h", s1, 1, 1, R, 256, fproj, 256, 0, 0, 0, 1, 1, 1);
+        if (c.rc == LOCR_OK) {
+            AttnWeights w;
+            w.h2h_wt = h->f32["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
+            w.wih_t = h->f32["att.wih_t"]; w.whh_t = h->f32["att.whh_t"]; w.gate_b = h->f32["att.gate_b"];
+            w.gen_w = h->f32["att.gen_w"]; w.gen_b = h->f32["att.gen_b"];
+            launch_attention(s1, fproj, w, lg, B, C, f16, s);
+            h->launches++;
+        }
+    }
+    if (c.rc != LOCR_OK) return c.rc;
+    LOCR_CUDA_OK(cudaGetLastError());
+    dbg(h, "fiducials", fid, 1, {B, 20, 2}, 2);
+    dbg(h, "grid", grid, 1, {B, 3200, 2}, 2);
+    dbg(h, "rectified", xr, 1, {B, 32, 100}, 100);
+    dbg(h, "visual", vis, 0, {B, 26, 512}, 512);
+    dbg(h, "contextual", s1, 0, {B, 26, 256}, 256);
+    dbg(h, "logits", lg, 1, {B, 26, C}, C);
+    *logits = lg;
+    return LOCR_OK;
+}
+
+}  // namespace locr

@@ -1,0 +1,85 @@
+// The per-GPU engine behind locr_handle: weight store, BN folding / layout conversion, and the CRAFT and CRNN
+// forward passes expressed as sequences of kernels on one CUDA stream.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "nn_kernels.cuh"
+#include "util.cuh"
+
+namespace locr {
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// One folded convolution / linear layer resident on the device.
+struct ConvW {
+    void* w = nullptr;       // 16-bit [cout_pad][kh][kw][cin] (tensor-core path)
+    float* w32 = nullptr;    // fp32 [kh*kw*cin][cout]         (direct path, tiny cin)
+    float* bias = nullptr;   // fp32 [cout_pad]
+    int cin = 0, cout = 0, cout_pad = 0, kh = 1, kw = 1;
+};
+
+struct DebugTensor {
+    const void* p;
+    int kind;  // 0 = 16-bit activation, 1 = fp32, 2 = int32, 3 = uint8
+    std::vector<int64_t> shape;
+    long pitch;  // elements per innermost row (>= shape.back())
+};
+
+}  // namespace locr
+
+struct ResidentImage {
+    const uint8_t* p;  // device, packed rows of w*3 bytes
+    int h, w;
+};
+
+struct locr_handle {
+    locr_config cfg;
+    std::vector<ResidentImage> resident;  // images of the last locr_detect call (for locr_recognize_boxes)
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    bool ready[2] = {false, false};
+    std::map<std::string, locr::HostTensor> host[2];
+    std::map<std::string, locr::ConvW> conv;
+    std::map<std::string, float*> f32;   // misc fp32 device arrays (TPS buffers, FC weights, attention weights)
+    void* lstm_whh[2] = {nullptr, nullptr};
+    std::map<std::string, std::pair<void*, size_t>> buffers;  // named activation buffers, grown on demand
+    std::map<std::string, locr::DebugTensor> dbg;
+    std::vector<void*> owned;  // weight allocations
+
+    int fail(int code, const std::string& m) {
+        err = m;
+        locr::tls_error() = m;
+        return code;
+    }
+    int is_f16() const { return cfg.act_dtype == LOCR_ACT_F16 ? 1 : 0; }
+};
+
+namespace locr {
+
+int engine_finalize_craft(locr_handle* h);
+int engine_finalize_crnn(locr_handle* h);
+
+// images: device uint8 [B][img_h][img_w][3] (packed rows).  Canvas H x W (multiples of 32, >= image).
+// On success *score points at fp32 [B][H/2][W/2][2].
+int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img_h, int img_w, int H, int W,
+                         float** score);
+
+// x: device fp32 [B][32][100] normalised crops.  On success *logits points at fp32 [B][26][num_classes].
+int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits);
+
+// Named activation buffer (device), at least `bytes` large; contents are undefined after growth.
+void* engine_buffer(locr_handle* h, const std::string& name, size_t bytes);
+
+}  // namespace locr

@@ -1,0 +1,604 @@
+#include "nn_kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace locr {
+
+namespace {
+
+__device__ __forceinline__ float act2f(uint16_t u, int f16) {
+    if (f16) return __half2float(__ushort_as_half(u));
+    return __bfloat162float(__ushort_as_bfloat16(u));
+}
+__device__ __forceinline__ uint16_t f2act(float v, int f16) {
+    if (f16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int f16) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = act2f((uint16_t)(w[i] & 0xffff), f16);
+        f[2 * i + 1] = act2f((uint16_t)(w[i] >> 16), f16);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int f16) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w[i] = (uint32_t)f2act(f[2 * i], f16) | ((uint32_t)f2act(f[2 * i + 1], f16) << 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------- direct conv (tiny Cin)
+template <int CIN, bool U8>
+__global__ void __launch_bounds__(256)
+direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
+                      long img_stride, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                      uint16_t* __restrict__ out, long out_pitch, int relu, int f16) {
+    extern __shared__ float sw[];  // [9*CIN][Cout] then bias[Cout]
+    const int nw = 9 * CIN * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias[i];
+    __syncthreads();
+    const int groups = Cout >> 3;
+    const long total = (long)B * H * W * groups;
+    // ImageNet constants applied in BGR order exactly as the reference does (float32 arithmetic, IEEE division).
+    const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
+    const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
+    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(gid % groups);
+        const long pix = gid / groups;
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long)W * H));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[nw + cg * 8 + j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = x + kx - 1;
+                if (xx < 0 || xx >= W) continue;
+                float v[CIN];
+                if (U8) {
+                    const bool inside = (yy < img_h) && (xx < img_w);
+                    const uint8_t* p =
+                        reinterpret_cast<const uint8_t*>(in) + (long)b * img_stride + (long)yy * row_stride + xx * 3;
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float raw = inside ? (float)p[c] : 0.0f;
+                        v[c] = (raw - mean[c]) / stdv[c];
+                    }
+                } else {
+                    v[0] = reinterpret_cast<const float*>(in)[((long)b * H + yy) * W + xx];
+                }
+                const float* wt = sw + ((ky * 3 + kx) * CIN) * Cout + cg * 8;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[c], wt[c * Cout + j], acc[j]);
+                }
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(acc, f16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- max pool
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C, uint16_t* __restrict__ out,
+               long out_pitch, int OH, int OW, int kh, int kw, int sh, int sw_, int ph, int pw, int f16) {
+    const int groups = C >> 3;
+    const long total = (long)B * OH * OW * groups;
+    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(gid % groups);
+        const long pix = gid / groups;
+        const int ox = (int)(pix % OW);
+        const int oy = (int)((pix / OW) % OH);
+        const int b = (int)(pix / ((long)OW * OH));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int iy = oy * sh + ky - ph;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int ix = ox * sw_ + kx - pw;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 u =
+                    __ldg(reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * in_pitch + cg * 8));
+                float f[8];
+                unpack8(u, f, f16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(m, f16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- bilinear 2x
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C,
+                  uint16_t* __restrict__ out, long out_pitch, int f16) {
+    const int groups = C >> 3;
+    const int OH = 2 * H, OW = 2 * W;
+    const long total = (long)B * OH * OW * groups;
+    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(gid % groups);
+        const long pix = gid / groups;
+        const int ox = (int)(pix % OW);
+        const int oy = (int)((pix / OW) % OH);
+        const int b = (int)(pix / ((long)OW * OH));
+        // PyTorch area_pixel_compute_source_index, align_corners=False, scale 0.5, negative sources clamp to 0
+        float sy = 0.5f * (oy + 0.5f) - 0.5f;
+        float sx = 0.5f * (ox + 0.5f) - 0.5f;
+        if (sy < 0.f) sy = 0.f;
+        if (sx < 0.f) sx = 0.f;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+        const float ly = sy - y0, lx = sx - x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const uint16_t* base = in + (long)b * H * W * in_pitch + cg * 8;
+        float a[8], bq[8], c[8], d[8], r[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * in_pitch)), a, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * in_pitch)), bq, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * in_pitch)), c, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * in_pitch)), d, f16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * c[j] + lx * d[j]);
+        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(r, f16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- TPS localisation head
+__global__ void __launch_bounds__(256)
+loc_head_kernel(const uint16_t* __restrict__ feat, int hw, const float* __restrict__ w1t, const float* __restrict__ b1,
+                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ fid, int f16) {
+    __shared__ float pooled[512];
+    __shared__ float hid[256];
+    const int b = blockIdx.x;
+    const uint16_t* f = feat + (long)b * hw * 512;
+    for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < hw; ++p) s += act2f(f[(long)p * 512 + c], f16);
+        pooled[c] = s / (float)hw;
+    }
+    __syncthreads();
+    {
+        const int j = threadIdx.x;  // 256 threads
+        float s = b1[j];
+        for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], w1t[k * 256 + j], s);
+        hid[j] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < 40) {
+        const int j = threadIdx.x;
+        float s = b2[j];
+        for (int k = 0; k < 256; ++k) s = fmaf(hid[k], w2t[k * 40 + j], s);
+        fid[b * 40 + j] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- TPS grid + sampling
+__global__ void __launch_bounds__(256)
+tps_sample_kernel(const float* __restrict__ fid, const float* __restrict__ inv_delta_c,
+                  const float* __restrict__ p_hat_t, const float* __restrict__ x, float* __restrict__ out,
+                  float* __restrict__ grid, int B) {
+    constexpr int F = 20, F3 = 23, IH = 32, IW = 100, NP = IH * IW;
+    __shared__ float T[F3][2];
+    __shared__ float img[NP];
+    const int b = blockIdx.x;
+    if (threadIdx.x < F3 * 2) {
+        const int i = threadIdx.x >> 1, d = threadIdx.x & 1;
+        float s = 0.f;
+        for (int j = 0; j < F; ++j) s = fmaf(inv_delta_c[i * F3 + j], fid[b * 40 + j * 2 + d], s);
+        T[i][d] = s;  // the three appended zero rows of C' contribute nothing
+    }
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) img[p] = x[(long)b * NP + p];
+    __syncthreads();
+    for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int i = 0; i < F3; ++i) {
+            const float ph = __ldg(&p_hat_t[i * NP + p]);
+            gx = fmaf(ph, T[i][0], gx);
+            gy = fmaf(ph, T[i][1], gy);
+        }
+        if (grid != nullptr) {
+            grid[((long)b * NP + p) * 2] = gx;
+            grid[((long)b * NP + p) * 2 + 1] = gy;
+        }
+        // grid_sampler_2d: align_corners=True un-normalisation, border padding = clip coordinates
+        float ix = ((gx + 1.f) * 0.5f) * (IW - 1);
+        float iy = ((gy + 1.f) * 0.5f) * (IH - 1);
+        ix = fminf(fmaxf(ix, 0.f), (float)(IW - 1));
+        iy = fminf(fmaxf(iy, 0.f), (float)(IH - 1));
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+        const float nw = (x1 - ix) * (y1 - iy), ne = (ix - x0) * (y1 - iy);
+        const float sw_ = (x1 - ix) * (iy - y0), se = (ix - x0) * (iy - y0);
+        float v = 0.f;
+        if (x0 < IW && y0 < IH) v += img[y0 * IW + x0] * nw;
+        if (x1 < IW && y0 < IH) v += img[y0 * IW + x1] * ne;
+        if (x0 < IW && y1 < IH) v += img[y1 * IW + x0] * sw_;
+        if (x1 < IW && y1 < IH) v += img[y1 * IW + x1] * se;
+        out[(long)b * NP + p] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- BiLSTM recurrence
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+constexpr int kLstmG = 8;  // crops per CTA
+
+__global__ void __launch_bounds__(256)
+lstm_kernel(const float* __restrict__ xproj, const uint16_t* __restrict__ whh_t, uint16_t* __restrict__ out, int B,
+            int T, int f16) {
+    __shared__ float hs[kLstmG][256];
+    const int dir = blockIdx.y;
+    const int b0 = blockIdx.x * kLstmG;
+    const int j = threadIdx.x;
+    const uint16_t* wd = whh_t + (size_t)dir * 256 * 256 * 4;
+    float c[kLstmG];
+#pragma unroll
+    for (int g = 0; g < kLstmG; ++g) {
+        c[g] = 0.f;
+        hs[g][j] = 0.f;
+    }
+    __syncthreads();
+    for (int step = 0; step < T; ++step) {
+        const int t = dir == 0 ? step : T - 1 - step;
+        float acc[kLstmG][4];
+#pragma unroll
+        for (int g = 0; g < kLstmG; ++g) {
+            const int b = b0 + g;
+            if (b < B) {
+                const float* xp = xproj + ((long)b * T + t) * 2048 + dir * 1024 + j;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[g][q] = xp[q * 256];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[g][q] = 0.f;
+            }
+        }
+#pragma unroll 4
+        for (int k = 0; k < 256; ++k) {
+            const uint2 wv = __ldg(reinterpret_cast<const uint2*>(wd + ((size_t)k * 256 + j) * 4));
+            const float w0 = act2f((uint16_t)(wv.x & 0xffff), f16), w1 = act2f((uint16_t)(wv.x >> 16), f16);
+            const float w2 = act2f((uint16_t)(wv.y & 0xffff), f16), w3 = act2f((uint16_t)(wv.y >> 16), f16);
+#pragma unroll
+            for (int g = 0; g < kLstmG; ++g) {
+                const float hv = hs[g][k];
+                acc[g][0] = fmaf(w0, hv, acc[g][0]);
+                acc[g][1] = fmaf(w1, hv, acc[g][1]);
+                acc[g][2] = fmaf(w2, hv, acc[g][2]);
+                acc[g][3] = fmaf(w3, hv, acc[g][3]);
+            }
+        }
+        __syncthreads();  // everyone has consumed h_{t-1}
+#pragma unroll
+        for (int g = 0; g < kLstmG; ++g) {
+            const float ig = sigmoidf_(acc[g][0]), fg = sigmoidf_(acc[g][1]);
+            const float gg = tanhf(acc[g][2]), og = sigmoidf_(acc[g][3]);
+            c[g] = fg * c[g] + ig * gg;
+            const float h = og * tanhf(c[g]);
+            hs[g][j] = h;
+            const int b = b0 + g;
+            if (b < B) out[((long)b * T + t) * 512 + dir * 256 + j] = f2act(h, f16);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- attention decoder
+constexpr int kAttG = 4;  // crops per CTA
+constexpr int kAttT = 26;
+
+__global__ void __launch_bounds__(256)
+attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ fproj, AttnWeights w,
+                 float* __restrict__ preds, int B, int C, int f16) {
+    __shared__ float hs[kAttG][256];
+    __shared__ float ctx[kAttG][256];
+    __shared__ float e[kAttG][32];
+    __shared__ float red[kAttG][kAttT][8];
+    __shared__ float logit[kAttG][64];
+    __shared__ int prev[kAttG];
+    const int j = threadIdx.x;
+    const int lane = j & 31, wp = j >> 5;
+    const int b0 = blockIdx.x * kAttG;
+    float c[kAttG];
+#pragma unroll
+    for (int g = 0; g < kAttG; ++g) {
+        c[g] = 0.f;
+        hs[g][j] = 0.f;
+    }
+    if (j < kAttG) prev[j] = 0;  // [GO]
+    __syncthreads();
+    const float sc = w.score_w[j];
+    for (int step = 0; step < kAttT; ++step) {
+        // (a) hp = h2h(h)
+        float hp[kAttG];
+#pragma unroll
+        for (int g = 0; g < kAttG; ++g) hp[g] = w.h2h_b[j];
+        for (int k = 0; k < 256; ++k) {
+            const float wv = __ldg(&w.h2h_wt[k * 256 + j]);
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) hp[g] = fmaf(wv, hs[g][k], hp[g]);
+        }
+        // (b) e[t] = score . tanh(i2h(H)[t] + hp)
+#pragma unroll
+        for (int g = 0; g < kAttG; ++g) {
+            const int b = b0 + g;
+            for (int t = 0; t < kAttT; ++t) {
+                float v = 0.f;
+                if (b < B) v = sc * tanhf(fproj[((long)b * kAttT + t) * 256 + j] + hp[g]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[g][t][wp] = v;
+            }
+        }
+        __syncthreads();
+        if (j < kAttG * 32) {
+            const int g = j >> 5, t = j & 31;
+            float v = -INFINITY;
+            if (t < kAttT) {
+                v = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v += red[g][t][q];
+            }
+            // (c) softmax over the 26 time steps (one warp per crop)
+            float m = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float ex = (t < kAttT) ? expf(v - m) : 0.f;
+            float s = ex;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            e[g][t] = ex / s;
+        }
+        __syncthreads();
+        // (d) context = alpha^T H
+#pragma unroll
+        for (int g = 0; g < kAttG; ++g) {
+            const int b = b0 + g;
+            float v = 0.f;
+            if (b < B) {
+                for (int t = 0; t < kAttT; ++t) v = fmaf(e[g][t], act2f(feats[((long)b * kAttT + t) * 256 + j], f16), v);
+            }
+            ctx[g][j] = v;
+        }
+        __syncthreads();
+        // (e) LSTMCell gates
+        float acc[kAttG][4];
+#pragma unroll
+        for (int g = 0; g < kAttG; ++g) {
+            const float4 oh = __ldg(reinterpret_cast<const float4*>(w.wih_t + ((size_t)(256 + prev[g]) * 256 + j) * 4));
+            acc[g][0] = w.gate_b[j] + oh.x;
+            acc[g][1] = w.gate_b[256 + j] + oh.y;
+            acc[g][2] = w.gate_b[512 + j] + oh.z;
+            acc[g][3] = w.gate_b[768 + j] + oh.w;
+        }
+        for (int k = 0; k < 256; ++k) {
+            const float4 wi = __ldg(reinterpret_cast<const float4*>(w.wih_t + ((size_t)k * 256 + j) * 4));
+            const float4 wh = __ldg(reinterpret_cast<const float4*>(w.whh_t + ((size_t)k * 256 + j) * 4));
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) {
+                const float cv = ctx[g][k], hv = hs[g][k];
+                acc[g][0] = fmaf(wi.x, cv, fmaf(wh.x, hv, acc[g][0]));
+                acc[g][1] = fmaf(wi.y, cv, fmaf(wh.y, hv, acc[g][1]));
+                acc[g][2] = fmaf(wi.z, cv, fmaf(wh.z, hv, acc[g][2]));
+                acc[g][3] = fmaf(wi.w, cv, fmaf(wh.w, hv, acc[g][3]));
+            }
+        }
+        __syncthreads();  // all reads of hs done
+#pragma unroll
+        for (int g = 0; g < kAttG; ++g) {
+            const float ig = sigmoidf_(acc[g][0]), fg = sigmoidf_(acc[g][1]);
+            const float gg = tanhf(acc[g][2]), og = sigmoidf_(acc[g][3]);
+            c[g] = fg * c[g] + ig * gg;
+            hs[g][j] = og * tanhf(c[g]);
+        }
+        __syncthreads();
+        // (g) generator: one warp per class
+        for (int idx = wp; idx < kAttG * C; idx += 8) {
+            const int g = idx / C, v = idx - g * C;
+            float s = 0.f;
+            for (int k = lane; k < 256; k += 32) s = fmaf(__ldg(&w.gen_w[v * 256 + k]), hs[g][k], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) logit[g][v] = s + w.gen_b[v];
+        }
+        __syncthreads();
+        // (h) store + greedy argmax (first maximum wins, like torch.max)
+        for (int idx = j; idx < kAttG * C; idx += 256) {
+            const int g = idx / C, v = idx - g * C;
+            if (b0 + g < B) preds[((long)(b0 + g) * kAttT + step) * C + v] = logit[g][v];
+        }
+        if (j < kAttG) {
+            float best = logit[j][0];
+            int bi = 0;
+            for (int v = 1; v < C; ++v)
+                if (logit[j][v] > best) {
+                    best = logit[j][v];
+                    bi = v;
+                }
+            prev[j] = bi;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------- token decode
+__global__ void __launch_bounds__(128)
+decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int32_t* __restrict__ ids,
+              char* __restrict__ text, int text_stride, int32_t* __restrict__ has_eos, float* __restrict__ conf) {
+    constexpr int T = 26;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* lg = logits + (long)warp * T * C;
+    int my_id = 0;        // lane t keeps the argmax of step t
+    float my_p = 1.f;     // and its softmax probability
+    for (int t = 0; t < T; ++t) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int v = lane; v < C; v += 32) {
+            const float x = lg[t * C + v];
+            if (x > best) {
+                best = x;
+                bi = v;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        float s = 0.f;
+        for (int v = lane; v < C; v += 32) s += expf(lg[t * C + v] - best);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == t) {
+            my_id = bi;
+            my_p = 1.f / s;
+        }
+    }
+    if (lane < T) ids[warp * T + lane] = my_id;
+    // The sequential tail needs values held by other lanes: gather them through shuffles executed by the whole warp.
+    int idv[T];
+    float pv[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        idv[t] = __shfl_sync(0xffffffffu, my_id, t);
+        pv[t] = __shfl_sync(0xffffffffu, my_p, t);
+    }
+    if (lane != 0) return;
+    const char* alphabet = "0123456789abcdefghijklmnopqrstuvwxyz";
+    char* out = text + (long)warp * text_stride;
+    int n = 0;
+    if (!head_attn) {
+        float p = 1.f;
+        for (int t = 0; t < T; ++t) {
+            const int id = idv[t];
+            if (id != 0 && !(t > 0 && idv[t - 1] == id) && n < text_stride - 1) out[n++] = alphabet[id - 1];
+            p *= pv[t];
+        }
+        out[n] = 0;
+        has_eos[warp] = 1;
+        conf[warp] = p;
+    } else {
+        // tokens: 0 = "[GO]", 1 = "[s]", 2.. = alphabet.  The reference cuts string and probabilities at the CHARACTER
+        // index of the first "[s]" (net.py:184-186).
+        int eos_tok = -1;
+        for (int t = 0; t < T; ++t)
+            if (idv[t] == 1) {
+                eos_tok = t;
+                break;
+            }
+        const int upto = eos_tok < 0 ? T : eos_tok;
+        for (int t = 0; t < upto; ++t) {
+            const int id = idv[t];
+            if (id == 0) {
+                const char* go = "[GO]";
+                for (int q = 0; q < 4 && n < text_stride - 1; ++q) out[n++] = go[q];
+            } else if (id >= 2 && n < text_stride - 1) {
+                out[n++] = alphabet[id - 2];
+            }
+        }
+        out[n] = 0;
+        if (eos_tok < 0) {
+            has_eos[warp] = 0;
+            conf[warp] = 0.f;
+        } else if (n == 0) {
+            has_eos[warp] = -1;  // reference: cumprod of an empty tensor, [-1] raises IndexError
+            conf[warp] = 0.f;
+        } else {
+            const int m = n < T ? n : T;  // n = character index of "[s]"
+            float p = 1.f;
+            for (int t = 0; t < m; ++t) p *= pv[t];
+            has_eos[warp] = 1;
+            conf[warp] = p;
+        }
+    }
+}
+
+inline int grid_for(long total, int block) {
+    long g = (total + block - 1) / block;
+    const long cap = 148L * 16;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
+                           long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
+                           long out_pitch, int relu, int is_f16, cudaStream_t s) {
+    const long total = (long)B * H * W * (Cout / 8);
+    const int grid = grid_for(total, 256);
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
+    if (u8_mode)
+        direct_conv3x3_kernel<3, true><<<grid, 256, smem, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride, w,
+                                                               bias, Cout, (uint16_t*)out, out_pitch, relu, is_f16);
+    else
+        direct_conv3x3_kernel<1, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
+                                                                (uint16_t*)out, out_pitch, relu, is_f16);
+}
+
+void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
+                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s) {
+    const int OH = (H + 2 * ph - kh) / sh + 1, OW = (W + 2 * pw - kw) / sw + 1;
+    const long total = (long)B * OH * OW * (C / 8);
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint16_t*)in, in_pitch, B, H, W, C, (uint16_t*)out,
+                                                        out_pitch, OH, OW, kh, kw, sh, sw, ph, pw, is_f16);
+}
+
+void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch,
+                       int is_f16, cudaStream_t s) {
+    const long total = (long)B * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint16_t*)in, in_pitch, B, H, W, C, (uint16_t*)out,
+                                                           out_pitch, is_f16);
+}
+
+void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const float* b1, const float* w2t,
+                     const float* b2, float* fid, int is_f16, cudaStream_t s) {
+    loc_head_kernel<<<B, 256, 0, s>>>((const uint16_t*)feat, hw, w1t, b1, w2t, b2, fid, is_f16);
+}
+
+void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,
+                       float* grid, int B, cudaStream_t s) {
+    tps_sample_kernel<<<B, 256, 0, s>>>(fid, inv_delta_c, p_hat_t, x, out, grid, B);
+}
+
+void launch_lstm(const float* xproj, const void* whh_t, void* out, int B, int T, int is_f16, cudaStream_t s) {
+    dim3 grid((B + kLstmG - 1) / kLstmG, 2);
+    lstm_kernel<<<grid, 256, 0, s>>>(xproj, (const uint16_t*)whh_t, (uint16_t*)out, B, T, is_f16);
+}
+
+void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
+                      cudaStream_t s) {
+    attention_kernel<<<(B + kAttG - 1) / kAttG, 256, 0, s>>>((const uint16_t*)feats, fproj, w, preds, B, C, is_f16);
+}
+
+void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,
+                   int32_t* has_eos, float* conf, cudaStream_t s) {
+    const int warps_per_block = 4;
+    decode_kernel<<<(B + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(logits, B, C, head_attn, ids, text,
+                                                                              text_stride, has_eos, conf);
+}
+
+}  // namespace locr

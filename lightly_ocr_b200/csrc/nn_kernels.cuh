@@ -1,0 +1,63 @@
+// Non-GEMM neural-network kernels of the path (all HBM- or latency-bound): tiny-Cin direct convolution with the
+// CRAFT normalisation fused, max-pool, bilinear 2x up-sampling into concat views, the TPS localisation head, TPS grid
+// generation + grid_sample, the BiLSTM recurrence, the attention decoder and the CTC / attention token decode.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace locr {
+
+// 3x3 / pad 1 convolution for Cin in {1, 3} (reference layers basenet.slice1.0, LocalizationNetwork.conv.0,
+// ConvNet.conv0_1).  w: fp32 [9*Cin][Cout] (BN scale folded), bias fp32 [Cout], out 16-bit NHWC.
+//   u8 mode  : `in` is uint8 BGR [B][img_h][img_w][3] (row stride in bytes); the canvas is H x W, pixels outside the
+//              image but inside the canvas read as 0 and everything is normalised (x - mean)/std on the fly exactly
+//              like normalizeMeanVariance (imgproc.py:19-25) on the zero-padded canvas of resizeAspectRatio (:58-60).
+//   f32 mode : `in` is fp32 [B][H][W] (Cin = 1).
+void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
+                           long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
+                           long out_pitch, int relu, int is_f16, cudaStream_t s);
+
+void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
+                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s);
+
+// F.interpolate(scale 2, bilinear, align_corners=False) of [B,H,W,C] into a [B,2H,2W,*] view (model.py:47,51,55).
+void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch,
+                       int is_f16, cudaStream_t s);
+
+// AdaptiveAvgPool2d(1) + Linear(512,256)+ReLU + Linear(256,40)  (TPS_STN.py:57-60,70-76).
+// feat 16-bit [B][hw][512]; w1t fp32 [512][256]; w2t fp32 [256][40]; fid fp32 [B][40].
+void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const float* b1, const float* w2t,
+                     const float* b2, float* fid, int is_f16, cudaStream_t s);
+
+// build_P_prime + grid_sample(bilinear, border, align_corners=True)  (TPS_STN.py:142-150, :27).
+// inv_delta_c fp32 [23][23]; p_hat_t fp32 [23][3200] (transposed); x, out fp32 [B][32][100]; grid (optional) [B][3200][2].
+void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,
+                       float* grid, int B, cudaStream_t s);
+
+// BiLSTM recurrence (modules/biLSTM.py:18,24): xproj fp32 [B][T][2048] = x W_ih^T + b_ih + b_hh for (dir, gate, unit);
+// whh_t 16-bit [2 dirs][256 k][256 units][4 gates]; out 16-bit [B][T][512] (forward | backward).
+void launch_lstm(const float* xproj, const void* whh_t, void* out, int B, int T, int is_f16, cudaStream_t s);
+
+struct AttnWeights {
+    const float* h2h_wt;   // [256 k][256 j]
+    const float* h2h_b;    // [256]
+    const float* score_w;  // [256]
+    const float* wih_t;    // [256+C k][256 j][4 gates]   (LSTMCell weight_ih, context part then one-hot part)
+    const float* whh_t;    // [256 k][256 j][4 gates]
+    const float* gate_b;   // [4][256]  b_ih + b_hh
+    const float* gen_w;    // [C][256]
+    const float* gen_b;    // [C]
+};
+// Attention.forward inference branch (attention.py:46-59) with B=1 semantics per crop.
+// feats 16-bit [B][26][256] (contextual features), fproj fp32 [B][26][256] (= i2h(feats), hoisted out of the loop),
+// preds fp32 [B][26][C].
+void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
+                      cudaStream_t s);
+
+// Token decode + confidence (net.py:162-167,177-190; recog_utils.py:32-47,113-119).  logits fp32 [B][26][C].
+// ids int32 [B][26]; text char [B][text_stride]; has_eos int32 [B] (CTC: always 1; Attention: 0 when no [s] was
+// produced, -1 when the reference would raise IndexError because [s] is the first character); conf fp32 [B].
+void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,
+                   int32_t* has_eos, float* conf, cudaStream_t s);
+
+}  // namespace locr

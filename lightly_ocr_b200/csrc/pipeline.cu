@@ -1,0 +1,333 @@
+// The product entry points of the C ABI: locr_detect, locr_recognize, locr_recognize_boxes.
+#include <math.h>
+
+#include <algorithm>
+
+#include "engine.cuh"
+#include "imgops.cuh"
+#include "postproc.cuh"
+
+using namespace locr;
+
+namespace {
+
+constexpr int kTextStride = 128;
+constexpr int kMaxChunk = 8;  // images per CRAFT forward (activations: ~0.6 GB per 1280x960 image)
+
+struct Pinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~Pinned() { if (p) cudaFreeHost(p); }
+    void* get(size_t n) {
+        if (n <= cap) return p;
+        if (p) cudaFreeHost(p);
+        cap = n + n / 4 + 4096;
+        if (cudaMallocHost(&p, cap) != cudaSuccess) { p = nullptr; cap = 0; }
+        return p;
+    }
+};
+
+// Per-thread pinned staging (one host thread drives one handle).
+Pinned& staging(int which) {
+    static thread_local Pinned s[4];
+    return s[which];
+}
+
+// resizeAspectRatio's size arithmetic (reference ocr/tools/imgproc.py:38-57), Python float semantics.
+void craft_geometry(const locr_config& cfg, int h, int w, int* th, int* tw, int* H32, int* W32, double* ratio) {
+    const int mx = h > w ? h : w;
+    double target = (double)cfg.mag_ratio * mx;
+    if (target > cfg.canvas_size) target = cfg.canvas_size;
+    *ratio = target / mx;
+    *th = (int)(h * *ratio);
+    *tw = (int)(w * *ratio);
+    *H32 = *th % 32 ? *th + (32 - *th % 32) : *th;
+    *W32 = *tw % 32 ? *tw + (32 - *tw % 32) : *tw;
+}
+
+int run_crnn_and_decode(locr_handle* h, const float* d_x, int n, float* logits, int32_t* ids, char* text,
+                        int32_t* has_eos, float* conf) {
+    float* lg = nullptr;
+    int rc = engine_crnn_forward(h, d_x, n, &lg);
+    if (rc != LOCR_OK) return rc;
+    const int C = h->cfg.num_classes;
+    int32_t* d_ids = (int32_t*)engine_buffer(h, "dec.ids", (size_t)n * 26 * 4);
+    char* d_text = (char*)engine_buffer(h, "dec.text", (size_t)n * kTextStride);
+    int32_t* d_eos = (int32_t*)engine_buffer(h, "dec.eos", (size_t)n * 4);
+    float* d_conf = (float*)engine_buffer(h, "dec.conf", (size_t)n * 4);
+    if (!d_ids || !d_text || !d_eos || !d_conf) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    launch_decode(lg, n, C, h->cfg.head == LOCR_HEAD_ATTN, d_ids, d_text, kTextStride, d_eos, d_conf, h->stream);
+    h->launches++;
+    LOCR_CUDA_OK(cudaGetLastError());
+    cudaStream_t s = h->stream;
+    if (logits) LOCR_CUDA_OK(cudaMemcpyAsync(logits, lg, (size_t)n * 26 * C * 4, cudaMemcpyDeviceToHost, s));
+    if (ids) LOCR_CUDA_OK(cudaMemcpyAsync(ids, d_ids, (size_t)n * 26 * 4, cudaMemcpyDeviceToHost, s));
+    if (text) LOCR_CUDA_OK(cudaMemcpyAsync(text, d_text, (size_t)n * kTextStride, cudaMemcpyDeviceToHost, s));
+    if (has_eos) LOCR_CUDA_OK(cudaMemcpyAsync(has_eos, d_eos, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (conf) LOCR_CUDA_OK(cudaMemcpyAsync(conf, d_conf, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    return LOCR_OK;
+}
+
+// Uploads crop descriptors, runs crop -> gray -> bicubic -> normalise, then the recogniser.
+int run_crops(locr_handle* h, std::vector<CropDesc>& descs, float* logits, int32_t* ids, char* text,
+              int32_t* has_eos, float* conf, uint8_t* resized_u8) {
+    const int n = (int)descs.size();
+    long coef_total = 0, inter_total = 0;
+    for (auto& d : descs) {
+        long ci, ib;
+        crop_scratch_sizes(d.h, d.w, &d.ksh, &d.ksv, &ci, &ib);
+        d.coef_off = coef_total;
+        d.inter_off = inter_total;
+        coef_total += ci;
+        inter_total += ib;
+    }
+    CropDesc* d_desc = (CropDesc*)engine_buffer(h, "crop.desc", (size_t)n * sizeof(CropDesc));
+    int32_t* d_coef = (int32_t*)engine_buffer(h, "crop.coef", (size_t)coef_total * 4);
+    uint8_t* d_inter = (uint8_t*)engine_buffer(h, "crop.inter", (size_t)inter_total + 16);
+    float* d_x = (float*)engine_buffer(h, "crnn.x", (size_t)n * 3200 * 4);
+    uint8_t* d_u8 = (uint8_t*)engine_buffer(h, "crop.u8", (size_t)n * 3200);
+    if (!d_desc || !d_coef || !d_inter || !d_x || !d_u8) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    void* hd = staging(2).get((size_t)n * sizeof(CropDesc));
+    if (!hd) return h->fail(LOCR_ERR_CUDA, "pinned allocation failed");
+    memcpy(hd, descs.data(), (size_t)n * sizeof(CropDesc));
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_desc, hd, (size_t)n * sizeof(CropDesc), cudaMemcpyHostToDevice, h->stream));
+    launch_crop_resize(d_desc, n, d_coef, d_inter, d_x, d_u8, h->stream);
+    h->launches++;
+    {
+        DebugTensor dt;
+        dt.p = d_u8; dt.kind = 3; dt.shape = {n, 32, 100}; dt.pitch = 100;
+        h->dbg["crop_u8"] = dt;
+    }
+    LOCR_CUDA_OK(cudaGetLastError());
+    if (resized_u8)
+        LOCR_CUDA_OK(cudaMemcpyAsync(resized_u8, d_u8, (size_t)n * 3200, cudaMemcpyDeviceToHost, h->stream));
+    return run_crnn_and_decode(h, d_x, n, logits, ids, text, has_eos, conf);
+}
+
+}  // namespace
+
+extern "C" {
+
+LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
+                         const int* strides, int n, int max_boxes_total, int32_t* rects, float* boxes,
+                         int32_t* box_counts, float* score_maps) {
+    if (h == nullptr || bgr == nullptr || heights == nullptr || widths == nullptr || n <= 0 || rects == nullptr ||
+        box_counts == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_detect: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    cudaStream_t s = h->stream;
+    // all images stay resident (packed) for a following locr_recognize_boxes
+    size_t total_bytes = 0;
+    std::vector<size_t> img_off(n);
+    for (int i = 0; i < n; ++i) {
+        if (heights[i] <= 0 || widths[i] <= 0 || bgr[i] == nullptr) return h->fail(LOCR_ERR_INVALID, "locr_detect: empty image");
+        img_off[i] = total_bytes;
+        total_bytes += (size_t)heights[i] * widths[i] * 3;
+    }
+    uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
+    uint8_t* h_img = (uint8_t*)staging(0).get(total_bytes);
+    if (!d_img || !h_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
+    for (int i = 0; i < n; ++i) {
+        const size_t row = (size_t)widths[i] * 3;
+        const size_t st = strides ? (size_t)strides[i] : row;
+        for (int y = 0; y < heights[i]; ++y) memcpy(h_img + img_off[i] + y * row, bgr[i] + y * st, row);
+    }
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_img, h_img, total_bytes, cudaMemcpyHostToDevice, s));
+    h->resident.clear();
+    for (int i = 0; i < n; ++i) h->resident.push_back({d_img + img_off[i], heights[i], widths[i]});
+
+    int out_base = 0;
+    size_t score_base = 0;
+    int i0 = 0;
+    while (i0 < n) {
+        int i1 = i0 + 1;
+        while (i1 < n && i1 - i0 < kMaxChunk && heights[i1] == heights[i0] && widths[i1] == widths[i0] &&
+               img_off[i1] - img_off[i1 - 1] == (size_t)heights[i0] * widths[i0] * 3)
+            ++i1;
+        const int B = i1 - i0, ih = heights[i0], iw = widths[i0];
+        int th, tw, H32, W32;
+        double ratio;
+        craft_geometry(h->cfg, ih, iw, &th, &tw, &H32, &W32, &ratio);
+        if (th <= 0 || tw <= 0) return h->fail(LOCR_ERR_INVALID, "locr_detect: image too small");
+        const uint8_t* src = d_img + img_off[i0];
+        if (th != ih || tw != iw) {
+            uint8_t* d_rs = (uint8_t*)engine_buffer(h, "resized", (size_t)B * th * tw * 3);
+            if (!d_rs) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+            launch_resize_linear_bgr(src, B, ih, iw, d_rs, th, tw, s);
+            h->launches++;
+            src = d_rs;
+        }
+        float* sc = nullptr;
+        int rc = engine_craft_forward(h, src, B, th, tw, H32, W32, &sc);
+        if (rc != LOCR_OK) return rc;
+        const int mh = H32 / 2, mw = W32 / 2;
+        const int cap = 4096;
+        void* ws = engine_buffer(h, "pp.ws", postproc_workspace_bytes(B, mh, mw));
+        float* d_boxes = (float*)engine_buffer(h, "pp.boxes", (size_t)B * cap * 8 * 4);
+        int32_t* d_rects = (int32_t*)engine_buffer(h, "pp.rects", (size_t)B * cap * 4 * 4);
+        int32_t* d_lab = (int32_t*)engine_buffer(h, "pp.lab", (size_t)B * cap * 4);
+        int32_t* d_counts = (int32_t*)engine_buffer(h, "pp.counts", (size_t)B * 2 * 4);
+        if (!ws || !d_boxes || !d_rects || !d_lab || !d_counts) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+        PostprocParams pp;
+        pp.B = B; pp.H = mh; pp.W = mw;
+        pp.low_text = h->cfg.low_text; pp.link_threshold = h->cfg.link_threshold;
+        pp.text_threshold = h->cfg.text_threshold;
+        const double inv = 1.0 / ratio;  // ratio_w = ratio_h = 1 / target_ratio (net.py:75)
+        pp.scale_x = inv * 2;
+        pp.scale_y = inv * 2;
+        pp.max_boxes = cap;
+        const int nl = launch_postproc(sc, pp, ws, d_boxes, d_rects, d_lab, d_counts, nullptr, s);
+        if (nl < 0) return h->fail(LOCR_ERR_INVALID, "locr_detect: score map larger than 1024 x 1024");
+        h->launches += nl;
+        LOCR_CUDA_OK(cudaGetLastError());
+        int32_t counts[kMaxChunk * 2];
+        LOCR_CUDA_OK(cudaMemcpyAsync(counts, d_counts, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost, s));
+        LOCR_CUDA_OK(cudaStreamSynchronize(s));
+        for (int b = 0; b < B; ++b) {
+            if (counts[b * 2 + 1] >= 65535) return h->fail(LOCR_ERR_CAPACITY, "locr_detect: more than 65534 components");
+            const int k = counts[b * 2] < cap ? counts[b * 2] : cap;
+            if (out_base + k > max_boxes_total) return h->fail(LOCR_ERR_CAPACITY, "locr_detect: max_boxes_total too small");
+            LOCR_CUDA_OK(cudaMemcpyAsync(rects + (size_t)out_base * 4, d_rects + (size_t)b * cap * 4, (size_t)k * 16,
+                                         cudaMemcpyDeviceToHost, s));
+            if (boxes)
+                LOCR_CUDA_OK(cudaMemcpyAsync(boxes + (size_t)out_base * 8, d_boxes + (size_t)b * cap * 8,
+                                             (size_t)k * 32, cudaMemcpyDeviceToHost, s));
+            box_counts[i0 + b] = k;
+            out_base += k;
+        }
+        if (score_maps) {
+            const size_t cnt = (size_t)B * mh * mw * 2;
+            LOCR_CUDA_OK(cudaMemcpyAsync(score_maps + score_base, sc, cnt * 4, cudaMemcpyDeviceToHost, s));
+            score_base += cnt;
+        }
+        LOCR_CUDA_OK(cudaStreamSynchronize(s));
+        i0 = i1;
+    }
+    return LOCR_OK;
+}
+
+LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,
+                            const int* strides, const int* channels, int n, float* logits, int32_t* token_ids,
+                            char* text, int32_t* has_eos, float* conf) {
+    if (h == nullptr || img == nullptr || heights == nullptr || widths == nullptr || n <= 0)
+        return fail(LOCR_ERR_INVALID, "locr_recognize: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    size_t total = 0;
+    std::vector<size_t> off(n);
+    for (int i = 0; i < n; ++i) {
+        const int ch = channels ? channels[i] : 1;
+        if (ch != 1 && ch != 3) return h->fail(LOCR_ERR_INVALID, "locr_recognize: channels must be 1 or 3");
+        if (heights[i] <= 0 || widths[i] <= 0)
+            return h->fail(LOCR_ERR_INVALID, "locr_recognize: empty crop (the reference's cv2.cvtColor raises here)");
+        off[i] = total;
+        total += ((size_t)heights[i] * widths[i] * ch + 15) / 16 * 16;
+    }
+    uint8_t* d_buf = (uint8_t*)engine_buffer(h, "crop.src", total);
+    uint8_t* h_buf = (uint8_t*)staging(1).get(total);
+    if (!d_buf || !h_buf) return h->fail(LOCR_ERR_CUDA, "crop buffer allocation failed");
+    std::vector<CropDesc> descs(n);
+    for (int i = 0; i < n; ++i) {
+        const int ch = channels ? channels[i] : 1;
+        const size_t row = (size_t)widths[i] * ch;
+        const size_t st = strides ? (size_t)strides[i] : row;
+        for (int y = 0; y < heights[i]; ++y) memcpy(h_buf + off[i] + y * row, img[i] + y * st, row);
+        CropDesc& d = descs[i];
+        d.src = d_buf + off[i];
+        d.stride = (long)row;
+        d.h = heights[i];
+        d.w = widths[i];
+        d.channels = ch;
+    }
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_buf, h_buf, total, cudaMemcpyHostToDevice, h->stream));
+    return run_crops(h, descs, logits, token_ids, text, has_eos, conf, nullptr);
+}
+
+LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, const int32_t* rects, int n,
+                                  float* logits, int32_t* token_ids, char* text, int32_t* has_eos, float* conf,
+                                  uint8_t* resized_u8) {
+    if (h == nullptr || image_index == nullptr || rects == nullptr || n <= 0)
+        return fail(LOCR_ERR_INVALID, "locr_recognize_boxes: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    std::vector<CropDesc> descs(n);
+    auto py_slice = [](int start, int stop, int size, int* s0, int* len) {  // a[start:stop] for ints, step 1
+        int a = start < 0 ? std::max(start + size, 0) : std::min(start, size);
+        int b = stop < 0 ? std::max(stop + size, 0) : std::min(stop, size);
+        *s0 = a;
+        *len = b > a ? b - a : 0;
+    };
+    for (int i = 0; i < n; ++i) {
+        const int ii = image_index[i];
+        if (ii < 0 || ii >= (int)h->resident.size())
+            return h->fail(LOCR_ERR_STATE, "locr_recognize_boxes: image index not resident (call locr_detect first)");
+        const auto& im = h->resident[ii];
+        int y0, hh, x0, ww;
+        // sub = image[min_y:max_y, min_x:max_x, :]  (net.py:109-111, numpy slice semantics)
+        py_slice(rects[i * 4 + 0], rects[i * 4 + 2], im.h, &y0, &hh);
+        py_slice(rects[i * 4 + 1], rects[i * 4 + 3], im.w, &x0, &ww);
+        CropDesc& d = descs[i];
+        d.stride = (long)im.w * 3;
+        d.src = im.p + (size_t)y0 * d.stride + (size_t)x0 * 3;
+        d.h = (hh > 0 && ww > 0) ? hh : 0;
+        d.w = (hh > 0 && ww > 0) ? ww : 0;
+        d.channels = 3;
+    }
+    int rc = run_crops(h, descs, logits, token_ids, text, has_eos, conf, resized_u8);
+    if (rc != LOCR_OK) return rc;
+    if (has_eos)
+        for (int i = 0; i < n; ++i)
+            if (descs[i].h == 0) has_eos[i] = -2;  // empty crop: the reference's cv2.cvtColor would raise
+    return LOCR_OK;
+}
+
+/* Post-processing only, on host score maps [B][H][W][2] (tests: bit-exact parity with det_boxes_core). */
+LOCR_API int locr_debug_postproc(locr_handle* h, const float* score, int B, int H, int W, double ratio_w,
+                                 double ratio_h, int max_boxes, float* boxes, int32_t* rects, int32_t* box_label,
+                                 int32_t* counts, int32_t* labels) {
+    if (h == nullptr || score == nullptr || B <= 0) return fail(LOCR_ERR_INVALID, "bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    cudaStream_t s = h->stream;
+    const size_t npix = (size_t)B * H * W;
+    float* d_sc = (float*)engine_buffer(h, "score", npix * 2 * 4);
+    void* ws = engine_buffer(h, "pp.ws", postproc_workspace_bytes(B, H, W));
+    float* d_boxes = (float*)engine_buffer(h, "pp.boxes", (size_t)B * max_boxes * 8 * 4);
+    int32_t* d_rects = (int32_t*)engine_buffer(h, "pp.rects", (size_t)B * max_boxes * 4 * 4);
+    int32_t* d_lab = (int32_t*)engine_buffer(h, "pp.lab", (size_t)B * max_boxes * 4);
+    int32_t* d_counts = (int32_t*)engine_buffer(h, "pp.counts", (size_t)B * 2 * 4);
+    int32_t* d_labels = labels ? (int32_t*)engine_buffer(h, "pp.labels", npix * 4) : nullptr;
+    if (!d_sc || !ws || !d_boxes || !d_rects || !d_lab || !d_counts || (labels && !d_labels))
+        return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_sc, score, npix * 8, cudaMemcpyHostToDevice, s));
+    PostprocParams pp;
+    pp.B = B; pp.H = H; pp.W = W;
+    pp.low_text = h->cfg.low_text; pp.link_threshold = h->cfg.link_threshold; pp.text_threshold = h->cfg.text_threshold;
+    pp.scale_x = ratio_w * 2; pp.scale_y = ratio_h * 2; pp.max_boxes = max_boxes;
+    const int nl = launch_postproc(d_sc, pp, ws, d_boxes, d_rects, d_lab, d_counts, d_labels, s);
+    if (nl < 0) return h->fail(LOCR_ERR_INVALID, "score map larger than 1024 x 1024");
+    h->launches += nl;
+    LOCR_CUDA_OK(cudaGetLastError());
+    LOCR_CUDA_OK(cudaMemcpyAsync(boxes, d_boxes, (size_t)B * max_boxes * 32, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(rects, d_rects, (size_t)B * max_boxes * 16, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(box_label, d_lab, (size_t)B * max_boxes * 4, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(counts, d_counts, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (labels) LOCR_CUDA_OK(cudaMemcpyAsync(labels, d_labels, npix * 4, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    return LOCR_OK;
+}
+
+/* cv2.resize(INTER_LINEAR) alone (tests). */
+LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw) {
+    if (h == nullptr || src == nullptr || dst == nullptr) return fail(LOCR_ERR_INVALID, "bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    uint8_t* d_s = (uint8_t*)engine_buffer(h, "images", (size_t)sh * sw * 3);
+    uint8_t* d_d = (uint8_t*)engine_buffer(h, "resized", (size_t)dh * dw * 3);
+    if (!d_s || !d_d) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_s, src, (size_t)sh * sw * 3, cudaMemcpyHostToDevice, h->stream));
+    launch_resize_linear_bgr(d_s, 1, sh, sw, d_d, dh, dw, h->stream);
+    h->launches++;
+    LOCR_CUDA_OK(cudaMemcpyAsync(dst, d_d, (size_t)dh * dw * 3, cudaMemcpyDeviceToHost, h->stream));
+    LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return LOCR_OK;
+}
+
+}  // extern "C"

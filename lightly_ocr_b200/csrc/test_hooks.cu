@@ -22,10 +22,6 @@ using namespace locr;
 extern "C" {
 
 LOCR_API const char* locr_version(void) { return "liblocr 0.1 (sm_100a)"; }
-LOCR_API const char* locr_last_error(const locr_handle* h) {
-    (void)h;
-    return tls_error().c_str();
-}
 
 LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
                             const float* residual, float* y) {

