@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Throughput of the detect-then-recognize path (BASELINE.json metric: end-to-end receipts/sec at 1280 px,
+CRAFT + CRNN, 1/2/4/8 B200; crops/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the whole path (CRAFT forward, thresholds + labelling + boxes, host reading-order sort, GPU
+crops + BICUBIC, CRNN forward, CTC decode) over a batch of RECEIPTS_PER_STEP distinct synthetic 1280x960 receipts per
+GPU (weak scaling: per-GPU work is fixed).  `value` times the path with the receipts already resident in HBM;
+`e2e` times the same path through the C ABI with host buffers (host->device copy of the images and device->host copy
+of rects, strings and confidences inside the timed region).  Receipts are independent units: no collective on the
+data path, torch.distributed only provides the barrier and the max-over-ranks reduction of the elapsed time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RECEIPTS_PER_STEP = 16
+POOL = 32                      # distinct receipts cycled through (118 MB of pixels)
+METRIC = "receipts_per_sec_1280px_craft_crnn_ctc"
+UNIT = "receipts/s"
+CRAFT_FLOPS = 874.217e9        # per 1280x960 canvas
+CRNN_FLOPS_PER_CROP = 10.593e9
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_receipts(rank, count):
+    from lightly_ocr_b200.synth import receipts
+    return [receipts.receipt(1000 * rank + i) for i in range(count)]
+
+
+def cpu_oracle_sample(n_threads):
+    """The oracle (CPU port of the reference path, torch fp32 + cv2 + PIL) on a bounded sample: one quarter receipt
+    (640x480 window of receipt 0, ~20 words).  Returns (seconds, crops)."""
+    import numpy as np
+    import torch
+    from lightly_ocr_b200.synth import receipts
+    from oracle import ocr_ref, weights
+    torch.set_num_threads(n_threads)
+    craft_sd, crnn_sd = weights.craft_calibrated(0, ink=True), weights.crnn_calibrated(1, "CTC")
+    img = np.ascontiguousarray(receipts.receipt(0)[:640, :480])
+    t0 = time.perf_counter()
+    res = ocr_ref.get_text(craft_sd, crnn_sd, img, "CTC")
+    return time.perf_counter() - t0, len(res), (craft_sd, crnn_sd, img)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference cannot travel to
+    the GPU box) on the box's host cores, all threads, one quarter receipt per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ocr_ref
+    cores = os.cpu_count() or 1
+    _, _, (craft_sd, crnn_sd, img) = cpu_oracle_sample(cores)          # also serves as first warm-up
+    for _ in range(max(args.warmup - 1, 0)):
+        ocr_ref.get_text(craft_sd, crnn_sd, img, "CTC")
+    t0 = time.perf_counter()
+    crops = 0
+    for _ in range(args.steps):
+        crops += len(ocr_ref.get_text(craft_sd, crnn_sd, img, "CTC"))
+    dt = time.perf_counter() - t0
+    value = 0.25 * args.steps / dt
+    sample = "one 640x480 window (1/4 of a 1280x960 receipt, ~%d crops) per step" % (crops // max(args.steps, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "end-to-end CRAFT+CRNN(CTC) over synthetic 1280x960 receipts (BASELINE config 4)",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "crops_per_sec": crops / dt}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lightly_ocr_b200 import bridge, shard
+    from lightly_ocr_b200.synth import weights
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    runner = bridge.OcrRunner(device_id=local_rank, act_dtype=bridge.ACT_F16, head="CTC")
+    runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
+    runner.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, "CTC"))
+    pool = make_receipts(rank, POOL)
+    batches = [pool[i:i + RECEIPTS_PER_STEP] for i in range(0, POOL, RECEIPTS_PER_STEP)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- e2e: host buffers in, host results out, every step
+    for w in range(max(args.warmup, 3)):
+        runner.ocr(batches[w % len(batches)])
+    barrier()
+    launches0 = runner.launch_count()
+    runner.timer_start()
+    t0 = time.perf_counter()
+    crops_e2e = 0
+    d2h = 0
+    for k in range(args.steps):
+        per_image, out = runner.ocr(batches[k % len(batches)])
+        crops_e2e += len(out["text"])
+        d2h += sum(len(r) for r in per_image) * 16 + len(out["text"]) * (26 * 4 + bridge.TEXT_STRIDE + 8)
+    e2e_ms = runner.timer_stop()
+    e2e_wall = time.perf_counter() - t0
+    barrier()
+    e2e_s = shard.max_over_ranks(max(e2e_ms / 1e3, e2e_wall), dev)
+    launches_e2e = runner.launch_count() - launches0
+
+    # ---------------- value: the same path with the step's receipts already resident in HBM
+    runner.ocr(batches[0])                               # leaves batch 0 resident
+    for _ in range(3):
+        runner.ocr_resident(RECEIPTS_PER_STEP)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    runner.profile(True)
+    runner.profile_read()
+    launches0 = runner.launch_count()
+    runner.timer_start()
+    t0 = time.perf_counter()
+    crops = 0
+    for k in range(args.steps):
+        _, out = runner.ocr_resident(RECEIPTS_PER_STEP)
+        crops += len(out["text"])
+    dev_ms = runner.timer_stop()
+    wall = time.perf_counter() - t0
+    barrier()
+    conv_ms, conv_flops, conv_launches = runner.profile_read()
+    runner.profile(False)
+    clk = clocks.stop() if rank == 0 else None
+    elapsed = shard.max_over_ranks(max(dev_ms / 1e3, wall), dev)
+    launches = runner.launch_count() - launches0
+    total_crops = crops
+    if world > 1:
+        t = torch.tensor([crops, crops_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        total_crops, crops_e2e = int(t[0].item()), int(t[1].item())
+
+    if rank == 0:
+        peak_tf, peak_hbm, which = measured_peaks()
+        receipts_total = world * RECEIPTS_PER_STEP * args.steps
+        value = receipts_total / elapsed
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "end-to-end CRAFT+CRNN(CTC) over synthetic 1280x960 receipts, %d receipts per "
+                                   "step per GPU (BASELINE config 4; ~%d crops per receipt)"
+                                   % (RECEIPTS_PER_STEP, total_crops // max(receipts_total, 1)),
+                       "l2": "inputs + activations per step (~0.6 GB per receipt) far exceed the 126 MB L2",
+                       "weights": "synthetic random-init (lightly_ocr_b200/synth), fp16 storage, fp32 accumulate",
+                       "parallelism": "replicas x%d, receipts sharded, no collective" % world},
+            "crops_per_sec": total_crops / elapsed,
+            "e2e": {"value": world * RECEIPTS_PER_STEP * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(sum(im.nbytes for im in batches[0])),
+                    "d2h_bytes_per_step": int(d2h / max(args.steps, 1)), "crops_per_sec": crops_e2e / e2e_s,
+                    "gpu_launches": launches_e2e},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all layers)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "bf16_tflops_sustained, %s (fp16 and bf16 share the tensor rate)" % which,
+                         "launches": conv_launches, "kernel_ms_per_step": conv_ms / max(args.steps, 1),
+                         "kernel_share_of_step": (conv_ms / 1e3) / (dev_ms / 1e3) if dev_ms > 0 else None,
+                         "algorithmic_flops_per_step": conv_flops / max(args.steps, 1)},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            secs, ncrops, _ = cpu_oracle_sample(cores)
+            line["cpu_baseline"] = {"value": 0.25 / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "one 640x480 window (1/4 receipt, %d crops), oracle/ocr_ref.get_text, "
+                                              "torch fp32 with %d threads + cv2 + PIL, single timed pass after model "
+                                              "build" % (ncrops, cores)}
+        print(json.dumps(line))
+    runner.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,18 @@ LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, co
                                   float* logits, int32_t* token_ids, char* text, int32_t* has_eos, float* conf,
                                   uint8_t* resized_u8);
 
+/* locr_detect on the images left resident on the device by the previous locr_detect call (no host-to-device copy). */
+LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, float* boxes,
+                                  int32_t* box_counts, float* score_maps);
+
+/* CUDA-event timing on the handle's own stream (bench.py; torch.cuda.Event only sees torch's streams). */
+LOCR_API int locr_timer_start(locr_handle* h);
+LOCR_API int locr_timer_stop(locr_handle* h, float* ms);
+/* Per-launch CUDA-event profiling of the tensor-core convolution kernel: enable, run, then read the totals since the
+ * last read (kernel milliseconds, algorithmic FLOPs = 2*M*N*K of the unpadded layers, launches). */
+LOCR_API int locr_profile(locr_handle* h, int enable);
+LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flops, int64_t* conv_launches);
+
 /* Kernel launches issued by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 LOCR_API int64_t locr_launch_count(const locr_handle* h);
 

@@ -315,3 +315,89 @@ class Pipeline(Engine):
         _check(self.L.locr_debug_resize(self.h, _fptr(img), img.shape[0], img.shape[1], _fptr(out), out_h, out_w),
                self.h)
         return out
+
+
+def _bind_bench(L):
+    if getattr(L, "_bench_bound", False):
+        return
+    vp = C.c_void_p
+    L.locr_detect_resident.restype = C.c_int
+    L.locr_detect_resident.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.locr_timer_start.restype = C.c_int
+    L.locr_timer_start.argtypes = [vp]
+    L.locr_timer_stop.restype = C.c_int
+    L.locr_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.locr_profile.restype = C.c_int
+    L.locr_profile.argtypes = [vp, C.c_int]
+    L.locr_profile_read.restype = C.c_int
+    L.locr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L._bench_bound = True
+
+
+class OcrRunner(Pipeline):
+    """getText for batches of receipts (reference ocr/pipeline.py:65-87): detect on the GPU, reading-order sort on the
+    host exactly like the reference, crops + recognition on the GPU.  Used by bench.py and the throughput tests."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        _bind_bench(self.L)
+        self._cap = 0
+
+    def _buffers(self, n):
+        cap = 1024 * n
+        if cap > self._cap:
+            self._rects = np.empty((cap, 4), np.int32)
+            self._counts = np.zeros(max(n, 1), np.int32)
+            self._cap = cap
+        if len(self._counts) < n:
+            self._counts = np.zeros(n, np.int32)
+        return self._rects, self._counts
+
+    def _sort_and_recognize(self, n, rects, counts, want_logits=False):
+        from .hostops import sort_rects
+        idx, srt = [], []
+        base = 0
+        per_image = []
+        for i in range(n):
+            k = int(counts[i])
+            s = sort_rects(rects[base:base + k].tolist())
+            per_image.append(s)
+            srt.extend(s)
+            idx.extend([i] * k)
+            base += k
+        if not srt:
+            return per_image, dict(text=[], conf=np.zeros(0, np.float32), has_eos=np.zeros(0, np.int32))
+        out = self.recognize_boxes(idx, srt, want_logits=want_logits)
+        return per_image, out
+
+    def ocr(self, images, want_logits=False):
+        """Host images in, (sorted rects per image, recognition outputs over all crops) out."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        rects, counts = self._buffers(n)
+        _check(self.L.locr_detect(self.h, _ptr_array(imgs), _int_array([i.shape[0] for i in imgs]),
+                                  _int_array([i.shape[1] for i in imgs]), None, n, self._cap, _fptr(rects), None,
+                                  _fptr(counts), None), self.h)
+        return self._sort_and_recognize(n, rects, counts, want_logits)
+
+    def ocr_resident(self, n, want_logits=False):
+        """Same, on the images the previous ocr()/detect() call left resident in HBM (no host-to-device copy)."""
+        rects, counts = self._buffers(n)
+        _check(self.L.locr_detect_resident(self.h, self._cap, _fptr(rects), None, _fptr(counts), None), self.h)
+        return self._sort_and_recognize(n, rects, counts, want_logits)
+
+    def timer_start(self):
+        _check(self.L.locr_timer_start(self.h), self.h)
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(self.L.locr_timer_stop(self.h, C.byref(ms)), self.h)
+        return float(ms.value)
+
+    def profile(self, enable):
+        _check(self.L.locr_profile(self.h, int(enable)), self.h)
+
+    def profile_read(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(self.L.locr_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)), self.h)
+        return float(ms.value), float(fl.value), int(n.value)

@@ -76,6 +76,52 @@ LOCR_API const char* locr_last_error(const locr_handle* h) {
     return tls_error().c_str();
 }
 
+LOCR_API int locr_timer_start(locr_handle* h) {
+    if (h == nullptr) return fail(LOCR_ERR_INVALID, "null handle");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    if (h->timer0 == nullptr) {
+        LOCR_CUDA_OK(cudaEventCreate(&h->timer0));
+        LOCR_CUDA_OK(cudaEventCreate(&h->timer1));
+    }
+    LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    LOCR_CUDA_OK(cudaEventRecord(h->timer0, h->stream));
+    return LOCR_OK;
+}
+
+LOCR_API int locr_timer_stop(locr_handle* h, float* ms) {
+    if (h == nullptr || ms == nullptr || h->timer0 == nullptr) return fail(LOCR_ERR_INVALID, "timer not started");
+    LOCR_CUDA_OK(cudaEventRecord(h->timer1, h->stream));
+    LOCR_CUDA_OK(cudaEventSynchronize(h->timer1));
+    LOCR_CUDA_OK(cudaEventElapsedTime(ms, h->timer0, h->timer1));
+    return LOCR_OK;
+}
+
+LOCR_API int locr_profile(locr_handle* h, int enable) {
+    if (h == nullptr) return fail(LOCR_ERR_INVALID, "null handle");
+    h->profile = enable != 0;
+    return LOCR_OK;
+}
+
+LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flops, int64_t* conv_launches) {
+    if (h == nullptr) return fail(LOCR_ERR_INVALID, "null handle");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    double ms = 0, fl = 0;
+    for (auto& r : h->prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        ms += t;
+        fl += r.flops;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (conv_ms) *conv_ms = ms;
+    if (conv_flops) *conv_flops = fl;
+    if (conv_launches) *conv_launches = (int64_t)h->prof.size();
+    h->prof.clear();
+    return LOCR_OK;
+}
+
 /* ---- debug / test entry points ---- */
 
 LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score) {

@@ -122,7 +122,18 @@ struct Ctx {
         c.bias = cw.bias; c.residual = res; c.res_pitch = res_pitch; c.relu = relu;
         c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
         char err[256] = {0};
+        locr_handle::ProfRec pr;
+        if (h->profile) {
+            cudaEventCreate(&pr.e0);
+            cudaEventCreate(&pr.e1);
+            pr.flops = 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin * cw.kh * cw.kw;
+            cudaEventRecord(pr.e0, h->stream);
+        }
         cudaError_t e = conv_tc_launch(c, h->stream, err, sizeof(err));
+        if (h->profile) {
+            cudaEventRecord(pr.e1, h->stream);
+            h->prof.push_back(pr);
+        }
         h->launches++;
         if (e != cudaSuccess) rc = h->fail(LOCR_ERR_CUDA, layer + ": " + err);
     }

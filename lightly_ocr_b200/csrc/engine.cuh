@@ -57,6 +57,11 @@ struct locr_handle {
     std::map<std::string, std::pair<void*, size_t>> buffers;  // named activation buffers, grown on demand
     std::map<std::string, locr::DebugTensor> dbg;
     std::vector<void*> owned;  // weight allocations
+    // per-launch profiling of the tensor-core conv kernel (bench.py roofline): event pairs + algorithmic FLOPs
+    bool profile = false;
+    struct ProfRec { cudaEvent_t e0, e1; double flops; };
+    std::vector<ProfRec> prof;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
     int fail(int code, const std::string& m) {
         err = m;

@@ -109,34 +109,18 @@ int run_crops(locr_handle* h, std::vector<CropDesc>& descs, float* logits, int32
 
 extern "C" {
 
-LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
-                         const int* strides, int n, int max_boxes_total, int32_t* rects, float* boxes,
-                         int32_t* box_counts, float* score_maps) {
-    if (h == nullptr || bgr == nullptr || heights == nullptr || widths == nullptr || n <= 0 || rects == nullptr ||
-        box_counts == nullptr)
-        return fail(LOCR_ERR_INVALID, "locr_detect: bad argument");
-    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+static int detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, float* boxes,
+                           int32_t* box_counts, float* score_maps) {
     cudaStream_t s = h->stream;
-    // all images stay resident (packed) for a following locr_recognize_boxes
-    size_t total_bytes = 0;
+    const int n = (int)h->resident.size();
+    std::vector<int> heights(n), widths(n);
     std::vector<size_t> img_off(n);
+    const uint8_t* d_img = n ? h->resident[0].p : nullptr;
     for (int i = 0; i < n; ++i) {
-        if (heights[i] <= 0 || widths[i] <= 0 || bgr[i] == nullptr) return h->fail(LOCR_ERR_INVALID, "locr_detect: empty image");
-        img_off[i] = total_bytes;
-        total_bytes += (size_t)heights[i] * widths[i] * 3;
+        heights[i] = h->resident[i].h;
+        widths[i] = h->resident[i].w;
+        img_off[i] = (size_t)(h->resident[i].p - d_img);
     }
-    uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
-    uint8_t* h_img = (uint8_t*)staging(0).get(total_bytes);
-    if (!d_img || !h_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
-    for (int i = 0; i < n; ++i) {
-        const size_t row = (size_t)widths[i] * 3;
-        const size_t st = strides ? (size_t)strides[i] : row;
-        for (int y = 0; y < heights[i]; ++y) memcpy(h_img + img_off[i] + y * row, bgr[i] + y * st, row);
-    }
-    LOCR_CUDA_OK(cudaMemcpyAsync(d_img, h_img, total_bytes, cudaMemcpyHostToDevice, s));
-    h->resident.clear();
-    for (int i = 0; i < n; ++i) h->resident.push_back({d_img + img_off[i], heights[i], widths[i]});
-
     int out_base = 0;
     size_t score_base = 0;
     int i0 = 0;
@@ -205,6 +189,47 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
         i0 = i1;
     }
     return LOCR_OK;
+}
+
+LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* heights, const int* widths,
+                         const int* strides, int n, int max_boxes_total, int32_t* rects, float* boxes,
+                         int32_t* box_counts, float* score_maps) {
+    if (h == nullptr || bgr == nullptr || heights == nullptr || widths == nullptr || n <= 0 || rects == nullptr ||
+        box_counts == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_detect: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    cudaStream_t s = h->stream;
+    // all images stay resident (packed) for a following locr_recognize_boxes / locr_detect_resident
+    size_t total_bytes = 0;
+    std::vector<size_t> img_off(n);
+    for (int i = 0; i < n; ++i) {
+        if (heights[i] <= 0 || widths[i] <= 0 || bgr[i] == nullptr) return h->fail(LOCR_ERR_INVALID, "locr_detect: empty image");
+        img_off[i] = total_bytes;
+        total_bytes += (size_t)heights[i] * widths[i] * 3;
+    }
+    uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
+    uint8_t* h_img = (uint8_t*)staging(0).get(total_bytes);
+    if (!d_img || !h_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
+    for (int i = 0; i < n; ++i) {
+        const size_t row = (size_t)widths[i] * 3;
+        const size_t st = strides ? (size_t)strides[i] : row;
+        if (st == row) memcpy(h_img + img_off[i], bgr[i], row * heights[i]);
+        else for (int y = 0; y < heights[i]; ++y) memcpy(h_img + img_off[i] + y * row, bgr[i] + y * st, row);
+    }
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_img, h_img, total_bytes, cudaMemcpyHostToDevice, s));
+    h->resident.clear();
+    for (int i = 0; i < n; ++i) h->resident.push_back({d_img + img_off[i], heights[i], widths[i]});
+    return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
+}
+
+/* Detection on the images already resident on the device from the previous locr_detect call (no host-to-device copy):
+ * the HBM-resident variant bench.py times as `value`. */
+LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, float* boxes,
+                                  int32_t* box_counts, float* score_maps) {
+    if (h == nullptr || rects == nullptr || box_counts == nullptr) return fail(LOCR_ERR_INVALID, "bad argument");
+    if (h->resident.empty()) return h->fail(LOCR_ERR_STATE, "locr_detect_resident: no resident images");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
 }
 
 LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,

@@ -1,0 +1,93 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol include/locr.h declares; host logic
+(comparator, converters, sharding over a 2-process gloo group) behaves like the reference's."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lightly_ocr_b200 import build
+    lib = ctypes.CDLL(build.build())
+    header = open(os.path.join(ROOT, "include", "locr.h")).read()
+    names = sorted(set(re.findall(r"LOCR_API[^;(]*?\b(locr_\w+)\s*\(", header)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "include/locr.h declares %s but liblocr.so does not export it" % n
+    lib.locr_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.locr_version()
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lightly_ocr_b200 import bridge
+    with pytest.raises(bridge.LocrError):
+        bridge.Engine()
+
+
+def test_compare_rects_and_sort_match_oracle_restatement():
+    from lightly_ocr_b200 import hostops
+    from oracle import ocr_ref
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(0, 90))
+        rects = []
+        for _ in range(n):
+            y0, x0 = int(rng.integers(0, 600)), int(rng.integers(0, 900))
+            rects.append([y0, x0, y0 + int(rng.integers(1, 60)), x0 + int(rng.integers(1, 200))])
+        assert hostops.sort_rects(rects) == ocr_ref.sort_rects(rects)
+
+
+def test_sorted_rects_match_reference_golden():
+    from lightly_ocr_b200 import hostops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ctc.npz"))
+    for s in (1, 2):
+        assert np.array_equal(np.array(hostops.sort_rects(g["maps%d_rects" % s].tolist()), np.int32),
+                              g["maps%d_sorted" % s])
+
+
+def test_converters_match_reference_known_answers():
+    from lightly_ocr_b200 import hostops
+    conv = hostops.CTCLabelConverter("abcdefghijklmnopqrstuvwxyz")
+    assert conv.decode([6, 9, 6, 1], [4]) == ["fifa"]          # reference ocr/test/utils_test.py:37-39
+    assert conv.decode([5, 5, 0, 1], [4]) == ["ea"]            # :41-43
+    att = hostops.AttnLabelConverter(hostops.ALPHABET)
+    assert att.decode(np.array([[0, 12, 1, 2]]), [25]) == ["[GO]a[s]0"]
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from lightly_ocr_b200 import shard
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["MASTER_PORT"], rank=rank, world_size=world)
+mine = shard.shard_indices(11, rank, world)
+res = shard.gather_in_order([(i, "r%%d" %% i) for i in mine], 11, rank, world)
+t = shard.max_over_ranks(1.0 + rank)
+if rank == 0:
+    assert res == ["r%%d" %% i for i in range(11)], res
+    assert t == float(world), t
+    print("OK")
+dist.barrier()
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_sharding_two_process_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29713")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
