@@ -19,6 +19,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -28,7 +29,7 @@ namespace locr {
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
 constexpr int kTileM = 128;
 
 struct ConvParams {
@@ -47,6 +48,13 @@ struct ConvParams {
     long res_pitch;
     const float* bias;
     int relu, is_f16;
+    // TMA-store epilogue: accumulators -> registers -> swizzled staging tile in smem -> one bulk tensor store
+    int tma_store;      // 0 = direct per-thread global stores (unaligned fp32 outputs)
+    int stage_cols;     // output columns per staging chunk (row bytes stage_rb = stage_cols * elem size: 32/64/128)
+    int stage_rb;
+    int n_chunks;       // n_tile / stage_cols
+    long long* timing;  // experiments only: per-CTA cycle counters [gridDim][8] (null = off)
+    int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
 struct TileCoord {
@@ -88,7 +96,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
 template <int SWZ>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmap_y, const ConvParams p) {
     constexpr int BLOCK_K = SWZ / 2;      // 16-bit elements per swizzled row
     constexpr int MMAS_PER_STAGE = BLOCK_K / 16;
 
@@ -104,6 +112,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     uint64_t* tfull_bar = bars + 2 * kMaxStages;
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);                       // [256]
+    uint8_t* staging = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(bias_s + 256) + 1023) & ~(uintptr_t)1023);                // 2 x [128][stage_rb]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -111,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmap_x);
         ptx::tma_prefetch_desc(&tmap_w);
+        if (p.tma_store) ptx::tma_prefetch_desc(&tmap_y);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -119,7 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 4);
+            ptx::mbar_init(&tempty_bar[a], 8);
         }
         ptx::fence_mbar_init();
     }
@@ -138,6 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)(kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+            long long t_wait = 0, t_begin = clock64();
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 for (int kb = 0; kb < p.num_kblocks; ++kb) {
@@ -145,8 +158,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     const int cc = kb - tap * p.cin_chunks;
                     const int kh = tap / p.KW;
                     const int kw = tap - kh * p.KW;
+                    long long tw0 = p.timing ? clock64() : 0;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    if (p.timing) t_wait += clock64() - tw0;
+                    uint32_t txb = tx_bytes;
+                    if (p.dbg & 2) txb -= (uint32_t)(kTileM * SWZ);
+                    if (p.dbg & 4) txb -= (uint32_t)(p.n_tile * SWZ);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], txb);
                     const int iw0 = t.ow0 + kw * p.dil_w - p.pad_w;
                     int c2, c3;
                     if (p.stride2) {  // input row = 2*oh + kh : dim2 selects kh, dim3 walks oh
@@ -156,15 +174,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         c2 = 0;
                         c3 = t.oh0 + kh * p.dil_h - p.pad_h;
                     }
-                    ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_x, &full_bar[stage],
-                                     cc * BLOCK_K, iw0, c2, c3, t.b0);
-                    ptx::tma_load_2d(smem_b + (size_t)stage * p.b_stage_bytes, &tmap_w, &full_bar[stage],
-                                     kb * BLOCK_K, t.n0);
+                    if (!(p.dbg & 2))
+                        ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_x, &full_bar[stage],
+                                         cc * BLOCK_K, iw0, c2, c3, t.b0);
+                    if (!(p.dbg & 4))
+                        ptx::tma_load_2d(smem_b + (size_t)stage * p.b_stage_bytes, &tmap_w, &full_bar[stage],
+                                         kb * BLOCK_K, t.n0);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
+            }
+            if (p.timing) {
+                p.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
+                p.timing[blockIdx.x * 8 + 1] = t_wait;
             }
         }
     } else if (warp == 1) {
@@ -174,12 +198,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            long long t_wfull = 0, t_wtempty = 0, t_begin = clock64();
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                long long tw0 = p.timing ? clock64() : 0;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 200 + acc);
+                if (p.timing) t_wtempty += clock64() - tw0;
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile_alloc);
                 for (int kb = 0; kb < p.num_kblocks; ++kb) {
+                    long long tw1 = p.timing ? clock64() : 0;
                     ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
+                    if (p.timing) t_wfull += clock64() - tw1;
                     ptx::tc_fence_after();
                     const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
                     const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * p.b_stage_bytes);
@@ -187,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     for (int k = 0; k < MMAS_PER_STAGE; ++k) {
                         const uint64_t da = ptx::make_kmajor_desc(a_addr + k * 32, SWZ);
                         const uint64_t db = ptx::make_kmajor_desc(b_addr + k * 32, SWZ);
-                        ptx::umma_f16(d_tmem, da, db, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (!(p.dbg & 1)) ptx::umma_f16(d_tmem, da, db, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                     if (++stage == p.stages) {
@@ -199,10 +228,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
+            if (p.timing) {
+                p.timing[blockIdx.x * 8 + 2] = clock64() - t_begin;
+                p.timing[blockIdx.x * 8 + 3] = t_wfull;
+                p.timing[blockIdx.x * 8 + 4] = t_wtempty;
+            }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (4 warps, one TMEM lane quarter each)
-        const int ew = warp - 4;
+        // ------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
+        const int ew = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = ew * 32 + lane;
         const int rw = row % p.bw;
         const int rh = (row / p.bw) % p.bh;
@@ -210,6 +245,137 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int chunks = (p.n_tile + 31) / 32;
+        if (p.tma_store) {
+            // 8 epilogue warps: warp (ew, half) owns TMEM lanes [32*ew, +32) and one half of every staging chunk's
+            // columns, so each scheduler overlaps two warps' worth of TMEM loads / conversions / smem stores.
+            const int etid = threadIdx.x - 128;
+            const int cpw = p.stage_cols >> 1;             // columns per warp per chunk: 32, 16 or 8
+            const uint32_t xor_term = ((((uint32_t)row * (uint32_t)p.stage_rb) >> 7) &
+                                       (uint32_t)(p.stage_rb / 16 - 1)) << 4;
+            const uint32_t row_off = (uint32_t)row * (uint32_t)p.stage_rb;
+            uint32_t chunk_ctr = 0;
+            long long t_wtfull = 0, t_begin = clock64();
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const int ow = t.ow0 + rw, oh = t.oh0 + rh, b = t.b0 + rb;
+                const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
+                const long pix = ((long)b * p.OH + oh) * p.OW + ow;
+                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
+                long long tw0 = p.timing ? clock64() : 0;
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                if (p.timing) t_wtfull += clock64() - tw0;
+                ptx::tc_fence_after();
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    uint8_t* sbuf = staging + (size_t)(chunk_ctr & 1u) * 128 * p.stage_rb;
+                    if (etid == 0) ptx::tma_store_wait_read<1>();   // the store that used this buffer two chunks ago
+                    ptx::named_bar_sync(1, 256);                    // ... is done; bias_s of this tile is visible
+                    const int col0 = c * p.stage_cols + half * cpw;  // first column (within the n-tile) of this warp
+                    const uint32_t taddr =
+                        tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile_alloc + col0);
+                    float v[32];
+                    if (cpw == 32) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32(taddr, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    } else if (cpw == 16) {
+                        uint32_t r[16];
+                        ptx::tmem_ld_32x16(taddr, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    } else {
+                        uint32_t r[8];
+                        ptx::tmem_ld_32x8(taddr, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+                    }
+                    if (c == p.n_chunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (q * 4 < cpw) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[col0 + q * 4]);
+                            v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
+                        }
+                    }
+                    if (p.res != nullptr && valid) {
+                        const int nb = t.n0 + col0;
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pitch + nb;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q * 8 < cpw && nb + q * 8 < p.Cout) {
+                                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + q * 8));
+                                const float2 f0 = unpack2(u.x, p.is_f16), f1 = unpack2(u.y, p.is_f16);
+                                const float2 f2 = unpack2(u.z, p.is_f16), f3 = unpack2(u.w, p.is_f16);
+                                v[q * 8 + 0] += f0.x; v[q * 8 + 1] += f0.y;
+                                v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
+                                v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y;
+                                v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    // swizzled staging write: 16-byte piece k of this row lands at (k*16) ^ xor_term
+                    if (p.out_fp32) {
+                        const uint32_t piece0 = (uint32_t)(half * cpw) >> 2;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (q * 4 < cpw) {
+                                uint4 u;
+                                u.x = __float_as_uint(v[q * 4 + 0]); u.y = __float_as_uint(v[q * 4 + 1]);
+                                u.z = __float_as_uint(v[q * 4 + 2]); u.w = __float_as_uint(v[q * 4 + 3]);
+                                *reinterpret_cast<uint4*>(sbuf + row_off + (((piece0 + q) << 4) ^ xor_term)) = u;
+                            }
+                        }
+                    } else {
+                        const uint32_t piece0 = (uint32_t)(half * cpw) >> 3;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q * 8 < cpw) {
+                                uint4 u;
+                                u.x = pack2(v[q * 8 + 0], v[q * 8 + 1], p.is_f16);
+                                u.y = pack2(v[q * 8 + 2], v[q * 8 + 3], p.is_f16);
+                                u.z = pack2(v[q * 8 + 4], v[q * 8 + 5], p.is_f16);
+                                u.w = pack2(v[q * 8 + 6], v[q * 8 + 7], p.is_f16);
+                                *reinterpret_cast<uint4*>(sbuf + row_off + (((piece0 + q) << 4) ^ xor_term)) = u;
+                            }
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(1, 256);
+                    if (etid == 0) {
+                        ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, t.oh0, t.b0);
+                        ptx::tma_store_commit();
+                    }
+                    ++chunk_ctr;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+            if (etid == 0) ptx::tma_store_wait_all();
+            if (p.timing && etid == 0) {
+                p.timing[blockIdx.x * 8 + 5] = clock64() - t_begin;
+                p.timing[blockIdx.x * 8 + 6] = t_wtfull;
+            }
+        } else if (half == 1) {
+            // direct-store path uses four warps; the second warpgroup only keeps the TMEM hand-shake balanced
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        } else
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             const int ow = t.ow0 + rw, oh = t.oh0 + rh, b = t.b0 + rb;
@@ -310,8 +476,8 @@ void set_err(char* err, int errlen, const char* msg) {
 }
 
 template <int SWZ>
-cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, int grid, size_t smem,
-                       cudaStream_t stream) {
+cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& p,
+                       int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -319,7 +485,7 @@ cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const ConvP
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ><<<grid, kThreads, smem, stream>>>(mx, mw, p);
+    conv_tc_kernel<SWZ><<<grid, kThreads, smem, stream>>>(mx, mw, my, p);
     return cudaGetLastError();
 }
 
@@ -414,7 +580,16 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.a_stage_bytes = (uint32_t)(kTileM * swz);
     p.b_stage_bytes = (uint32_t)((n_tile * swz + 1023) / 1024 * 1024);
     const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    // epilogue staging: only when the output rows keep 16-byte alignment and the n-tile splits into whole chunks
+    const int elem = c.out_fp32 ? 4 : 2;
+    p.stage_cols = n_tile < 128 / elem ? n_tile : 128 / elem;
+    p.stage_rb = p.stage_cols * elem;
+    p.n_chunks = n_tile / p.stage_cols;
+    p.tma_store = ((c.y_pitch * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
+                   n_tile % p.stage_cols == 0 && (p.stage_rb == 32 || p.stage_rb == 64 || p.stage_rb == 128))
+                      ? 1 : 0;
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 1024 + 2 * 128 * 128;
+    int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
     if (stages < 2) stages = 2;
@@ -423,6 +598,16 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.y = c.y; p.y_pitch = c.y_pitch; p.out_fp32 = c.out_fp32;
     p.res = c.residual; p.res_pitch = c.res_pitch;
     p.bias = c.bias; p.relu = c.relu; p.is_f16 = (c.dtype == ACT_F16) ? 1 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("LOCR_CONV_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+        static long long* tbuf = nullptr;
+        static int want = -1;
+        if (want < 0) want = getenv("LOCR_CONV_TIMING") ? 1 : 0;
+        if (want && tbuf == nullptr) cudaMalloc(&tbuf, 148 * 8 * sizeof(long long));
+        p.timing = want ? tbuf : nullptr;
+    }
 
     const CUtensorMapDataType dt =
         (c.dtype == ACT_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -465,13 +650,45 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         }
     }
 
-    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
+    CUtensorMap my;
+    memset(&my, 0, sizeof(my));
+    if (p.tma_store) {
+        const cuuint64_t eb = (cuuint64_t)elem;
+        cuuint64_t dims[4] = {(cuuint64_t)c.Cout, (cuuint64_t)c.OW, (cuuint64_t)c.OH, (cuuint64_t)c.B};
+        const cuuint64_t pb = (cuuint64_t)c.y_pitch * eb;
+        cuuint64_t strides[3] = {pb, pb * c.OW, pb * c.OW * c.OH};
+        cuuint32_t box[4] = {(cuuint32_t)p.stage_cols, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUtensorMapDataType ydt = c.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;
+        const CUtensorMapSwizzle ysw = p.stage_rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                         : (p.stage_rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                             : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = encode(&my, ydt, 4, c.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, ysw,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "conv_tc: output tensor map encode failed (CUresult %d)", (int)r);
+            set_err(err, errlen, msg);
+            return cudaErrorInvalidValue;
+        }
+    }
+    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
-    if (swz == 128) e = launch_swz<128>(mx, mw, p, grid, smem, stream);
-    else if (swz == 64) e = launch_swz<64>(mx, mw, p, grid, smem, stream);
-    else e = launch_swz<32>(mx, mw, p, grid, smem, stream);
+    if (swz == 128) e = launch_swz<128>(mx, mw, my, p, grid, smem, stream);
+    else if (swz == 64) e = launch_swz<64>(mx, mw, my, p, grid, smem, stream);
+    else e = launch_swz<32>(mx, mw, my, p, grid, smem, stream);
     if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
+    if (p.timing != nullptr && e == cudaSuccess) {
+        long long h[148 * 8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, p.timing, sizeof(h), cudaMemcpyDeviceToHost);
+        const int tiles_cta = (p.num_tiles + grid - 1) / grid;
+        fprintf(stderr,
+                "[conv timing] tiles/cta %d kblocks %d n_tile %d | producer total %lld wait_empty %lld | mma total %lld "
+                "wait_full %lld wait_tempty %lld | epi total %lld wait_tfull %lld  (cycles, CTA 0)\n",
+                tiles_cta, p.num_kblocks, p.n_tile, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    }
     return e;
 }
 

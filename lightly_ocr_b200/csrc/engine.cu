@@ -24,7 +24,8 @@ T* dev_upload(locr_handle* h, const std::vector<T>& v) {
 }
 
 // Conv (+ optional BatchNorm, eval mode, eps 1e-5) -> weights with the BN scale folded in and a single fp32 bias.
-int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct) {
+int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct,
+              bool fold_image_std = false, int cin_pad = 0) {
     const HostTensor* w = find(h, model, prefix + ".weight");
     if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
         return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
@@ -58,17 +59,26 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
         for (int n = 0; n < cout; ++n)
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < taps; ++t)
-                    w32[((size_t)t * cin + c) * cout + n] = (float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]);
+                {
+                    // u8 mode of the direct kernel: (x - mean)/std with 1/std folded into the weights (BGR order
+                    // meets the RGB constants exactly as in the reference, imgproc.py:19-25)
+                    static const double stdv[3] = {0.229 * 255.0, 0.224 * 255.0, 0.225 * 255.0};
+                    const double istd = fold_image_std ? 1.0 / (double)(float)stdv[c] : 1.0;
+                    w32[((size_t)t * cin + c) * cout + n] =
+                        (float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n] * istd);
+                }
         cw.w32 = dev_upload(h, w32);
         if (!cw.w32) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
     } else {
-        if (cin % 16 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": Cin must be a multiple of 16");
-        std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * cin, 0);
+        const int cp = cin_pad > 0 ? cin_pad : cin;   // input channels as laid out in memory (zero-padded)
+        if (cp % 16 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": Cin must be a multiple of 16");
+        std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * cp, 0);
         for (int n = 0; n < cout; ++n)
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < taps; ++t)
-                    w16[((size_t)n * taps + t) * cin + c] =
+                    w16[((size_t)n * taps + t) * cp + c] =
                         f32_to_act((float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]), h->cfg.act_dtype);
+        cw.cin = cp;
         cw.w = dev_upload(h, w16);
         if (!cw.w) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
     }
@@ -182,7 +192,7 @@ static const char* kCraftBn[][2] = {
 };
 
 int engine_finalize_craft(locr_handle* h) {
-    int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", true);
+    int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16);
     if (rc != LOCR_OK) return rc;
     for (auto& e : kCraftBn) {
         rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false);
@@ -237,10 +247,11 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     if (c.rc != LOCR_OK) return c.rc;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
 
-    const ConvW& first = h->conv["basenet.slice1.0"];
-    launch_direct_conv3x3(d_images, 1, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, first.w32,
-                          first.bias, 3, 64, a0, 64, 1, f16, s);
+    void* x16 = c.buf("x16", px * 16 * 2);
+    if (c.rc != LOCR_OK) return c.rc;
+    launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s);
     h->launches++;
+    c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 1);
     c.tc("basenet.slice1.3", a0, B, H, W, 64, a1, 64, 1, 1, 1);
     launch_maxpool(a1, 64, B, H, W, 64, p1, 64, 2, 2, 2, 2, 0, 0, f16, s);
     c.tc("basenet.slice1.7", p1, B, H2, W2, 64, a2, 128, 1, 1, 1);

@@ -33,30 +33,32 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int f16) {
 }
 
 // ------------------------------------------------------------------------------------------- direct conv (tiny Cin)
+// One thread = one pixel x CPT output channels (CPT = 32): the 9*CIN inputs are loaded and converted once and reused
+// for 32 accumulators.  In u8 mode the weights arrive pre-divided by the per-channel std, so the normalisation
+// (x - mean)/std costs one subtraction per input (canvas padding reads as raw 0, i.e. -mean/std, conv padding as 0).
 template <int CIN, bool U8>
 __global__ void __launch_bounds__(256)
 direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
                       long img_stride, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                       uint16_t* __restrict__ out, long out_pitch, int relu, int f16) {
+    constexpr int CPT = 32;
     extern __shared__ float sw[];  // [9*CIN][Cout] then bias[Cout]
     const int nw = 9 * CIN * Cout;
     for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias[i];
     __syncthreads();
-    const int groups = Cout >> 3;
+    const int groups = Cout / CPT;
     const long total = (long)B * H * W * groups;
-    // ImageNet constants applied in BGR order exactly as the reference does (float32 arithmetic, IEEE division).
     const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
-    const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
     for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
         const int cg = (int)(gid % groups);
         const long pix = gid / groups;
         const int x = (int)(pix % W);
         const int y = (int)((pix / W) % H);
         const int b = (int)(pix / ((long)W * H));
-        float acc[8];
+        float acc[CPT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = sw[nw + cg * 8 + j];
+        for (int j = 0; j < CPT; ++j) acc[j] = sw[nw + cg * CPT + j];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int yy = y + ky - 1;
@@ -71,26 +73,56 @@ direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_
                     const uint8_t* p =
                         reinterpret_cast<const uint8_t*>(in) + (long)b * img_stride + (long)yy * row_stride + xx * 3;
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) {
-                        const float raw = inside ? (float)p[c] : 0.0f;
-                        v[c] = (raw - mean[c]) / stdv[c];
-                    }
+                    for (int c = 0; c < CIN; ++c) v[c] = (inside ? (float)p[c] : 0.0f) - mean[c];
                 } else {
                     v[0] = reinterpret_cast<const float*>(in)[((long)b * H + yy) * W + xx];
                 }
-                const float* wt = sw + ((ky * 3 + kx) * CIN) * Cout + cg * 8;
+                const float* wt = sw + ((ky * 3 + kx) * CIN) * Cout + cg * CPT;
 #pragma unroll
                 for (int c = 0; c < CIN; ++c) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[c], wt[c * Cout + j], acc[j]);
+                    for (int j = 0; j < CPT; j += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wt + c * Cout + j);
+                        acc[j] = fmaf(v[c], w4.x, acc[j]);
+                        acc[j + 1] = fmaf(v[c], w4.y, acc[j + 1]);
+                        acc[j + 2] = fmaf(v[c], w4.z, acc[j + 2]);
+                        acc[j + 3] = fmaf(v[c], w4.w, acc[j + 3]);
+                    }
                 }
             }
         }
-        if (relu) {
+        uint16_t* op = out + pix * out_pitch + cg * CPT;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        for (int q = 0; q < CPT / 8; ++q) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(acc[q * 8 + j], 0.f) : acc[q * 8 + j];
+            *reinterpret_cast<uint4*>(op + q * 8) = pack8(r, f16);
         }
-        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(acc, f16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- CRAFT image -> NHWC16
+// normalizeMeanVariance on the zero-padded canvas (reference imgproc.py:19-25, :58-60) written as a 16-channel NHWC
+// tensor (channels 3..15 zero) so that the first convolution runs on the tensor cores like every other layer.
+__global__ void __launch_bounds__(256)
+preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
+                      long img_stride, uint16_t* __restrict__ out, int f16) {
+    const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
+    const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
+    const long total = (long)B * H * W;
+    for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int b = (int)(pix / ((long)W * H));
+        const bool inside = (y < img_h) && (x < img_w);
+        const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
+        uint4* o = reinterpret_cast<uint4*>(out + pix * 16);
+        o[0] = pack8(v, f16);
+        o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -548,7 +580,7 @@ inline int grid_for(long total, int block) {
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
                            long out_pitch, int relu, int is_f16, cudaStream_t s) {
-    const long total = (long)B * H * W * (Cout / 8);
+    const long total = (long)B * H * W * (Cout / 32);
     const int grid = grid_for(total, 256);
     const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
     if (u8_mode)
@@ -557,6 +589,13 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
     else
         direct_conv3x3_kernel<1, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
                                                                 (uint16_t*)out, out_pitch, relu, is_f16);
+}
+
+void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
+                           long img_stride, void* out, int is_f16, cudaStream_t s) {
+    const long total = (long)B * H * W;
+    preproc_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
+                                                               (uint16_t*)out, is_f16);
 }
 
 void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,

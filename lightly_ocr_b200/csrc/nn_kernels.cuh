@@ -17,6 +17,11 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
                            long out_pitch, int relu, int is_f16, cudaStream_t s);
 
+// CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
+// channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.
+void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
+                           long img_stride, void* out, int is_f16, cudaStream_t s);
+
 void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
                     int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s);
 
