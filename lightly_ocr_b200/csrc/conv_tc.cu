@@ -34,7 +34,9 @@ constexpr int kTileM = 128;
 
 struct ConvParams {
     int B, OH, OW, Cout;
-    int bw, bh, bb;
+    int bw, bh, bb;      // 128-pixel half box
+    int halves;          // 1 or 2 half boxes per tile (M = 128 or 256), stacked along h (split_b = 0) or b (1)
+    int split_b;
     int tiles_w, tiles_h, tiles_n, num_tiles;
     int n_tile, n_tile_alloc, tmem_cols;
     int cin_chunks, KW, dil_h, dil_w, pad_h, pad_w, stride2;
@@ -53,7 +55,6 @@ struct ConvParams {
     int stage_cols;     // output columns per staging chunk (row bytes stage_rb = stage_cols * elem size: 32/64/128)
     int stage_rb;
     int n_chunks;       // n_tile / stage_cols
-    long long* timing;  // experiments only: per-CTA cycle counters [gridDim][8] (null = off)
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
@@ -71,8 +72,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     int tb = rest / p.tiles_h;
     t.n0 = n_idx * p.n_tile;
     t.ow0 = tw * p.bw;
-    t.oh0 = th * p.bh;
-    t.b0 = tb * p.bb;
+    t.oh0 = th * p.bh * (p.split_b ? 1 : p.halves);
+    t.b0 = tb * p.bb * (p.split_b ? p.halves : 1);
     return t;
 }
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
     }
 }
 
-template <int SWZ>
+template <int SWZ, int HALVES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const ConvParams p) {
@@ -145,93 +146,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer (single thread)
+        // The loop body is kept to a handful of instructions: a lone thread issues ~one instruction per 4-6 cycles, so
+        // index arithmetic (divisions, 64-bit address math) in here directly bounds the k-block rate.
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
-            long long t_wait = 0, t_begin = clock64();
+            const uint32_t tx_bytes = (uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+            const uint32_t a0 = ptx::smem_u32(smem_a), b0s = ptx::smem_u32(smem_b);
+            const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+            const uint32_t a_end = a0 + (uint32_t)p.stages * p.a_stage_bytes;
+            uint32_t a_s = a0, b_s = b0s, full_s = full0, empty_s = empty0, phase = 1;
+            const int KH = p.num_kblocks / (p.KW * p.cin_chunks);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
-                for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                    const int tap = kb / p.cin_chunks;
-                    const int cc = kb - tap * p.cin_chunks;
-                    const int kh = tap / p.KW;
-                    const int kw = tap - kh * p.KW;
-                    long long tw0 = p.timing ? clock64() : 0;
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
-                    if (p.timing) t_wait += clock64() - tw0;
-                    uint32_t txb = tx_bytes;
-                    if (p.dbg & 2) txb -= (uint32_t)(kTileM * SWZ);
-                    if (p.dbg & 4) txb -= (uint32_t)(p.n_tile * SWZ);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], txb);
-                    const int iw0 = t.ow0 + kw * p.dil_w - p.pad_w;
-                    int c2, c3;
-                    if (p.stride2) {  // input row = 2*oh + kh : dim2 selects kh, dim3 walks oh
-                        c2 = kh;
-                        c3 = t.oh0;
-                    } else {
-                        c2 = 0;
-                        c3 = t.oh0 + kh * p.dil_h - p.pad_h;
-                    }
-                    if (!(p.dbg & 2))
-                        ptx::tma_load_5d(smem_a + (size_t)stage * p.a_stage_bytes, &tmap_x, &full_bar[stage],
-                                         cc * BLOCK_K, iw0, c2, c3, t.b0);
-                    if (!(p.dbg & 4))
-                        ptx::tma_load_2d(smem_b + (size_t)stage * p.b_stage_bytes, &tmap_w, &full_bar[stage],
-                                         kb * BLOCK_K, t.n0);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
+                int kcoord = 0;
+                for (int kh = 0; kh < KH; ++kh) {
+                    const int c2 = p.stride2 ? kh : 0;
+                    const int c3 = p.stride2 ? t.oh0 : t.oh0 + kh * p.dil_h - p.pad_h;
+                    int iw0 = t.ow0 - p.pad_w;
+                    for (int kw = 0; kw < p.KW; ++kw, iw0 += p.dil_w) {
+                        for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
+                            ptx::mbar_wait_a(empty_s, phase, 100);
+                            ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
+                            ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cc * BLOCK_K, iw0, c2, c3, t.b0);
+                            ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
+                            a_s += p.a_stage_bytes; b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
+                            if (a_s == a_end) {
+                                a_s = a0; b_s = b0s; full_s = full0; empty_s = empty0;
+                                phase ^= 1u;
+                            }
+                        }
                     }
                 }
-            }
-            if (p.timing) {
-                p.timing[blockIdx.x * 8 + 0] = clock64() - t_begin;
-                p.timing[blockIdx.x * 8 + 1] = t_wait;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            long long t_wfull = 0, t_wtempty = 0, t_begin = clock64();
+            // descriptors as 32-bit running values: hi word constant, lo word = (addr >> 4) | LBO field
+            const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, SWZ) >> 32);
+            const uint32_t lo_flag = 1u << 16;
+            const uint32_t a_lo0 = ((ptx::smem_u32(smem_a) & 0x3FFFFu) >> 4) | lo_flag;
+            const uint32_t b_lo0 = ((ptx::smem_u32(smem_b) & 0x3FFFFu) >> 4) | lo_flag;
+            const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+            const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+            const uint32_t full_end = full0 + 8u * (uint32_t)p.stages;
+            uint32_t a_lo = a_lo0, b_lo = b_lo0, full_s = full0, empty_s = empty0, phase = 0;
+            const uint32_t tfull0 = ptx::smem_u32(tfull_bar), tempty0 = ptx::smem_u32(tempty_bar);
+            uint32_t acc = 0, acc_phase = 1;
+            const uint32_t acc_cols = (uint32_t)(HALVES * p.n_tile_alloc);
+            const uint32_t idesc = p.idesc;
+            constexpr uint32_t kHalfStep = (uint32_t)(kTileM * SWZ) >> 4;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                long long tw0 = p.timing ? clock64() : 0;
-                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 200 + acc);
-                if (p.timing) t_wtempty += clock64() - tw0;
+                ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile_alloc);
+                const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                uint32_t accum = 0;
                 for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                    long long tw1 = p.timing ? clock64() : 0;
-                    ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
-                    if (p.timing) t_wfull += clock64() - tw1;
+                    ptx::mbar_wait_a(full_s, phase, 300);
                     ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
-                    const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * p.b_stage_bytes);
 #pragma unroll
                     for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-                        const uint64_t da = ptx::make_kmajor_desc(a_addr + k * 32, SWZ);
-                        const uint64_t db = ptx::make_kmajor_desc(b_addr + k * 32, SWZ);
-                        if (!(p.dbg & 1)) ptx::umma_f16(d_tmem, da, db, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int hf = 0; hf < HALVES; ++hf) {
+                            // independent accumulators (M = 256 tiles) alternate, hiding the MMA pipeline latency
+                            ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
+                                               desc_hi, b_lo + k * 2, desc_hi, idesc, accum);
+                        }
+                        accum = 1;
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                    if (++stage == p.stages) {
-                        stage = 0;
+                    ptx::umma_commit_a(empty_s);  // frees the smem slot once these MMAs retire
+                    a_lo += a_step; b_lo += b_step; full_s += 8; empty_s += 8;
+                    if (full_s == full_end) {
+                        a_lo = a_lo0; b_lo = b_lo0; full_s = full0; empty_s = empty0;
                         phase ^= 1u;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                acc ^= 1;
+                ptx::umma_commit_a(tfull0 + acc * 8u);  // accumulators complete -> epilogue
+                acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
-            }
-            if (p.timing) {
-                p.timing[blockIdx.x * 8 + 2] = clock64() - t_begin;
-                p.timing[blockIdx.x * 8 + 3] = t_wfull;
-                p.timing[blockIdx.x * 8 + 4] = t_wtempty;
             }
         }
     } else if (warp >= 4) {
@@ -254,24 +246,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                        (uint32_t)(p.stage_rb / 16 - 1)) << 4;
             const uint32_t row_off = (uint32_t)row * (uint32_t)p.stage_rb;
             uint32_t chunk_ctr = 0;
-            long long t_wtfull = 0, t_begin = clock64();
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
-                const int ow = t.ow0 + rw, oh = t.oh0 + rh, b = t.b0 + rb;
+                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                ptx::tc_fence_after();
+                for (int hf = 0; hf < p.halves; ++hf) {
+                const int oh0 = t.oh0 + (p.split_b ? 0 : hf * p.bh), b0 = t.b0 + (p.split_b ? hf * p.bb : 0);
+                const int ow = t.ow0 + rw, oh = oh0 + rh, b = b0 + rb;
                 const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
                 const long pix = ((long)b * p.OH + oh) * p.OW + ow;
-                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
-                long long tw0 = p.timing ? clock64() : 0;
-                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
-                if (p.timing) t_wtfull += clock64() - tw0;
-                ptx::tc_fence_after();
                 for (int c = 0; c < p.n_chunks; ++c) {
                     uint8_t* sbuf = staging + (size_t)(chunk_ctr & 1u) * 128 * p.stage_rb;
                     if (etid == 0) ptx::tma_store_wait_read<1>();   // the store that used this buffer two chunks ago
                     ptx::named_bar_sync(1, 256);                    // ... is done; bias_s of this tile is visible
                     const int col0 = c * p.stage_cols + half * cpw;  // first column (within the n-tile) of this warp
                     const uint32_t taddr =
-                        tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile_alloc + col0);
+                        tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * p.halves + hf) * p.n_tile_alloc + col0);
                     float v[32];
                     if (cpw == 32) {
                         uint32_t r[32];
@@ -292,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
                     }
-                    if (c == p.n_chunks - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    if (c == p.n_chunks - 1 && hf == p.halves - 1) {  // accumulators fully read: hand the TMEM stage back to the MMA warp
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -353,19 +344,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     ptx::fence_proxy_async();
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) {
-                        ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, t.oh0, t.b0);
+                        ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
                         ptx::tma_store_commit();
                     }
                     ++chunk_ctr;
+                }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
             if (etid == 0) ptx::tma_store_wait_all();
-            if (p.timing && etid == 0) {
-                p.timing[blockIdx.x * 8 + 5] = clock64() - t_begin;
-                p.timing[blockIdx.x * 8 + 6] = t_wtfull;
-            }
         } else if (half == 1) {
             // direct-store path uses four warps; the second warpgroup only keeps the TMEM hand-shake balanced
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -475,17 +463,17 @@ void set_err(char* err, int errlen, const char* msg) {
     }
 }
 
-template <int SWZ>
+template <int SWZ, int HALVES>
 cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& p,
                        int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(conv_tc_kernel<SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ><<<grid, kThreads, smem, stream>>>(mx, mw, my, p);
+    conv_tc_kernel<SWZ, HALVES><<<grid, kThreads, smem, stream>>>(mx, mw, my, p);
     return cudaGetLastError();
 }
 
@@ -539,17 +527,45 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     }
 
     // Pick the 128-pixel patch shape (bw x bh x bb, all powers of two) that covers the output with fewest tiles.
+    // An M = 256 tile is two such patches stacked along b (if the patch spans several images) or along h.  It is used
+    // for n_tile <= 128: one TMA instruction then feeds two independent accumulators, which amortises the fixed
+    // per-instruction cost of the producer and hides the latency of back-to-back MMAs into one accumulator.
+    auto search = [&](int rows, int& obw, int& obh, int& obb) {
+        long best = -1;
+        for (int bw = rows > 256 ? 256 : rows; bw >= 1; bw >>= 1) {
+            for (int bh = rows / bw; bh >= 1; bh >>= 1) {
+                const int bb = rows / (bw * bh);
+                if (bw > 256 || bh > 256 || bb > 256) continue;
+                if (rows == 256 && !((bb > 1) || (bh > 1))) continue;   // must split into two 128-pixel halves
+                const long tiles = (long)((c.OW + bw - 1) / bw) * ((c.OH + bh - 1) / bh) * ((c.B + bb - 1) / bb);
+                if (best < 0 || tiles < best) {
+                    best = tiles;
+                    obw = bw; obh = bh; obb = bb;
+                }
+            }
+        }
+        return best;
+    };
     int best_bw = 0, best_bh = 0, best_bb = 0;
-    long best_tiles = -1;
-    for (int bw = 128; bw >= 1; bw >>= 1) {
-        for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
-            const int bb = 128 / (bw * bh);
-            const long tiles = (long)((c.OW + bw - 1) / bw) * ((c.OH + bh - 1) / bh) * ((c.B + bb - 1) / bb);
-            if (best_tiles < 0 || tiles < best_tiles) {
-                best_tiles = tiles;
-                best_bw = bw;
-                best_bh = bh;
-                best_bb = bb;
+    const long tiles128 = search(128, best_bw, best_bh, best_bb);
+    int halves = 1, split_b = 0;
+    {
+        static int allow256 = -1;
+        if (allow256 < 0) { const char* e = getenv("LOCR_CONV_M256"); allow256 = e ? atoi(e) : 1; }
+        const int elem_ = c.out_fp32 ? 4 : 2;
+        const int sc_ = n_tile < 128 / elem_ ? n_tile : 128 / elem_;
+        const int rb_ = sc_ * elem_;
+        const bool aligned_out = (c.y_pitch * elem_) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
+                                 n_tile % sc_ == 0 && (rb_ == 32 || rb_ == 64 || rb_ == 128);
+        int w2 = 0, h2 = 0, b2 = 0;
+        if (allow256 && n_tile <= 128 && aligned_out) {
+            const long tiles256 = search(256, w2, h2, b2);
+            const long n_tiles_n = c.Cout_pad / n_tile;
+            // worthwhile when it wastes no more pixels than the 128-row tiling and still fills the machine
+            if (tiles256 > 0 && tiles256 * 2 <= tiles128 + tiles128 / 16 && tiles256 * n_tiles_n >= 2L * device_sm_count()) {
+                halves = 2;
+                if (b2 > 1) { split_b = 1; best_bw = w2; best_bh = h2; best_bb = b2 / 2; }
+                else { split_b = 0; best_bw = w2; best_bh = h2 / 2; best_bb = b2; }
             }
         }
     }
@@ -558,9 +574,11 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     memset(&p, 0, sizeof(p));
     p.B = c.B; p.OH = c.OH; p.OW = c.OW; p.Cout = c.Cout;
     p.bw = best_bw; p.bh = best_bh; p.bb = best_bb;
+    p.halves = halves; p.split_b = split_b;
+    const int full_bh = p.bh * (split_b ? 1 : halves), full_bb = p.bb * (split_b ? halves : 1);
     p.tiles_w = (c.OW + p.bw - 1) / p.bw;
-    p.tiles_h = (c.OH + p.bh - 1) / p.bh;
-    const int tiles_b = (c.B + p.bb - 1) / p.bb;
+    p.tiles_h = (c.OH + full_bh - 1) / full_bh;
+    const int tiles_b = (c.B + full_bb - 1) / full_bb;
     p.tiles_n = c.Cout_pad / n_tile;
     const long num_tiles = (long)p.tiles_w * p.tiles_h * tiles_b * p.tiles_n;
     if (num_tiles <= 0 || num_tiles > 0x7fffffffL) {
@@ -571,13 +589,13 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.n_tile = n_tile;
     p.n_tile_alloc = (n_tile + 31) / 32 * 32;
     int cols = 32;
-    while (cols < 2 * p.n_tile_alloc) cols <<= 1;
+    while (cols < 2 * halves * p.n_tile_alloc) cols <<= 1;
     p.tmem_cols = cols;
     p.cin_chunks = c.Cin / block_k;
     p.KW = c.KW; p.dil_h = c.dil_h; p.dil_w = c.dil_w; p.pad_h = c.pad_h; p.pad_w = c.pad_w;
     p.stride2 = (c.stride_h == 2) ? 1 : 0;
     p.num_kblocks = c.KH * c.KW * p.cin_chunks;
-    p.a_stage_bytes = (uint32_t)(kTileM * swz);
+    p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
     p.b_stage_bytes = (uint32_t)((n_tile * swz + 1023) / 1024 * 1024);
     const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     // epilogue staging: only when the output rows keep 16-byte alignment and the n-tile splits into whole chunks
@@ -602,11 +620,6 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("LOCR_CONV_DBG"); dbg = e ? atoi(e) : 0; }
         p.dbg = dbg;
-        static long long* tbuf = nullptr;
-        static int want = -1;
-        if (want < 0) want = getenv("LOCR_CONV_TIMING") ? 1 : 0;
-        if (want && tbuf == nullptr) cudaMalloc(&tbuf, 148 * 8 * sizeof(long long));
-        p.timing = want ? tbuf : nullptr;
     }
 
     const CUtensorMapDataType dt =
@@ -621,7 +634,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                               (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.x_pitch * 2;
         cuuint64_t strides[4] = {pb, pb * c.W, pb * c.W * S, pb * c.W * c.H};
-        cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
+        cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)full_bh, (cuuint32_t)full_bb};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&mx, dt, 5, const_cast<void*>(c.x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -675,20 +688,16 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
-    if (swz == 128) e = launch_swz<128>(mx, mw, my, p, grid, smem, stream);
-    else if (swz == 64) e = launch_swz<64>(mx, mw, my, p, grid, smem, stream);
-    else e = launch_swz<32>(mx, mw, my, p, grid, smem, stream);
-    if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
-    if (p.timing != nullptr && e == cudaSuccess) {
-        long long h[148 * 8];
-        cudaStreamSynchronize(stream);
-        cudaMemcpy(h, p.timing, sizeof(h), cudaMemcpyDeviceToHost);
-        const int tiles_cta = (p.num_tiles + grid - 1) / grid;
-        fprintf(stderr,
-                "[conv timing] tiles/cta %d kblocks %d n_tile %d | producer total %lld wait_empty %lld | mma total %lld "
-                "wait_full %lld wait_tempty %lld | epi total %lld wait_tfull %lld  (cycles, CTA 0)\n",
-                tiles_cta, p.num_kblocks, p.n_tile, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+    if (halves == 2) {
+        if (swz == 128) e = launch_swz<128, 2>(mx, mw, my, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 2>(mx, mw, my, p, grid, smem, stream);
+        else e = launch_swz<32, 2>(mx, mw, my, p, grid, smem, stream);
+    } else {
+        if (swz == 128) e = launch_swz<128, 1>(mx, mw, my, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 1>(mx, mw, my, p, grid, smem, stream);
+        else e = launch_swz<32, 1>(mx, mw, my, p, grid, smem, stream);
     }
+    if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
     return e;
 }
 

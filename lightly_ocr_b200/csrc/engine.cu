@@ -48,7 +48,7 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
         }
     }
     ConvW cw;
-    cw.cin = cin; cw.cout = cout; cw.kh = kh; cw.kw = kw;
+    cw.cin = cin; cw.cin_real = cin; cw.cout = cout; cw.kh = kh; cw.kw = kw;
     cw.cout_pad = (cout + 15) / 16 * 16;
     std::vector<float> bias(cw.cout_pad, 0.f);
     for (int n = 0; n < cout; ++n) bias[n] = (float)shift[n];
@@ -136,7 +136,7 @@ struct Ctx {
         if (h->profile) {
             cudaEventCreate(&pr.e0);
             cudaEventCreate(&pr.e1);
-            pr.flops = 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin * cw.kh * cw.kw;
+            pr.flops = 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin_real * cw.kh * cw.kw;
             cudaEventRecord(pr.e0, h->stream);
         }
         cudaError_t e = conv_tc_launch(c, h->stream, err, sizeof(err));

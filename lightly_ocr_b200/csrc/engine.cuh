@@ -27,6 +27,7 @@ struct ConvW {
     float* w32 = nullptr;    // fp32 [kh*kw*cin][cout]         (direct path, tiny cin)
     float* bias = nullptr;   // fp32 [cout_pad]
     int cin = 0, cout = 0, cout_pad = 0, kh = 1, kw = 1;
+    int cin_real = 0;        // input channels of the reference layer (cin may be zero-padded to 16)
 };
 
 struct DebugTensor {
