@@ -4,9 +4,8 @@ Nothing under oracle/ is part of the product: only tests/, __graft_entry__.smoke
 import it, and only as the checker / the timed CPU baseline.  The product path (lightly_ocr_b200/) never imports it.
 
 Contents
-  specs.py      layer tables (state-dict key names and shapes) of the reference's CRAFT and CRNN graphs
-  weights.py    deterministic synthetic state dicts (checkpoints cannot be downloaded offline)
-  receipts.py   synthetic receipt images and crops (BASELINE.json configs)
+  specs.py / receipts.py / weights.py   re-exports of the synthetic input generators that live in
+                lightly_ocr_b200/synth/ (data only); weights.py adds the one-off calibration that needs the oracle
   ocr_ref.py    restatement of the reference path with the reference's own third-party arithmetic
                 (torch CPU fp32, cv2, PIL) - the parity oracle and the CPU baseline ("port")
   exact.py      library-free numpy restatements of the cv2 / PIL integer and float32 routines the path calls
