@@ -55,6 +55,8 @@ struct ConvParams {
     int stage_cols;     // output columns per staging chunk (row bytes stage_rb = stage_cols * elem size: 32/64/128)
     int stage_rb;
     int n_chunks;       // n_tile / stage_cols
+    int cin_wrap;       // channel coordinate wraps at this value (split-precision inputs), huge when unused
+    int split_out;      // write hi / lo halves (split-precision outputs)
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
@@ -167,7 +169,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
                             ptx::mbar_wait_a(empty_s, phase, 100);
                             ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
-                            ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cc * BLOCK_K, iw0, c2, c3, t.b0);
+                            int cch = cc * BLOCK_K;
+                            if (cch >= p.cin_wrap) cch -= p.cin_wrap;   // [hi | lo | hi] of a split-precision input
+                            ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
                             ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
                             a_s += p.a_stage_bytes; b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
                             if (a_s == a_end) {
@@ -257,8 +261,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
                 const long pix = ((long)b * p.OH + oh) * p.OW + ow;
                 for (int c = 0; c < p.n_chunks; ++c) {
-                    uint8_t* sbuf = staging + (size_t)(chunk_ctr & 1u) * 128 * p.stage_rb;
-                    if (etid == 0) ptx::tma_store_wait_read<1>();   // the store that used this buffer two chunks ago
+                    uint8_t* sbuf = staging + (size_t)((p.split_out ? 0u : chunk_ctr) & 1u) * 128 * p.stage_rb;
+                    uint8_t* sbuf_lo = staging + (size_t)128 * p.stage_rb;   // split-precision: second tile = lo parts
+                    if (etid == 0) {
+                        if (p.split_out) ptx::tma_store_wait_read<0>();
+                        else ptx::tma_store_wait_read<1>();        // the store that used this buffer two chunks ago
+                    }
                     ptx::named_bar_sync(1, 256);                    // ... is done; bias_s of this tile is visible
                     const int col0 = c * p.stage_cols + half * cpw;  // first column (within the n-tile) of this warp
                     const uint32_t taddr =
@@ -338,6 +346,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 u.z = pack2(v[q * 8 + 4], v[q * 8 + 5], p.is_f16);
                                 u.w = pack2(v[q * 8 + 6], v[q * 8 + 7], p.is_f16);
                                 *reinterpret_cast<uint4*>(sbuf + row_off + (((piece0 + q) << 4) ^ xor_term)) = u;
+                                if (p.split_out) {
+                                    const float2 h0 = unpack2(u.x, p.is_f16), h1 = unpack2(u.y, p.is_f16);
+                                    const float2 h2 = unpack2(u.z, p.is_f16), h3 = unpack2(u.w, p.is_f16);
+                                    uint4 l;
+                                    l.x = pack2(v[q * 8 + 0] - h0.x, v[q * 8 + 1] - h0.y, p.is_f16);
+                                    l.y = pack2(v[q * 8 + 2] - h1.x, v[q * 8 + 3] - h1.y, p.is_f16);
+                                    l.z = pack2(v[q * 8 + 4] - h2.x, v[q * 8 + 5] - h2.y, p.is_f16);
+                                    l.w = pack2(v[q * 8 + 6] - h3.x, v[q * 8 + 7] - h3.y, p.is_f16);
+                                    *reinterpret_cast<uint4*>(sbuf_lo + row_off + (((piece0 + q) << 4) ^ xor_term)) = l;
+                                }
                             }
                         }
                     }
@@ -345,6 +363,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) {
                         ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                        if (p.split_out)
+                            ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
                         ptx::tma_store_commit();
                     }
                     ++chunk_ctr;
@@ -513,6 +533,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         set_err(err, errlen, "conv_tc: channel counts / pitches must keep 16-byte alignment");
         return cudaErrorInvalidValue;
     }
+    if (c.split_out && (c.out_fp32 || c.Cout != c.Cout_pad || c.Cout % 64 != 0)) {
+        set_err(err, errlen, "conv_tc: split-precision output needs a 16-bit output with Cout a multiple of 64");
+        return cudaErrorInvalidValue;
+    }
     int n_tile = c.n_tile;
     if (n_tile == 0) {
         if (c.Cout_pad % 256 == 0) n_tile = 256;
@@ -620,6 +644,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("LOCR_CONV_DBG"); dbg = e ? atoi(e) : 0; }
         p.dbg = dbg;
+        p.cin_wrap = c.cin_wrap > 0 ? c.cin_wrap : 0x7fffffff;
+        p.split_out = c.split_out;
     }
 
     const CUtensorMapDataType dt =
@@ -630,7 +656,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     CUtensorMap mx, mw;
     {
         const int S = p.stride2 ? 2 : 1;
-        cuuint64_t dims[5] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)S, (cuuint64_t)(c.H / S),
+        cuuint64_t dims[5] = {(cuuint64_t)(c.cin_wrap > 0 ? c.cin_wrap : c.Cin), (cuuint64_t)c.W, (cuuint64_t)S, (cuuint64_t)(c.H / S),
                               (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.x_pitch * 2;
         cuuint64_t strides[4] = {pb, pb * c.W, pb * c.W * S, pb * c.W * c.H};
@@ -667,7 +693,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     memset(&my, 0, sizeof(my));
     if (p.tma_store) {
         const cuuint64_t eb = (cuuint64_t)elem;
-        cuuint64_t dims[4] = {(cuuint64_t)c.Cout, (cuuint64_t)c.OW, (cuuint64_t)c.OH, (cuuint64_t)c.B};
+        cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)c.OW, (cuuint64_t)c.OH,
+                              (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.y_pitch * eb;
         cuuint64_t strides[3] = {pb, pb * c.OW, pb * c.OW * c.OH};
         cuuint32_t box[4] = {(cuuint32_t)p.stage_cols, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};

@@ -29,6 +29,10 @@ struct ConvCall {
     int relu = 0;
     int dtype = ACT_BF16;
     int n_tile = 0;  // 0 = choose automatically
+    // Split-precision (hi + lo) tensors: a value v is stored as two 16-bit numbers hi = round(v), lo = round(v - hi) in
+    // channels [c] and [C + c] of a 2C-channel tensor (~22 significant bits).
+    int cin_wrap = 0;   // > 0: the K channels of a tap are [hi | lo | hi] = 3C, read from a tensor of cin_wrap = 2C channels
+    int split_out = 0;  // 1: write hi to channel n and lo to channel Cout + n of a 2*Cout-channel output
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).

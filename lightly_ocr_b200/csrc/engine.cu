@@ -25,7 +25,7 @@ T* dev_upload(locr_handle* h, const std::vector<T>& v) {
 
 // Conv (+ optional BatchNorm, eval mode, eps 1e-5) -> weights with the BN scale folded in and a single fp32 bias.
 int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct,
-              bool fold_image_std = false, int cin_pad = 0) {
+              bool fold_image_std = false, int cin_pad = 0, bool split3 = false) {
     const HostTensor* w = find(h, model, prefix + ".weight");
     if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
         return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
@@ -70,6 +70,31 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
         cw.w32 = dev_upload(h, w32);
         if (!cw.w32) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
     } else {
+        if (split3) {
+            // split-precision layer: K channels per tap are [x_hi | x_lo | x_hi] against [w_hi | w_hi | w_lo], i.e.
+            // x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with ~22 significant bits on both operands
+            if (cin % 64 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": split precision needs Cin % 64 == 0");
+            const int K3 = 3 * cin;
+            std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * K3, 0);
+            for (int n = 0; n < cout; ++n)
+                for (int c = 0; c < cin; ++c)
+                    for (int t = 0; t < taps; ++t) {
+                        const float wv = (float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]);
+                        const uint16_t hi = f32_to_act(wv, h->cfg.act_dtype);
+                        const uint16_t lo = f32_to_act(wv - act_to_f32(hi, h->cfg.act_dtype), h->cfg.act_dtype);
+                        uint16_t* row = &w16[((size_t)n * taps + t) * K3];
+                        row[c] = hi;
+                        row[cin + c] = hi;
+                        row[2 * cin + c] = lo;
+                    }
+            cw.w = dev_upload(h, w16);
+            if (!cw.w) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+            cw.cin = K3;
+            cw.cin_wrap = 2 * cin;
+            if (!cw.bias) return h->fail(LOCR_ERR_CUDA, "bias upload failed");
+            h->conv[prefix] = cw;
+            return LOCR_OK;
+        }
         const int cp = cin_pad > 0 ? cin_pad : cin;   // input channels as laid out in memory (zero-padded)
         if (cp % 16 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": Cin must be a multiple of 16");
         std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * cp, 0);
@@ -113,7 +138,7 @@ struct Ctx {
     // y = act(conv(x)) through the tensor-core kernel.  Shapes are those of the INPUT; returns output dims.
     void tc(const std::string& layer, const void* x, int B, int H, int W, long x_pitch, void* y, long y_pitch, int relu,
             int pad_h, int pad_w, int dil = 1, int stride_h = 1, int out_fp32 = 0, const void* res = nullptr,
-            long res_pitch = 0) {
+            long res_pitch = 0, int split_out = 0) {
         if (rc != LOCR_OK) return;
         auto it = h->conv.find(layer);
         if (it == h->conv.end() || it->second.w == nullptr) {
@@ -131,6 +156,8 @@ struct Ctx {
         c.y = y; c.y_pitch = y_pitch; c.out_fp32 = out_fp32;
         c.bias = cw.bias; c.residual = res; c.res_pitch = res_pitch; c.relu = relu;
         c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
+        c.cin_wrap = cw.cin_wrap;
+        c.split_out = split_out;
         char err[256] = {0};
         locr_handle::ProfRec pr;
         if (h->profile) {
@@ -313,9 +340,11 @@ int engine_finalize_crnn(locr_handle* h) {
         return fold_conv(h, M, p, bn, direct);
     };
     if ((rc = F(loc + "conv.0", loc + "conv.1", true))) return rc;
-    if ((rc = F(loc + "conv.4", loc + "conv.5"))) return rc;
-    if ((rc = F(loc + "conv.8", loc + "conv.9"))) return rc;
-    if ((rc = F(loc + "conv.12", loc + "conv.13"))) return rc;
+    // The localisation network runs in split precision (hi + lo 16-bit pairs, ~22 bits): its output moves the TPS
+    // sampling grid, and a 1e-4 fiducial error of plain 16-bit storage becomes a 1e-2 error of the rectified crop.
+    if ((rc = fold_conv(h, M, loc + "conv.4", loc + "conv.5", false, false, 0, true))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.8", loc + "conv.9", false, false, 0, true))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.12", loc + "conv.13", false, false, 0, true))) return rc;
     if ((rc = F(fe + "conv0_1", fe + "bn0_1", true))) return rc;
     if ((rc = F(fe + "conv0_2", fe + "bn0_2"))) return rc;
     const int nblocks[5] = {0, 1, 2, 5, 3};
@@ -444,7 +473,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     cudaStream_t s = h->stream;
     const std::string loc = kLoc, fe = kFe;
     const size_t big = (size_t)B * 32 * 100 * 64 * 2;
-    void* sA = c.buf("crnn.sA", big);
+    void* sA = c.buf("crnn.sA", big * 2);   // the split-precision localisation tensors have 2x the channels
     void* sB = c.buf("crnn.sB", big);
     void* sC = c.buf("crnn.sC", big / 2);
     void* sD = c.buf("crnn.sD", big / 2);
@@ -460,16 +489,16 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     float* lg = (float*)c.buf("crnn.logits", (size_t)B * 26 * C * 4);
     if (c.rc != LOCR_OK) return c.rc;
 
-    // ---- TPS localisation network (TPS_STN.py:38-58)
+    // ---- TPS localisation network (TPS_STN.py:38-58), split precision: tensors hold [hi | lo] channel halves
     const ConvW& l0 = h->conv[loc + "conv.0"];
-    launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 64, 1, f16, s);
-    launch_maxpool(sA, 64, B, 32, 100, 64, sB, 64, 2, 2, 2, 2, 0, 0, f16, s);
-    c.tc(loc + "conv.4", sB, B, 16, 50, 64, sA, 128, 1, 1, 1);
-    launch_maxpool(sA, 128, B, 16, 50, 128, sB, 128, 2, 2, 2, 2, 0, 0, f16, s);
-    c.tc(loc + "conv.8", sB, B, 8, 25, 128, sA, 256, 1, 1, 1);
-    launch_maxpool(sA, 256, B, 8, 25, 256, sB, 256, 2, 2, 2, 2, 0, 0, f16, s);
-    c.tc(loc + "conv.12", sB, B, 4, 12, 256, sA, 512, 1, 1, 1);
-    launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s);
+    launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 128, 1, f16, s, 1);
+    launch_maxpool(sA, 128, B, 32, 100, 64, sB, 128, 2, 2, 2, 2, 0, 0, f16, s, 1);
+    c.tc(loc + "conv.4", sB, B, 16, 50, 128, sA, 256, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
+    launch_maxpool(sA, 256, B, 16, 50, 128, sB, 256, 2, 2, 2, 2, 0, 0, f16, s, 1);
+    c.tc(loc + "conv.8", sB, B, 8, 25, 256, sA, 512, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
+    launch_maxpool(sA, 512, B, 8, 25, 256, sB, 512, 2, 2, 2, 2, 0, 0, f16, s, 1);
+    c.tc(loc + "conv.12", sB, B, 4, 12, 512, sA, 1024, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
+    launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s, 1);
     launch_tps_sample(fid, h->f32["tps.inv"], h->f32["tps.phat_t"], d_x, xr, grid, B, s);
     h->launches += 6;
 

@@ -28,6 +28,7 @@ struct ConvW {
     float* bias = nullptr;   // fp32 [cout_pad]
     int cin = 0, cout = 0, cout_pad = 0, kh = 1, kw = 1;
     int cin_real = 0;        // input channels of the reference layer (cin may be zero-padded to 16)
+    int cin_wrap = 0;        // split-precision input: K channels [hi|lo|hi] = 3C read from a 2C-channel tensor
 };
 
 struct DebugTensor {

@@ -40,7 +40,7 @@ template <int CIN, bool U8>
 __global__ void __launch_bounds__(256)
 direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
                       long img_stride, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                      uint16_t* __restrict__ out, long out_pitch, int relu, int f16) {
+                      uint16_t* __restrict__ out, long out_pitch, int relu, int f16, int split) {
     constexpr int CPT = 32;
     extern __shared__ float sw[];  // [9*CIN][Cout] then bias[Cout]
     const int nw = 9 * CIN * Cout;
@@ -97,7 +97,15 @@ direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_
             float r[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(acc[q * 8 + j], 0.f) : acc[q * 8 + j];
-            *reinterpret_cast<uint4*>(op + q * 8) = pack8(r, f16);
+            const uint4 hi = pack8(r, f16);
+            *reinterpret_cast<uint4*>(op + q * 8) = hi;
+            if (split) {  // split precision: lo = v - hi goes to channel Cout + n
+                float h[8];
+                unpack8(hi, h, f16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] -= h[j];
+                *reinterpret_cast<uint4*>(op + Cout + q * 8) = pack8(r, f16);
+            }
         }
     }
 }
@@ -129,7 +137,7 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
 // ------------------------------------------------------------------------------------------- max pool
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C, uint16_t* __restrict__ out,
-               long out_pitch, int OH, int OW, int kh, int kw, int sh, int sw_, int ph, int pw, int f16) {
+               long out_pitch, int OH, int OW, int kh, int kw, int sh, int sw_, int ph, int pw, int f16, int split) {
     const int groups = C >> 3;
     const long total = (long)B * OH * OW * groups;
     for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
@@ -151,11 +159,27 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
                     __ldg(reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * in_pitch + cg * 8));
                 float f[8];
                 unpack8(u, f, f16);
+                if (split) {  // value = hi + lo (exact in fp32), lo lives C channels further
+                    const uint4 ul = __ldg(
+                        reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * in_pitch + C + cg * 8));
+                    float l[8];
+                    unpack8(ul, l, f16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += l[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
             }
         }
-        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(m, f16);
+        const uint4 hi = pack8(m, f16);
+        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = hi;
+        if (split) {
+            float h[8];
+            unpack8(hi, h, f16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] -= h[j];
+            *reinterpret_cast<uint4*>(out + pix * out_pitch + C + cg * 8) = pack8(m, f16);
+        }
     }
 }
 
@@ -196,14 +220,19 @@ upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, 
 // ------------------------------------------------------------------------------------------- TPS localisation head
 __global__ void __launch_bounds__(256)
 loc_head_kernel(const uint16_t* __restrict__ feat, int hw, const float* __restrict__ w1t, const float* __restrict__ b1,
-                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ fid, int f16) {
+                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ fid, int f16, int split) {
     __shared__ float pooled[512];
     __shared__ float hid[256];
     const int b = blockIdx.x;
-    const uint16_t* f = feat + (long)b * hw * 512;
+    const int pitch = split ? 1024 : 512;
+    const uint16_t* f = feat + (long)b * hw * pitch;
     for (int c = threadIdx.x; c < 512; c += blockDim.x) {
         float s = 0.f;
-        for (int p = 0; p < hw; ++p) s += act2f(f[(long)p * 512 + c], f16);
+        for (int p = 0; p < hw; ++p) {
+            float v = act2f(f[(long)p * pitch + c], f16);
+            if (split) v += act2f(f[(long)p * pitch + 512 + c], f16);
+            s += v;
+        }
         pooled[c] = s / (float)hw;
     }
     __syncthreads();
@@ -579,16 +608,16 @@ inline int grid_for(long total, int block) {
 
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s) {
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out) {
     const long total = (long)B * H * W * (Cout / 32);
     const int grid = grid_for(total, 256);
     const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
     if (u8_mode)
         direct_conv3x3_kernel<3, true><<<grid, 256, smem, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride, w,
-                                                               bias, Cout, (uint16_t*)out, out_pitch, relu, is_f16);
+                                                               bias, Cout, (uint16_t*)out, out_pitch, relu, is_f16, split_out);
     else
         direct_conv3x3_kernel<1, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
-                                                                (uint16_t*)out, out_pitch, relu, is_f16);
+                                                                (uint16_t*)out, out_pitch, relu, is_f16, split_out);
 }
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
@@ -599,11 +628,11 @@ void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, in
 }
 
 void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
-                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s) {
+                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s, int split) {
     const int OH = (H + 2 * ph - kh) / sh + 1, OW = (W + 2 * pw - kw) / sw + 1;
     const long total = (long)B * OH * OW * (C / 8);
     maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint16_t*)in, in_pitch, B, H, W, C, (uint16_t*)out,
-                                                        out_pitch, OH, OW, kh, kw, sh, sw, ph, pw, is_f16);
+                                                        out_pitch, OH, OW, kh, kw, sh, sw, ph, pw, is_f16, split);
 }
 
 void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch,
@@ -614,8 +643,8 @@ void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C
 }
 
 void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const float* b1, const float* w2t,
-                     const float* b2, float* fid, int is_f16, cudaStream_t s) {
-    loc_head_kernel<<<B, 256, 0, s>>>((const uint16_t*)feat, hw, w1t, b1, w2t, b2, fid, is_f16);
+                     const float* b2, float* fid, int is_f16, cudaStream_t s, int split) {
+    loc_head_kernel<<<B, 256, 0, s>>>((const uint16_t*)feat, hw, w1t, b1, w2t, b2, fid, is_f16, split);
 }
 
 void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,

@@ -7,6 +7,9 @@
 
 namespace locr {
 
+// Split-precision tensors (hi + lo halves in channels [c] and [C + c], see conv_tc.cuh) are produced with split_out /
+// consumed with split = 1; C is then the number of LOGICAL channels.
+//
 // 3x3 / pad 1 convolution for Cin in {1, 3} (reference layers basenet.slice1.0, LocalizationNetwork.conv.0,
 // ConvNet.conv0_1).  w: fp32 [9*Cin][Cout] (BN scale folded), bias fp32 [Cout], out 16-bit NHWC.
 //   u8 mode  : `in` is uint8 BGR [B][img_h][img_w][3] (row stride in bytes); the canvas is H x W, pixels outside the
@@ -15,7 +18,7 @@ namespace locr {
 //   f32 mode : `in` is fp32 [B][H][W] (Cin = 1).
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s);
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out = 0);
 
 // CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
 // channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.
@@ -23,7 +26,7 @@ void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, in
                            long img_stride, void* out, int is_f16, cudaStream_t s);
 
 void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
-                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s);
+                    int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s, int split = 0);
 
 // F.interpolate(scale 2, bilinear, align_corners=False) of [B,H,W,C] into a [B,2H,2W,*] view (model.py:47,51,55).
 void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch,
@@ -32,7 +35,7 @@ void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C
 // AdaptiveAvgPool2d(1) + Linear(512,256)+ReLU + Linear(256,40)  (TPS_STN.py:57-60,70-76).
 // feat 16-bit [B][hw][512]; w1t fp32 [512][256]; w2t fp32 [256][40]; fid fp32 [B][40].
 void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const float* b1, const float* w2t,
-                     const float* b2, float* fid, int is_f16, cudaStream_t s);
+                     const float* b2, float* fid, int is_f16, cudaStream_t s, int split = 0);
 
 // build_P_prime + grid_sample(bilinear, border, align_corners=True)  (TPS_STN.py:142-150, :27).
 // inv_delta_c fp32 [23][23]; p_hat_t fp32 [23][3200] (transposed); x, out fp32 [B][32][100]; grid (optional) [B][3200][2].
