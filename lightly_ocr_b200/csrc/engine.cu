@@ -394,29 +394,35 @@ int engine_finalize_crnn(locr_handle* h) {
         const HostTensor* bhb = find(h, M, p + "bias_hh_l0_reverse");
         if (!wf || !wb || !hf || !hb || !bif || !bhf || !bib || !bhb) return h->fail(LOCR_ERR_STATE, "missing LSTM tensors");
         const int nin = (int)wf->shape[1];
+        // Row order of the recurrence kernel (lstm_tc.cu): n' = pass*256 + unit_in_pass*4 + gate with
+        // unit = pass*64 + unit_in_pass; PyTorch's order is gate*256 + unit (gates i, f, g, o).
+        auto perm = [](int np) {
+            const int pass = np >> 8, ul = (np & 255) >> 2, gate = np & 3;
+            return gate * 256 + pass * 64 + ul;
+        };
         HostTensor stacked, sbias;
         stacked.shape = {2048, nin};
-        stacked.data = wf->data;
-        stacked.data.insert(stacked.data.end(), wb->data.begin(), wb->data.end());
+        stacked.data.resize((size_t)2048 * nin);
         sbias.shape = {2048};
         sbias.data.resize(2048);
-        for (int i = 0; i < 1024; ++i) {
-            sbias.data[i] = bif->data[i] + bhf->data[i];
-            sbias.data[1024 + i] = bib->data[i] + bhb->data[i];
+        std::vector<uint16_t> whh((size_t)2048 * 256);
+        for (int d = 0; d < 2; ++d) {
+            const HostTensor* wi = d == 0 ? wf : wb;
+            const HostTensor* hh = d == 0 ? hf : hb;
+            const HostTensor* bi = d == 0 ? bif : bib;
+            const HostTensor* bh = d == 0 ? bhf : bhb;
+            for (int np = 0; np < 1024; ++np) {
+                const int r = perm(np);
+                memcpy(&stacked.data[(size_t)(d * 1024 + np) * nin], &wi->data[(size_t)r * nin], sizeof(float) * nin);
+                sbias.data[d * 1024 + np] = bi->data[r] + bh->data[r];
+                for (int k = 0; k < 256; ++k)
+                    whh[(size_t)(d * 1024 + np) * 256 + k] = f32_to_act(hh->data[(size_t)r * 256 + k], h->cfg.act_dtype);
+            }
         }
         const std::string name = "lstm" + std::to_string(l) + ".xproj";
         h->host[M][name + ".weight"] = stacked;
         h->host[M][name + ".bias"] = sbias;
         if ((rc = F(name, ""))) return rc;
-        std::vector<uint16_t> whh((size_t)2 * 256 * 256 * 4);
-        for (int d = 0; d < 2; ++d) {
-            const HostTensor* hh = d == 0 ? hf : hb;
-            for (int k = 0; k < 256; ++k)
-                for (int j = 0; j < 256; ++j)
-                    for (int q = 0; q < 4; ++q)
-                        whh[(((size_t)d * 256 + k) * 256 + j) * 4 + q] =
-                            f32_to_act(hh->data[(size_t)(q * 256 + j) * 256 + k], h->cfg.act_dtype);
-        }
         h->lstm_whh[l] = dev_upload(h, whh);
         if ((rc = F("SequenceModeling." + std::to_string(l) + ".linear", ""))) return rc;
     }
@@ -483,6 +489,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     void* vis = c.buf("crnn.visual", (size_t)B * 26 * 512 * 2);
     float* xproj = (float*)c.buf("crnn.xproj", (size_t)B * 26 * 2048 * 4);
     void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * 512 * 2);
+    float* cst = (float*)c.buf("crnn.cstate", lstm_tc_cstate_bytes(B));
     void* s0 = c.buf("crnn.s0", (size_t)B * 26 * 256 * 2);
     void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * 256 * 2);
     const int C = h->cfg.num_classes;
@@ -554,10 +561,12 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     // ---- sequence modelling (model.py:107-112; AdaptiveAvgPool over H=1 is the identity) as [B*26, C] GEMMs
     const int R = B * 26;
     c.tc("lstm0.xproj", vis, 1, 1, R, 512, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK) launch_lstm(xproj, h->lstm_whh[0], hcat, B, 26, f16, s);
+    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[0], cst, hcat, B, 26, f16, s) != cudaSuccess)
+        c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, 256, 0, 0, 0);
     c.tc("lstm1.xproj", s0, 1, 1, R, 256, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK) launch_lstm(xproj, h->lstm_whh[1], hcat, B, 26, f16, s);
+    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[1], cst, hcat, B, 26, f16, s) != cudaSuccess)
+        c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, 256, 0, 0, 0);
     h->launches += 2;
     if (h->cfg.head == LOCR_HEAD_CTC) {

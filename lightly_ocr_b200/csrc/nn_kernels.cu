@@ -298,69 +298,7 @@ tps_sample_kernel(const float* __restrict__ fid, const float* __restrict__ inv_d
     }
 }
 
-// ------------------------------------------------------------------------------------------- BiLSTM recurrence
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-constexpr int kLstmG = 8;  // crops per CTA
-
-__global__ void __launch_bounds__(256)
-lstm_kernel(const float* __restrict__ xproj, const uint16_t* __restrict__ whh_t, uint16_t* __restrict__ out, int B,
-            int T, int f16) {
-    __shared__ float hs[kLstmG][256];
-    const int dir = blockIdx.y;
-    const int b0 = blockIdx.x * kLstmG;
-    const int j = threadIdx.x;
-    const uint16_t* wd = whh_t + (size_t)dir * 256 * 256 * 4;
-    float c[kLstmG];
-#pragma unroll
-    for (int g = 0; g < kLstmG; ++g) {
-        c[g] = 0.f;
-        hs[g][j] = 0.f;
-    }
-    __syncthreads();
-    for (int step = 0; step < T; ++step) {
-        const int t = dir == 0 ? step : T - 1 - step;
-        float acc[kLstmG][4];
-#pragma unroll
-        for (int g = 0; g < kLstmG; ++g) {
-            const int b = b0 + g;
-            if (b < B) {
-                const float* xp = xproj + ((long)b * T + t) * 2048 + dir * 1024 + j;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[g][q] = xp[q * 256];
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[g][q] = 0.f;
-            }
-        }
-#pragma unroll 4
-        for (int k = 0; k < 256; ++k) {
-            const uint2 wv = __ldg(reinterpret_cast<const uint2*>(wd + ((size_t)k * 256 + j) * 4));
-            const float w0 = act2f((uint16_t)(wv.x & 0xffff), f16), w1 = act2f((uint16_t)(wv.x >> 16), f16);
-            const float w2 = act2f((uint16_t)(wv.y & 0xffff), f16), w3 = act2f((uint16_t)(wv.y >> 16), f16);
-#pragma unroll
-            for (int g = 0; g < kLstmG; ++g) {
-                const float hv = hs[g][k];
-                acc[g][0] = fmaf(w0, hv, acc[g][0]);
-                acc[g][1] = fmaf(w1, hv, acc[g][1]);
-                acc[g][2] = fmaf(w2, hv, acc[g][2]);
-                acc[g][3] = fmaf(w3, hv, acc[g][3]);
-            }
-        }
-        __syncthreads();  // everyone has consumed h_{t-1}
-#pragma unroll
-        for (int g = 0; g < kLstmG; ++g) {
-            const float ig = sigmoidf_(acc[g][0]), fg = sigmoidf_(acc[g][1]);
-            const float gg = tanhf(acc[g][2]), og = sigmoidf_(acc[g][3]);
-            c[g] = fg * c[g] + ig * gg;
-            const float h = og * tanhf(c[g]);
-            hs[g][j] = h;
-            const int b = b0 + g;
-            if (b < B) out[((long)b * T + t) * 512 + dir * 256 + j] = f2act(h, f16);
-        }
-        __syncthreads();
-    }
-}
 
 // ------------------------------------------------------------------------------------------- attention decoder
 constexpr int kAttG = 4;  // crops per CTA
@@ -650,11 +588,6 @@ void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const fl
 void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,
                        float* grid, int B, cudaStream_t s) {
     tps_sample_kernel<<<B, 256, 0, s>>>(fid, inv_delta_c, p_hat_t, x, out, grid, B);
-}
-
-void launch_lstm(const float* xproj, const void* whh_t, void* out, int B, int T, int is_f16, cudaStream_t s) {
-    dim3 grid((B + kLstmG - 1) / kLstmG, 2);
-    lstm_kernel<<<grid, 256, 0, s>>>(xproj, (const uint16_t*)whh_t, (uint16_t*)out, B, T, is_f16);
 }
 
 void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
