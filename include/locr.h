@@ -127,6 +127,13 @@ typedef struct {
 LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
                             const float* residual, float* y);
 
+/* The BiLSTM recurrence kernel alone (replaces the cuDNN RNN behind nn.LSTM, reference ocr/modules/biLSTM.py:18,24).
+ * xproj [B][T][2048] fp32 = W_ih x + b_ih + b_hh and whh [2][1024][256] fp32 in PyTorch's row order
+ * (direction*1024 + gate*256 + unit, gates i, f, g, o); out [B][T][512] fp32 (forward | backward hidden states).
+ * iters > 0 also times `iters` launches with CUDA events (ms per launch). */
+LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
+                            float* ms_per_iter);
+
 /* CRAFT forward only: bgr uint8 [B][img_h][img_w][3] packed -> score fp32 [B][H32/2][W32/2][2]. */
 LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score);
 /* CRNN forward + decode on already resized crops: u8 [n][32][100] (output of ResizeNormalize's BICUBIC resize). */

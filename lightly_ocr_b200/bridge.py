@@ -37,6 +37,9 @@ def lib():
         _lib.locr_test_conv.restype = C.c_int
         _lib.locr_test_conv.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
+        _lib.locr_test_lstm.restype = C.c_int
+        _lib.locr_test_lstm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.POINTER(C.c_float)]
     return _lib
 
 
@@ -73,6 +76,19 @@ def test_conv(x, w, bias=None, residual=None, *, dil=(1, 1), pad=(0, 0), stride_
         residual = np.ascontiguousarray(residual, np.float32)
     _check(lib().locr_test_conv(C.byref(d), _fptr(x), _fptr(w), _fptr(bias), _fptr(residual), _fptr(y)))
     return y
+
+
+def test_lstm(xproj, whh, act_dtype=0, iters=0):
+    """The BiLSTM recurrence kernel alone: xproj [B,T,2048] fp32 (W_ih x + biases, PyTorch row order), whh [2,1024,256]
+    -> hidden states [B,T,512] fp32 (and ms per launch when iters > 0)."""
+    xproj = np.ascontiguousarray(xproj, np.float32)
+    whh = np.ascontiguousarray(whh, np.float32)
+    B, T, n = xproj.shape
+    assert n == 2048 and whh.shape == (2, 1024, 256)
+    out = np.zeros((B, T, 512), np.float32)
+    ms = C.c_float(0)
+    _check(lib().locr_test_lstm(_fptr(xproj), _fptr(whh), B, T, act_dtype, _fptr(out), iters, C.byref(ms)))
+    return (out, ms.value) if iters > 0 else out
 
 
 class Config(C.Structure):

@@ -394,12 +394,8 @@ int engine_finalize_crnn(locr_handle* h) {
         const HostTensor* bhb = find(h, M, p + "bias_hh_l0_reverse");
         if (!wf || !wb || !hf || !hb || !bif || !bhf || !bib || !bhb) return h->fail(LOCR_ERR_STATE, "missing LSTM tensors");
         const int nin = (int)wf->shape[1];
-        // Row order of the recurrence kernel (lstm_tc.cu): n' = pass*256 + unit_in_pass*4 + gate with
-        // unit = pass*64 + unit_in_pass; PyTorch's order is gate*256 + unit (gates i, f, g, o).
-        auto perm = [](int np) {
-            const int pass = np >> 8, ul = (np & 255) >> 2, gate = np & 3;
-            return gate * 256 + pass * 64 + ul;
-        };
+        // Row order of the recurrence kernel (lstm_tc.cu): n' = unit*4 + gate; PyTorch's is gate*256 + unit (i, f, g, o).
+        auto perm = [](int np) { return (np & 3) * 256 + (np >> 2); };
         HostTensor stacked, sbias;
         stacked.shape = {2048, nin};
         stacked.data.resize((size_t)2048 * nin);
@@ -489,7 +485,6 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     void* vis = c.buf("crnn.visual", (size_t)B * 26 * 512 * 2);
     float* xproj = (float*)c.buf("crnn.xproj", (size_t)B * 26 * 2048 * 4);
     void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * 512 * 2);
-    float* cst = (float*)c.buf("crnn.cstate", lstm_tc_cstate_bytes(B));
     void* s0 = c.buf("crnn.s0", (size_t)B * 26 * 256 * 2);
     void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * 256 * 2);
     const int C = h->cfg.num_classes;
@@ -561,11 +556,11 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     // ---- sequence modelling (model.py:107-112; AdaptiveAvgPool over H=1 is the identity) as [B*26, C] GEMMs
     const int R = B * 26;
     c.tc("lstm0.xproj", vis, 1, 1, R, 512, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[0], cst, hcat, B, 26, f16, s) != cudaSuccess)
+    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s) != cudaSuccess)
         c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, 256, 0, 0, 0);
     c.tc("lstm1.xproj", s0, 1, 1, R, 256, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[1], cst, hcat, B, 26, f16, s) != cudaSuccess)
+    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s) != cudaSuccess)
         c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, 256, 0, 0, 0);
     h->launches += 2;

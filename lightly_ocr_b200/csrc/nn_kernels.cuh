@@ -42,13 +42,11 @@ void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const fl
 void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,
                        float* grid, int B, cudaStream_t s);
 
-// BiLSTM recurrence on the tensor cores (modules/biLSTM.py:18,24; kernel in lstm_tc.cu).
-//   xproj    fp32 [B][T][2048] = x W_ih^T + b_ih + b_hh, column = dir*1024 + pass*256 + unit_in_pass*4 + gate
-//            (unit = pass*64 + unit_in_pass, gate order i, f, g, o)
-//   whh_perm 16-bit [2 dirs * 1024][256], rows in the same (pass, unit, gate) order
-//   cstate   fp32 scratch of lstm_tc_cstate_bytes(B) bytes;  out 16-bit [B][T][512] (forward | backward)
-size_t lstm_tc_cstate_bytes(int B);
-cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, float* cstate, void* out, int B, int T, int is_f16,
+// BiLSTM recurrence (modules/biLSTM.py:18,24): cluster kernel with W_hh resident in shared memory (lstm_tc.cu).
+//   xproj    fp32 [B][T][2048] = x W_ih^T + b_ih + b_hh, column = dir*1024 + unit*4 + gate (gate order i, f, g, o)
+//   whh_perm 16-bit [2 dirs * 1024][256], rows in the same (unit, gate) order
+//   out      16-bit [B][T][512] (forward | backward); also the medium through which the cluster exchanges h_t
+cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, int B, int T, int is_f16,
                            cudaStream_t s);
 
 struct AttnWeights {

@@ -2,6 +2,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "nn_kernels.cuh"
 #include "util.cuh"
 
 namespace locr {
@@ -130,6 +131,59 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
     *ms_per_iter = ms / iters;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return LOCR_OK;
+}
+
+/* The BiLSTM recurrence kernel alone.  xproj [B][T][2048] fp32 and whh [2][1024][256] fp32 come in PyTorch's row order
+ * (dir*1024 + gate*256 + unit); out [B][T][512] fp32.  iters > 0 additionally times `iters` launches (ms per launch). */
+LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
+                            float* ms_per_iter) {
+    if (xproj == nullptr || whh == nullptr || out == nullptr || B <= 0 || T <= 0) return fail(LOCR_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LOCR_ERR_CUDA, "no CUDA device: liblocr has no CPU fallback");
+    const size_t nx = (size_t)B * T * 2048;
+    std::vector<float> xp(nx);
+    std::vector<uint16_t> w16((size_t)2048 * 256);
+    for (int d = 0; d < 2; ++d)
+        for (int np = 0; np < 1024; ++np) {
+            const int r = (np & 3) * 256 + (np >> 2);
+            for (int k = 0; k < 256; ++k)
+                w16[((size_t)d * 1024 + np) * 256 + k] = f32_to_act(whh[((size_t)d * 1024 + r) * 256 + k], act_dtype);
+        }
+    for (size_t row = 0; row < (size_t)B * T; ++row)
+        for (int d = 0; d < 2; ++d)
+            for (int np = 0; np < 1024; ++np)
+                xp[row * 2048 + d * 1024 + np] = xproj[row * 2048 + d * 1024 + (np & 3) * 256 + (np >> 2)];
+    DevBuf dx, dw, dy;
+    const size_t ny = (size_t)B * T * 512;
+    LOCR_CUDA_OK(dx.alloc(nx * 4));
+    LOCR_CUDA_OK(dw.alloc(w16.size() * 2));
+    LOCR_CUDA_OK(dy.alloc(ny * 2));
+    LOCR_CUDA_OK(cudaMemcpy(dx.p, xp.data(), nx * 4, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemcpy(dw.p, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemset(dy.p, 0xff, ny * 2));
+    const int f16 = act_dtype == LOCR_ACT_F16 ? 1 : 0;
+    cudaError_t e = launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0);
+    if (e != cudaSuccess) return fail(LOCR_ERR_CUDA, cudaGetErrorString(e));
+    LOCR_CUDA_OK(cudaDeviceSynchronize());
+    std::vector<uint16_t> hy(ny);
+    LOCR_CUDA_OK(cudaMemcpy(hy.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ny; ++i) out[i] = act_to_f32(hy[i], act_dtype);
+    if (iters > 0 && ms_per_iter != nullptr) {
+        cudaEvent_t e0, e1;
+        LOCR_CUDA_OK(cudaEventCreate(&e0));
+        LOCR_CUDA_OK(cudaEventCreate(&e1));
+        LOCR_CUDA_OK(cudaEventRecord(e0, 0));
+        for (int i = 0; i < iters; ++i) launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0);
+        LOCR_CUDA_OK(cudaEventRecord(e1, 0));
+        LOCR_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        LOCR_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_per_iter = ms / iters;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     return LOCR_OK;
 }
 

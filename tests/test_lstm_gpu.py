@@ -1,0 +1,72 @@
+"""Parity of the BiLSTM recurrence kernel (lstm_tc.cu) against torch.nn.LSTM (the module the reference uses,
+ocr/modules/biLSTM.py:18,24) on the same weights and the same precomputed input projections.
+
+Floating point: W_hh and h_t are stored in 16 bits on the GPU (fp32 accumulate, fp32 cell state); the fp32 reference
+sees W_hh rounded to the same 16-bit values, so the remaining difference is the rounding of h_t fed back through 26
+steps.  Tolerance 4e-3 max-abs (fp16) / 3e-2 (bf16) on hidden states in [-1, 1]."""
+import numpy as np
+import pytest
+import torch
+
+
+def _reference(xproj, whh, act):
+    """nn.LSTM forward with W_ih = I folded away: feed xproj as the gate pre-activations from the input side."""
+    B, T, _ = xproj.shape
+    dt = torch.float16 if act == 0 else torch.bfloat16
+    w = torch.from_numpy(whh).to(dt).float()
+    xp = torch.from_numpy(xproj)
+    out = torch.zeros(B, T, 512)
+    for d in range(2):
+        h = torch.zeros(B, 256)
+        c = torch.zeros(B, 256)
+        steps = range(T) if d == 0 else range(T - 1, -1, -1)
+        for t in steps:
+            g = xp[:, t, d * 1024:(d + 1) * 1024] + h @ w[d].T
+            i, f, gg, o = g[:, :256], g[:, 256:512], g[:, 512:768], g[:, 768:]
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out[:, t, d * 256:(d + 1) * 256] = h
+    return out.numpy()
+
+
+def test_reference_matches_nn_lstm():
+    """The hand-rolled loop above IS nn.LSTM(bidirectional=True, batch_first=True)."""
+    torch.manual_seed(0)
+    m = torch.nn.LSTM(64, 256, bidirectional=True, batch_first=True)
+    x = torch.randn(3, 7, 64)
+    with torch.no_grad():
+        want = m(x)[0]
+        xp = torch.cat([x @ m.weight_ih_l0.T + m.bias_ih_l0 + m.bias_hh_l0,
+                        x @ m.weight_ih_l0_reverse.T + m.bias_ih_l0_reverse + m.bias_hh_l0_reverse], 2)
+        whh = torch.stack([m.weight_hh_l0, m.weight_hh_l0_reverse])
+        # fp32 weights: emulate "no rounding" by passing act=None through a float path
+        B, T, _ = xp.shape
+        out = torch.zeros(B, T, 512)
+        for d in range(2):
+            h = torch.zeros(B, 256)
+            c = torch.zeros(B, 256)
+            for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
+                g = xp[:, t, d * 1024:(d + 1) * 1024] + h @ whh[d].T
+                i, f, gg, o = g[:, :256], g[:, 256:512], g[:, 512:768], g[:, 768:]
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                out[:, t, d * 256:(d + 1) * 256] = h
+    assert torch.allclose(out, want, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(1, 26), (37, 26), (128, 26), (129, 5), (300, 26), (700, 26), (5, 1)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_lstm_kernel(B, T, act):
+    from lightly_ocr_b200 import bridge
+    rng = np.random.default_rng(B * 100 + T)
+    xproj = rng.normal(0, 1.5, (B, T, 2048)).astype(np.float32)
+    xproj[0, :, :7] = 60.0                      # saturated gates must not overflow
+    xproj[0, :, 512:519] = -60.0
+    whh = rng.uniform(-1, 1, (2, 1024, 256)).astype(np.float32) / 16
+    got = bridge.test_lstm(xproj, whh, act_dtype=act)
+    want = _reference(xproj, whh, act)
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print("B=%d T=%d act=%d max-abs err %.3g" % (B, T, act, err))
+    assert err < (4e-3 if act == 0 else 3e-2)
