@@ -111,6 +111,9 @@ LOCR_API int locr_timer_stop(locr_handle* h, float* ms);
  * last read (kernel milliseconds, algorithmic FLOPs = 2*M*N*K of the unpadded layers, launches). */
 LOCR_API int locr_profile(locr_handle* h, int enable);
 LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flops, int64_t* conv_launches);
+/* Per-kernel totals accumulated by the locr_profile_read calls since the last call: text lines
+ * "layer-or-kernel-name milliseconds algorithmic-flops launches" (tools/prof_pipeline.py). */
+LOCR_API int locr_profile_layers(locr_handle* h, char* out, int64_t capacity);
 
 /* Kernel launches issued by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 LOCR_API int64_t locr_launch_count(const locr_handle* h);
@@ -126,6 +129,11 @@ typedef struct {
  * y [B,OH,OW,y_pitch] fp32.  Inputs are rounded to the 16-bit activation type on the way in. */
 LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
                             const float* residual, float* y);
+
+/* Same with the fused MaxPool2d(2, 2) of the activated output (vgg_bn.py / resnet50v1.py / TPS_STN.py max-pools that
+ * follow a conv+BN+ReLU): y_pool [B,OH/2,OW/2,Cout] fp32; y may be NULL (only the pooled tensor is written). */
+LOCR_API int locr_test_conv_pool(const locr_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                 float* y_pool);
 
 /* The BiLSTM recurrence kernel alone (replaces the cuDNN RNN behind nn.LSTM, reference ocr/modules/biLSTM.py:18,24).
  * xproj [B][T][2048] fp32 = W_ih x + b_ih + b_hh and whh [2][1024][256] fp32 in PyTorch's row order

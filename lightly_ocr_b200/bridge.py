@@ -37,6 +37,9 @@ def lib():
         _lib.locr_test_conv.restype = C.c_int
         _lib.locr_test_conv.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]
+        _lib.locr_test_conv_pool.restype = C.c_int
+        _lib.locr_test_conv_pool.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
         _lib.locr_test_lstm.restype = C.c_int
         _lib.locr_test_lstm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.POINTER(C.c_float)]
@@ -76,6 +79,23 @@ def test_conv(x, w, bias=None, residual=None, *, dil=(1, 1), pad=(0, 0), stride_
         residual = np.ascontiguousarray(residual, np.float32)
     _check(lib().locr_test_conv(C.byref(d), _fptr(x), _fptr(w), _fptr(bias), _fptr(residual), _fptr(y)))
     return y
+
+
+def test_conv_pool(x, w, bias=None, *, pad=(1, 1), relu=True, act_dtype=0, n_tile=0, want_full=True):
+    """conv + ReLU with the fused MaxPool2d(2, 2): returns (y or None, y_pool [B,OH//2,OW//2,Cout])."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    B, H, W, xp = x.shape
+    Cout, KH, KW, Cin = w.shape
+    OH = H + 2 * pad[0] - (KH - 1)
+    OW = W + 2 * pad[1] - (KW - 1)
+    d = ConvDesc(B, H, W, Cin, Cout, KH, KW, 1, 1, pad[0], pad[1], 1, xp, Cout, int(relu), 0, act_dtype, n_tile)
+    y = np.zeros((B, OH, OW, Cout), np.float32) if want_full else None
+    yp = np.zeros((B, OH // 2, OW // 2, Cout), np.float32)
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, np.float32)
+    _check(lib().locr_test_conv_pool(C.byref(d), _fptr(x), _fptr(w), _fptr(bias), _fptr(y), _fptr(yp)))
+    return y, yp
 
 
 def test_lstm(xproj, whh, act_dtype=0, iters=0):
@@ -347,6 +367,8 @@ def _bind_bench(L):
     L.locr_profile.argtypes = [vp, C.c_int]
     L.locr_profile_read.restype = C.c_int
     L.locr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.locr_profile_layers.restype = C.c_int
+    L.locr_profile_layers.argtypes = [vp, C.c_char_p, C.c_int64]
     L._bench_bound = True
 
 
@@ -417,3 +439,13 @@ class OcrRunner(Pipeline):
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
         _check(self.L.locr_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)), self.h)
         return float(ms.value), float(fl.value), int(n.value)
+
+    def profile_layers(self):
+        """[(name, ms, flops, launches)] accumulated by the profile_read() calls since the last call."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.L.locr_profile_layers(self.h, buf, len(buf)), self.h)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, ms, fl, n = line.rsplit(" ", 3)
+            rows.append((name, float(ms), float(fl), int(n)))
+        return rows

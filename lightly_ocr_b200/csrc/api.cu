@@ -107,18 +107,42 @@ LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flo
     LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
     LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
     double ms = 0, fl = 0;
+    int64_t n = 0;
     for (auto& r : h->prof) {
         float t = 0;
         cudaEventElapsedTime(&t, r.e0, r.e1);
-        ms += t;
-        fl += r.flops;
+        if (r.is_conv) {
+            ms += t;
+            fl += r.flops;
+            ++n;
+        }
+        auto& a = h->prof_layers[r.name];
+        a.ms += t;
+        a.flops += r.flops;
+        a.n += 1;
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
     if (conv_ms) *conv_ms = ms;
     if (conv_flops) *conv_flops = fl;
-    if (conv_launches) *conv_launches = (int64_t)h->prof.size();
+    if (conv_launches) *conv_launches = n;
     h->prof.clear();
+    return LOCR_OK;
+}
+
+/* Per-layer totals accumulated by locr_profile_read since the last call, as text lines "name ms flops launches". */
+LOCR_API int locr_profile_layers(locr_handle* h, char* out, int64_t capacity) {
+    if (h == nullptr || out == nullptr || capacity <= 0) return fail(LOCR_ERR_INVALID, "bad argument");
+    std::string s;
+    char line[256];
+    for (auto& kv : h->prof_layers) {
+        snprintf(line, sizeof(line), "%s %.6f %.0f %lld\n", kv.first.c_str(), kv.second.ms, kv.second.flops,
+                 (long long)kv.second.n);
+        s += line;
+    }
+    h->prof_layers.clear();
+    if ((int64_t)s.size() + 1 > capacity) return h->fail(LOCR_ERR_CAPACITY, "locr_profile_layers: buffer too small");
+    memcpy(out, s.c_str(), s.size() + 1);
     return LOCR_OK;
 }
 

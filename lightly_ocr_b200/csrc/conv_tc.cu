@@ -57,6 +57,8 @@ struct ConvParams {
     int n_chunks;       // n_tile / stage_cols
     int cin_wrap;       // channel coordinate wraps at this value (split-precision inputs), huge when unused
     int split_out;      // write hi / lo halves (split-precision outputs)
+    int pool;           // fused 2x2/2 max-pool of the activated output (TMA-store epilogue only)
+    int skip_full;      // pooled output only
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
@@ -99,7 +101,8 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
 template <int SWZ, int HALVES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_y, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_p,
+               const ConvParams p) {
     constexpr int BLOCK_K = SWZ / 2;      // 16-bit elements per swizzled row
     constexpr int MMAS_PER_STAGE = BLOCK_K / 16;
 
@@ -118,6 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);                       // [256]
     uint8_t* staging = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(bias_s + 256) + 1023) & ~(uintptr_t)1023);                // 2 x [128][stage_rb]
+    uint8_t* pool_staging = staging + 2 * 128 * 128;                                           // 2 x [32][stage_rb]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -125,7 +129,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmap_x);
         ptx::tma_prefetch_desc(&tmap_w);
-        if (p.tma_store) ptx::tma_prefetch_desc(&tmap_y);
+        if (p.tma_store && !p.skip_full) ptx::tma_prefetch_desc(&tmap_y);
+        if (p.pool) ptx::tma_prefetch_desc(&tmap_p);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -250,6 +255,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                        (uint32_t)(p.stage_rb / 16 - 1)) << 4;
             const uint32_t row_off = (uint32_t)row * (uint32_t)p.stage_rb;
             uint32_t chunk_ctr = 0;
+            // fused 2x2 max-pool: thread = (pooled pixel, 16-byte piece); its four source rows of the staged tile
+            const int pool_pr = etid >> 3;
+            const uint32_t pool_piece = (uint32_t)(etid & 7) << 4;
+            const bool pool_active = p.pool && (int)pool_piece < p.stage_rb;
+            uint32_t pool_src[4] = {0, 0, 0, 0}, pool_dst = 0;
+            if (pool_active) {
+                const int pw2 = p.bw >> 1, ph2 = p.bh >> 1;
+                const int qw = pool_pr % pw2, qh = (pool_pr / pw2) % ph2, qb = pool_pr / (pw2 * ph2);
+                const int r00 = (qb * p.bh + 2 * qh) * p.bw + 2 * qw;
+                const int rows[4] = {r00, r00 + 1, r00 + p.bw, r00 + p.bw + 1};
+                const uint32_t msk = (uint32_t)(p.stage_rb / 16 - 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t off = (uint32_t)rows[i] * (uint32_t)p.stage_rb;
+                    pool_src[i] = off + (pool_piece ^ (((off >> 7) & msk) << 4));
+                }
+                const uint32_t offp = (uint32_t)pool_pr * (uint32_t)p.stage_rb;
+                pool_dst = offp + (pool_piece ^ (((offp >> 7) & msk) << 4));
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
@@ -359,12 +383,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             }
                         }
                     }
+                    uint8_t* pbuf = pool_staging + (size_t)((p.split_out ? 0u : chunk_ctr) & 1u) * 32 * p.stage_rb;
+                    uint8_t* pbuf_lo = pool_staging + (size_t)32 * p.stage_rb;
+                    if (p.pool) {
+                        ptx::named_bar_sync(1, 256);   // the whole 128-pixel chunk is staged
+                        if (pool_active) {
+                            float m[8];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 u = *reinterpret_cast<const uint4*>(sbuf + pool_src[i]);
+                                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                                float f[8];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 v2 = unpack2(w4[q], p.is_f16);
+                                    f[2 * q] = v2.x; f[2 * q + 1] = v2.y;
+                                }
+                                if (p.split_out) {   // value = hi + lo, exact in fp32
+                                    const uint4 ul = *reinterpret_cast<const uint4*>(sbuf_lo + pool_src[i]);
+                                    const uint32_t l4[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 v2 = unpack2(l4[q], p.is_f16);
+                                        f[2 * q] += v2.x; f[2 * q + 1] += v2.y;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) m[j] = i == 0 ? f[j] : fmaxf(m[j], f[j]);
+                            }
+                            uint4 hi;
+                            hi.x = pack2(m[0], m[1], p.is_f16); hi.y = pack2(m[2], m[3], p.is_f16);
+                            hi.z = pack2(m[4], m[5], p.is_f16); hi.w = pack2(m[6], m[7], p.is_f16);
+                            *reinterpret_cast<uint4*>(pbuf + pool_dst) = hi;
+                            if (p.split_out) {
+                                const float2 h0 = unpack2(hi.x, p.is_f16), h1 = unpack2(hi.y, p.is_f16);
+                                const float2 h2 = unpack2(hi.z, p.is_f16), h3 = unpack2(hi.w, p.is_f16);
+                                uint4 lo;
+                                lo.x = pack2(m[0] - h0.x, m[1] - h0.y, p.is_f16);
+                                lo.y = pack2(m[2] - h1.x, m[3] - h1.y, p.is_f16);
+                                lo.z = pack2(m[4] - h2.x, m[5] - h2.y, p.is_f16);
+                                lo.w = pack2(m[6] - h3.x, m[7] - h3.y, p.is_f16);
+                                *reinterpret_cast<uint4*>(pbuf_lo + pool_dst) = lo;
+                            }
+                        }
+                    }
                     ptx::fence_proxy_async();
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) {
-                        ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
-                        if (p.split_out)
-                            ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                        if (!p.skip_full) {
+                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                            if (p.split_out)
+                                ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                        }
+                        if (p.pool) {
+                            ptx::tma_store_4d(&tmap_p, pbuf, t.n0 + c * p.stage_cols, t.ow0 >> 1, oh0 >> 1, b0);
+                            if (p.split_out)
+                                ptx::tma_store_4d(&tmap_p, pbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0 >> 1, oh0 >> 1, b0);
+                        }
                         ptx::tma_store_commit();
                     }
                     ++chunk_ctr;
@@ -484,8 +559,8 @@ void set_err(char* err, int errlen, const char* msg) {
 }
 
 template <int SWZ, int HALVES>
-cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& p,
-                       int grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mp,
+                       const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -493,7 +568,7 @@ cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUten
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ, HALVES><<<grid, kThreads, smem, stream>>>(mx, mw, my, p);
+    conv_tc_kernel<SWZ, HALVES><<<grid, kThreads, smem, stream>>>(mx, mw, my, mp, p);
     return cudaGetLastError();
 }
 
@@ -554,6 +629,11 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     // An M = 256 tile is two such patches stacked along b (if the patch spans several images) or along h.  It is used
     // for n_tile <= 128: one TMA instruction then feeds two independent accumulators, which amortises the fixed
     // per-instruction cost of the producer and hides the latency of back-to-back MMAs into one accumulator.
+    const int pool = c.pool_y != nullptr ? 1 : 0;
+    if (pool && (c.out_fp32 || c.stride_h != 1)) {
+        set_err(err, errlen, "conv_tc: fused max-pool needs a 16-bit, stride-1 output");
+        return cudaErrorInvalidValue;
+    }
     auto search = [&](int rows, int& obw, int& obh, int& obb) {
         long best = -1;
         for (int bw = rows > 256 ? 256 : rows; bw >= 1; bw >>= 1) {
@@ -561,6 +641,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                 const int bb = rows / (bw * bh);
                 if (bw > 256 || bh > 256 || bb > 256) continue;
                 if (rows == 256 && !((bb > 1) || (bh > 1))) continue;   // must split into two 128-pixel halves
+                // fused 2x2 pooling: every 128-pixel half must hold whole 2x2 windows
+                if (pool && (bw < 2 || (rows == 256 && bb == 1 ? bh < 4 : bh < 2))) continue;
                 const long tiles = (long)((c.OW + bw - 1) / bw) * ((c.OH + bh - 1) / bh) * ((c.B + bb - 1) / bb);
                 if (best < 0 || tiles < best) {
                     best = tiles;
@@ -630,13 +712,19 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.tma_store = ((c.y_pitch * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
                    n_tile % p.stage_cols == 0 && (p.stage_rb == 32 || p.stage_rb == 64 || p.stage_rb == 128))
                       ? 1 : 0;
-    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 1024 + 2 * 128 * 128;
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 1024 + 2 * 128 * 128 + (pool ? 2 * 32 * 128 : 0);
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, kTileM, n_tile);
+    p.pool = pool;
+    p.skip_full = (pool && c.skip_full) ? 1 : 0;
+    if (pool && !p.tma_store) {
+        set_err(err, errlen, "conv_tc: fused max-pool needs the TMA-store epilogue (aligned 16-bit output)");
+        return cudaErrorInvalidValue;
+    }
     p.y = c.y; p.y_pitch = c.y_pitch; p.out_fp32 = c.out_fp32;
     p.res = c.residual; p.res_pitch = c.res_pitch;
     p.bias = c.bias; p.relu = c.relu; p.is_f16 = (c.dtype == ACT_F16) ? 1 : 0;
@@ -691,7 +779,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
 
     CUtensorMap my;
     memset(&my, 0, sizeof(my));
-    if (p.tma_store) {
+    if (p.tma_store && !p.skip_full) {
         const cuuint64_t eb = (cuuint64_t)elem;
         cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)c.OW, (cuuint64_t)c.OH,
                               (cuuint64_t)c.B};
@@ -712,17 +800,43 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
             return cudaErrorInvalidValue;
         }
     }
+    CUtensorMap mp;
+    memset(&mp, 0, sizeof(mp));
+    if (pool) {
+        const int PH = c.OH / 2, PW = c.OW / 2;
+        if (PH < 1 || PW < 1 || (c.pool_pitch * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(c.pool_y) % 16) != 0) {
+            set_err(err, errlen, "conv_tc: bad pooled output");
+            return cudaErrorInvalidValue;
+        }
+        cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)PW, (cuuint64_t)PH,
+                              (cuuint64_t)c.B};
+        const cuuint64_t pb = (cuuint64_t)c.pool_pitch * 2;
+        cuuint64_t strides[3] = {pb, pb * PW, pb * PW * PH};
+        cuuint32_t box[4] = {(cuuint32_t)p.stage_cols, (cuuint32_t)(p.bw / 2), (cuuint32_t)(p.bh / 2), (cuuint32_t)p.bb};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUtensorMapSwizzle psw = p.stage_rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                         : (p.stage_rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                             : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = encode(&mp, dt, 4, c.pool_y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, psw,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[160];
+            snprintf(msg, sizeof(msg), "conv_tc: pooled tensor map encode failed (CUresult %d)", (int)r);
+            set_err(err, errlen, msg);
+            return cudaErrorInvalidValue;
+        }
+    }
     const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
     if (halves == 2) {
-        if (swz == 128) e = launch_swz<128, 2>(mx, mw, my, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 2>(mx, mw, my, p, grid, smem, stream);
-        else e = launch_swz<32, 2>(mx, mw, my, p, grid, smem, stream);
+        if (swz == 128) e = launch_swz<128, 2>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 2>(mx, mw, my, mp, p, grid, smem, stream);
+        else e = launch_swz<32, 2>(mx, mw, my, mp, p, grid, smem, stream);
     } else {
-        if (swz == 128) e = launch_swz<128, 1>(mx, mw, my, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 1>(mx, mw, my, p, grid, smem, stream);
-        else e = launch_swz<32, 1>(mx, mw, my, p, grid, smem, stream);
+        if (swz == 128) e = launch_swz<128, 1>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 1>(mx, mw, my, mp, p, grid, smem, stream);
+        else e = launch_swz<32, 1>(mx, mw, my, mp, p, grid, smem, stream);
     }
     if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
     return e;

@@ -33,6 +33,11 @@ struct ConvCall {
     // channels [c] and [C + c] of a 2C-channel tensor (~22 significant bits).
     int cin_wrap = 0;   // > 0: the K channels of a tap are [hi | lo | hi] = 3C, read from a tensor of cin_wrap = 2C channels
     int split_out = 0;  // 1: write hi to channel n and lo to channel Cout + n of a 2*Cout-channel output
+    // Fused MaxPool2d(2, 2) of the activated output (nn.MaxPool2d(kernel_size=2, stride=2) right after the conv's ReLU
+    // in vgg16_bn / ResNet / LocalizationNetwork): pooled tensor [B][OH/2][OW/2][Cout] with channel pitch pool_pitch.
+    void* pool_y = nullptr;
+    long pool_pitch = 0;
+    int skip_full = 0;  // 1: only the pooled tensor is written (y may be null)
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).

@@ -135,6 +135,11 @@ void dbg(locr_handle* h, const std::string& name, const void* p, int kind, std::
 struct Ctx {
     locr_handle* h;
     int rc = LOCR_OK;
+    // fused MaxPool2d(2, 2) request for the NEXT tc() call (consumed by it)
+    void* pool_y = nullptr;
+    long pool_pitch = 0;
+    int pool_only = 0;
+    void pool(void* y, long pitch, int only) { pool_y = y; pool_pitch = pitch; pool_only = only; }
     // y = act(conv(x)) through the tensor-core kernel.  Shapes are those of the INPUT; returns output dims.
     void tc(const std::string& layer, const void* x, int B, int H, int W, long x_pitch, void* y, long y_pitch, int relu,
             int pad_h, int pad_w, int dil = 1, int stride_h = 1, int out_fp32 = 0, const void* res = nullptr,
@@ -158,18 +163,13 @@ struct Ctx {
         c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
         c.cin_wrap = cw.cin_wrap;
         c.split_out = split_out;
+        c.pool_y = pool_y; c.pool_pitch = pool_pitch; c.skip_full = pool_only;
+        pool_y = nullptr; pool_pitch = 0; pool_only = 0;
         char err[256] = {0};
-        locr_handle::ProfRec pr;
-        if (h->profile) {
-            cudaEventCreate(&pr.e0);
-            cudaEventCreate(&pr.e1);
-            pr.flops = 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin_real * cw.kh * cw.kw;
-            cudaEventRecord(pr.e0, h->stream);
-        }
-        cudaError_t e = conv_tc_launch(c, h->stream, err, sizeof(err));
-        if (h->profile) {
-            cudaEventRecord(pr.e1, h->stream);
-            h->prof.push_back(pr);
+        cudaError_t e;
+        {
+            ProfScope ps(h, layer, 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin_real * cw.kh * cw.kw, true);
+            e = conv_tc_launch(c, h->stream, err, sizeof(err));
         }
         h->launches++;
         if (e != cudaSuccess) rc = h->fail(LOCR_ERR_CUDA, layer + ": " + err);
@@ -241,18 +241,15 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     cudaStream_t s = h->stream;
     const size_t px = (size_t)B * H * W;
     void* a0 = c.buf("a0", px * 64 * 2);
-    void* a1 = c.buf("a1", px * 64 * 2);
     void* p1 = c.buf("p1", px / 4 * 64 * 2);
     void* a2 = c.buf("a2", px / 4 * 128 * 2);
     uint16_t* cat4 = (uint16_t*)c.buf("cat4", px / 4 * 192 * 2);
     void* p2 = c.buf("p2", px / 16 * 128 * 2);
     void* a3 = c.buf("a3", px / 16 * 256 * 2);
     uint16_t* cat3 = (uint16_t*)c.buf("cat3", px / 16 * 384 * 2);
-    void* a4 = c.buf("a4", px / 16 * 256 * 2);
     void* p3 = c.buf("p3", px / 64 * 256 * 2);
     void* a5 = c.buf("a5", px / 64 * 512 * 2);
     uint16_t* cat2 = (uint16_t*)c.buf("cat2", px / 64 * 768 * 2);
-    void* a6 = c.buf("a6", px / 64 * 512 * 2);
     void* p4 = c.buf("p4", px / 256 * 512 * 2);
     void* a7 = c.buf("a7", px / 256 * 512 * 2);
     uint16_t* cat1 = (uint16_t*)c.buf("cat1", px / 256 * 1536 * 2);
@@ -276,38 +273,38 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
 
     void* x16 = c.buf("x16", px * 16 * 2);
     if (c.rc != LOCR_OK) return c.rc;
-    launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s);
+    { ProfScope ps_(h, "preproc_nhwc16", 0, false); launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s); }
     h->launches++;
     c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 1);
-    c.tc("basenet.slice1.3", a0, B, H, W, 64, a1, 64, 1, 1, 1);
-    launch_maxpool(a1, 64, B, H, W, 64, p1, 64, 2, 2, 2, 2, 0, 0, f16, s);
+    c.pool(p1, 64, 1);   // MaxPool2d(2, 2) fused into the epilogue; the full-resolution tensor is never needed
+    c.tc("basenet.slice1.3", a0, B, H, W, 64, nullptr, 64, 1, 1, 1);
     c.tc("basenet.slice1.7", p1, B, H2, W2, 64, a2, 128, 1, 1, 1);
     // relu2_2: the reference's slice ends on the BN, the next slice's in-place ReLU rectifies the tap as well
+    c.pool(p2, 128, 0);
     c.tc("basenet.slice1.10", a2, B, H2, W2, 128, cat4 + 64, 192, 1, 1, 1);
-    launch_maxpool(cat4 + 64, 192, B, H2, W2, 128, p2, 128, 2, 2, 2, 2, 0, 0, f16, s);
     c.tc("basenet.slice2.14", p2, B, H4, W4, 128, a3, 256, 1, 1, 1);
     c.tc("basenet.slice2.17", a3, B, H4, W4, 256, cat3 + 128, 384, 1, 1, 1);               // relu3_2
-    c.tc("basenet.slice3.20", cat3 + 128, B, H4, W4, 384, a4, 256, 1, 1, 1);
-    launch_maxpool(a4, 256, B, H4, W4, 256, p3, 256, 2, 2, 2, 2, 0, 0, f16, s);
+    c.pool(p3, 256, 1);
+    c.tc("basenet.slice3.20", cat3 + 128, B, H4, W4, 384, nullptr, 256, 1, 1, 1);
     c.tc("basenet.slice3.24", p3, B, H8, W8, 256, a5, 512, 1, 1, 1);
     c.tc("basenet.slice3.27", a5, B, H8, W8, 512, cat2 + 256, 768, 1, 1, 1);               // relu4_3
-    c.tc("basenet.slice4.30", cat2 + 256, B, H8, W8, 768, a6, 512, 1, 1, 1);
-    launch_maxpool(a6, 512, B, H8, W8, 512, p4, 512, 2, 2, 2, 2, 0, 0, f16, s);
+    c.pool(p4, 512, 1);
+    c.tc("basenet.slice4.30", cat2 + 256, B, H8, W8, 768, nullptr, 512, 1, 1, 1);
     c.tc("basenet.slice4.34", p4, B, H16, W16, 512, a7, 512, 1, 1, 1);
     // relu5_3 keeps its negatives: slice5 starts with a non-in-place max-pool (vgg_bn.py:54)
     c.tc("basenet.slice4.37", a7, B, H16, W16, 512, cat1 + 1024, 1536, 0, 1, 1);
-    launch_maxpool(cat1 + 1024, 1536, B, H16, W16, 512, p5, 512, 3, 3, 1, 1, 1, 1, f16, s);
+    { ProfScope ps_(h, "maxpool.craft5_3x3", 0, false); launch_maxpool(cat1 + 1024, 1536, B, H16, W16, 512, p5, 512, 3, 3, 1, 1, 1, 1, f16, s); }
     c.tc("basenet.slice5.1", p5, B, H16, W16, 512, a8, 1024, 0, 6, 6, 6);
     c.tc("basenet.slice5.2", a8, B, H16, W16, 1024, cat1, 1536, 0, 0, 0);                  // fc7
     c.tc("upconv1.conv.0", cat1, B, H16, W16, 1536, u1a, 512, 1, 0, 0);
     c.tc("upconv1.conv.3", u1a, B, H16, W16, 512, y1, 256, 1, 1, 1);
-    launch_upsample2x(y1, 256, B, H16, W16, 256, cat2, 768, f16, s);
+    { ProfScope ps_(h, "upsample.1", 0, false); launch_upsample2x(y1, 256, B, H16, W16, 256, cat2, 768, f16, s); }
     c.tc("upconv2.conv.0", cat2, B, H8, W8, 768, u2a, 256, 1, 0, 0);
     c.tc("upconv2.conv.3", u2a, B, H8, W8, 256, y2, 128, 1, 1, 1);
-    launch_upsample2x(y2, 128, B, H8, W8, 128, cat3, 384, f16, s);
+    { ProfScope ps_(h, "upsample.2", 0, false); launch_upsample2x(y2, 128, B, H8, W8, 128, cat3, 384, f16, s); }
     c.tc("upconv3.conv.0", cat3, B, H4, W4, 384, u3a, 128, 1, 0, 0);
     c.tc("upconv3.conv.3", u3a, B, H4, W4, 128, y3, 64, 1, 1, 1);
-    launch_upsample2x(y3, 64, B, H4, W4, 64, cat4, 192, f16, s);
+    { ProfScope ps_(h, "upsample.3", 0, false); launch_upsample2x(y3, 64, B, H4, W4, 64, cat4, 192, f16, s); }
     c.tc("upconv4.conv.0", cat4, B, H2, W2, 192, u4a, 64, 1, 0, 0);
     c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat, 32, 1, 1, 1);
     c.tc("conv_cls.0", feat, B, H2, W2, 32, c0, 32, 1, 1, 1);
@@ -315,7 +312,7 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     c.tc("conv_cls.4", c2, B, H2, W2, 32, c4, 16, 1, 1, 1);
     c.tc("conv_cls.6", c4, B, H2, W2, 16, c6, 16, 1, 0, 0);
     c.tc("conv_cls.8", c6, B, H2, W2, 16, sc, 2, 0, 0, 0, 1, 1, /*out_fp32=*/1);
-    h->launches += 8;  // 5 max-pools + 3 up-samplings
+    h->launches += 4;  // 1 max-pool (3x3 s1) + 3 up-samplings
     if (c.rc != LOCR_OK) return c.rc;
     LOCR_CUDA_OK(cudaGetLastError());
     dbg(h, "slice1.0", a0, 0, {B, H, W, 64}, 64);
@@ -493,26 +490,26 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
 
     // ---- TPS localisation network (TPS_STN.py:38-58), split precision: tensors hold [hi | lo] channel halves
     const ConvW& l0 = h->conv[loc + "conv.0"];
-    launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 128, 1, f16, s, 1);
-    launch_maxpool(sA, 128, B, 32, 100, 64, sB, 128, 2, 2, 2, 2, 0, 0, f16, s, 1);
-    c.tc(loc + "conv.4", sB, B, 16, 50, 128, sA, 256, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
-    launch_maxpool(sA, 256, B, 16, 50, 128, sB, 256, 2, 2, 2, 2, 0, 0, f16, s, 1);
-    c.tc(loc + "conv.8", sB, B, 8, 25, 256, sA, 512, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
-    launch_maxpool(sA, 512, B, 8, 25, 256, sB, 512, 2, 2, 2, 2, 0, 0, f16, s, 1);
+    { ProfScope ps_(h, "direct_conv.loc0", 0, false); launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 128, 1, f16, s, 1); }
+    { ProfScope ps_(h, "maxpool.loc1", 0, false); launch_maxpool(sA, 128, B, 32, 100, 64, sB, 128, 2, 2, 2, 2, 0, 0, f16, s, 1); }
+    c.pool(sC, 256, 1);
+    c.tc(loc + "conv.4", sB, B, 16, 50, 128, nullptr, 256, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
+    c.pool(sB, 512, 1);
+    c.tc(loc + "conv.8", sC, B, 8, 25, 256, nullptr, 512, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
     c.tc(loc + "conv.12", sB, B, 4, 12, 512, sA, 1024, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
-    launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s, 1);
-    launch_tps_sample(fid, h->f32["tps.inv"], h->f32["tps.phat_t"], d_x, xr, grid, B, s);
-    h->launches += 6;
+    { ProfScope ps_(h, "loc_head", 0, false); launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s, 1); }
+    { ProfScope ps_(h, "tps_sample", 0, false); launch_tps_sample(fid, h->f32["tps.inv"], h->f32["tps.phat_t"], d_x, xr, grid, B, s); }
+    h->launches += 4;
 
     // ---- ResNet feature extractor (resnet50v1.py:101-135)
     const ConvW& r0 = h->conv[fe + "conv0_1"];
-    launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, sA, 32, 1, f16, s);
-    c.tc(fe + "conv0_2", sA, B, 32, 100, 32, sB, 64, 1, 1, 1);
-    launch_maxpool(sB, 64, B, 32, 100, 64, sA, 64, 2, 2, 2, 2, 0, 0, f16, s);
-    h->launches += 2;
+    { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, sA, 32, 1, f16, s); }
+    c.pool(sB, 64, 1);
+    c.tc(fe + "conv0_2", sA, B, 32, 100, 32, nullptr, 64, 1, 1, 1);
+    h->launches += 1;
     // x lives in `cur`; BasicBlock (resnet50v1.py:33-48): relu(bn2(conv2(relu(bn1(conv1 x)))) + residual)
-    void* cur = sA;
-    void* other = sB;
+    void* cur = sB;
+    void* other = sA;
     int Hc = 16, Wc = 50, Cc = 64;
     const int nblocks[5] = {0, 1, 2, 5, 3};
     const int planes[5] = {0, 128, 256, 512, 512};
@@ -539,10 +536,10 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
         }
         if (l == 1 || l == 2) {
             if (l == 1) {
-                launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 2, 0, 0, f16, s);
+                { ProfScope ps_(h, "maxpool.res1", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 2, 0, 0, f16, s); }
                 Hc /= 2; Wc /= 2;
             } else {
-                launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s);  // k2 s(2,1) p(0,1)
+                { ProfScope ps_(h, "maxpool.res2", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s); }
                 Hc = (Hc - 2) / 2 + 1; Wc = Wc + 2 - 2 + 1;
             }
             h->launches++;
@@ -556,12 +553,18 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     // ---- sequence modelling (model.py:107-112; AdaptiveAvgPool over H=1 is the identity) as [B*26, C] GEMMs
     const int R = B * 26;
     c.tc("lstm0.xproj", vis, 1, 1, R, 512, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s) != cudaSuccess)
-        c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
+    if (c.rc == LOCR_OK) {
+        ProfScope ps_(h, "lstm", 0, false);
+        if (launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s) != cudaSuccess)
+            c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
+    }
     c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, 256, 0, 0, 0);
     c.tc("lstm1.xproj", s0, 1, 1, R, 256, xproj, 2048, 0, 0, 0, 1, 1, 1);
-    if (c.rc == LOCR_OK && launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s) != cudaSuccess)
-        c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
+    if (c.rc == LOCR_OK) {
+        ProfScope ps_(h, "lstm", 0, false);
+        if (launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s) != cudaSuccess)
+            c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
+    }
     c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, 256, 0, 0, 0);
     h->launches += 2;
     if (h->cfg.head == LOCR_HEAD_CTC) {
@@ -574,7 +577,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
             w.h2h_wt = h->f32["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
             w.wih_t = h->f32["att.wih_t"]; w.whh_t = h->f32["att.whh_t"]; w.gate_b = h->f32["att.gate_b"];
             w.gen_w = h->f32["att.gen_w"]; w.gen_b = h->f32["att.gen_b"];
-            launch_attention(s1, fproj, w, lg, B, C, f16, s);
+            { ProfScope ps_(h, "attention", 0, false); launch_attention(s1, fproj, w, lg, B, C, f16, s); }
             h->launches++;
         }
     }

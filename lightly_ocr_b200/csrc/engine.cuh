@@ -61,8 +61,10 @@ struct locr_handle {
     std::vector<void*> owned;  // weight allocations
     // per-launch profiling of the tensor-core conv kernel (bench.py roofline): event pairs + algorithmic FLOPs
     bool profile = false;
-    struct ProfRec { cudaEvent_t e0, e1; double flops; };
+    struct ProfRec { cudaEvent_t e0, e1; double flops; std::string name; bool is_conv; };
     std::vector<ProfRec> prof;
+    struct ProfAgg { double ms = 0, flops = 0; int64_t n = 0; };
+    std::map<std::string, ProfAgg> prof_layers;  // per-layer totals accumulated by locr_profile_read
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 
     int fail(int code, const std::string& m) {
@@ -74,6 +76,25 @@ struct locr_handle {
 };
 
 namespace locr {
+
+// Brackets one kernel launch with CUDA events on the handle's stream while profiling is enabled.
+struct ProfScope {
+    locr_handle* h;
+    locr_handle::ProfRec r;
+    bool on;
+    ProfScope(locr_handle* h_, const std::string& name, double flops, bool is_conv) : h(h_), on(h_->profile) {
+        if (!on) return;
+        r.name = name; r.flops = flops; r.is_conv = is_conv;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, h->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.e1, h->stream);
+        h->prof.push_back(r);
+    }
+};
 
 int engine_finalize_craft(locr_handle* h);
 int engine_finalize_crnn(locr_handle* h);

@@ -56,7 +56,8 @@ int run_crnn_and_decode(locr_handle* h, const float* d_x, int n, float* logits, 
     int32_t* d_eos = (int32_t*)engine_buffer(h, "dec.eos", (size_t)n * 4);
     float* d_conf = (float*)engine_buffer(h, "dec.conf", (size_t)n * 4);
     if (!d_ids || !d_text || !d_eos || !d_conf) return h->fail(LOCR_ERR_CUDA, "allocation failed");
-    launch_decode(lg, n, C, h->cfg.head == LOCR_HEAD_ATTN, d_ids, d_text, kTextStride, d_eos, d_conf, h->stream);
+    { ProfScope ps_(h, "decode", 0, false);
+    launch_decode(lg, n, C, h->cfg.head == LOCR_HEAD_ATTN, d_ids, d_text, kTextStride, d_eos, d_conf, h->stream); }
     h->launches++;
     LOCR_CUDA_OK(cudaGetLastError());
     cudaStream_t s = h->stream;
@@ -92,7 +93,7 @@ int run_crops(locr_handle* h, std::vector<CropDesc>& descs, float* logits, int32
     if (!hd) return h->fail(LOCR_ERR_CUDA, "pinned allocation failed");
     memcpy(hd, descs.data(), (size_t)n * sizeof(CropDesc));
     LOCR_CUDA_OK(cudaMemcpyAsync(d_desc, hd, (size_t)n * sizeof(CropDesc), cudaMemcpyHostToDevice, h->stream));
-    launch_crop_resize(d_desc, n, d_coef, d_inter, d_x, d_u8, h->stream);
+    { ProfScope ps_(h, "crop_resize", 0, false); launch_crop_resize(d_desc, n, d_coef, d_inter, d_x, d_u8, h->stream); }
     h->launches++;
     {
         DebugTensor dt;
@@ -161,7 +162,8 @@ static int detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, 
         pp.scale_x = inv * 2;
         pp.scale_y = inv * 2;
         pp.max_boxes = cap;
-        const int nl = launch_postproc(sc, pp, ws, d_boxes, d_rects, d_lab, d_counts, nullptr, s);
+        int nl;
+        { ProfScope ps_(h, "postproc", 0, false); nl = launch_postproc(sc, pp, ws, d_boxes, d_rects, d_lab, d_counts, nullptr, s); }
         if (nl < 0) return h->fail(LOCR_ERR_INVALID, "locr_detect: score map larger than 1024 x 1024");
         h->launches += nl;
         LOCR_CUDA_OK(cudaGetLastError());

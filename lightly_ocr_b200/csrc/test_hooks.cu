@@ -24,9 +24,10 @@ extern "C" {
 
 LOCR_API const char* locr_version(void) { return "liblocr 0.1 (sm_100a)"; }
 
-LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
-                            const float* residual, float* y) {
-    if (d == nullptr || x == nullptr || w == nullptr || y == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
+static int test_conv_impl(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
+                          const float* residual, float* y, float* y_pool) {
+    if (d == nullptr || x == nullptr || w == nullptr || (y == nullptr && y_pool == nullptr))
+        return fail(LOCR_ERR_INVALID, "null argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(LOCR_ERR_CUDA, "no CUDA device: liblocr has no CPU fallback");
@@ -74,18 +75,47 @@ LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float
     c.bias = db.as<float>();
     c.residual = residual ? dr.p : nullptr; c.res_pitch = d->Cout;
     c.relu = d->relu; c.dtype = d->act_dtype; c.n_tile = d->n_tile;
+    DevBuf dp;
+    const size_t np_ = (size_t)d->B * (OH / 2) * (OW / 2) * d->Cout;
+    if (y_pool != nullptr) {
+        LOCR_CUDA_OK(dp.alloc(np_ * 2));
+        LOCR_CUDA_OK(cudaMemset(dp.p, 0, np_ * 2));
+        c.pool_y = dp.p;
+        c.pool_pitch = d->Cout;
+        c.skip_full = y == nullptr ? 1 : 0;
+        if (y == nullptr) c.y = nullptr;
+    }
     char err[256] = {0};
     cudaError_t e = conv_tc_launch(c, 0, err, sizeof(err));
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? LOCR_ERR_INVALID : LOCR_ERR_CUDA, err);
     LOCR_CUDA_OK(cudaDeviceSynchronize());
-    if (d->out_fp32) {
-        LOCR_CUDA_OK(cudaMemcpy(y, dy.p, ny * 4, cudaMemcpyDeviceToHost));
-    } else {
-        std::vector<uint16_t> hy(ny);
-        LOCR_CUDA_OK(cudaMemcpy(hy.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < ny; ++i) y[i] = act_to_f32(hy[i], d->act_dtype);
+    if (y != nullptr) {
+        if (d->out_fp32) {
+            LOCR_CUDA_OK(cudaMemcpy(y, dy.p, ny * 4, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> hy(ny);
+            LOCR_CUDA_OK(cudaMemcpy(hy.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < ny; ++i) y[i] = act_to_f32(hy[i], d->act_dtype);
+        }
+    }
+    if (y_pool != nullptr) {
+        std::vector<uint16_t> hy(np_);
+        LOCR_CUDA_OK(cudaMemcpy(hy.data(), dp.p, np_ * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < np_; ++i) y_pool[i] = act_to_f32(hy[i], d->act_dtype);
     }
     return LOCR_OK;
+}
+
+LOCR_API int locr_test_conv(const locr_conv_desc* d, const float* x, const float* w, const float* bias,
+                            const float* residual, float* y) {
+    return test_conv_impl(d, x, w, bias, residual, y, nullptr);
+}
+
+/* Same with the fused MaxPool2d(2, 2): y_pool [B, OH/2, OW/2, Cout] fp32; y may be NULL (pooled output only). */
+LOCR_API int locr_test_conv_pool(const locr_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                 float* y_pool) {
+    if (y_pool == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
+    return test_conv_impl(d, x, w, bias, nullptr, y, y_pool);
 }
 
 /* Times `iters` back-to-back launches of one conv layer on uninitialised (zeroed) device buffers. */

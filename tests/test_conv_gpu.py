@@ -75,3 +75,37 @@ def test_conv_parity(case):
     assert err <= tol, "%s: max abs err %g > tol %g (scale %g)" % (name, err, tol, scale)
     if y_extra:
         assert np.all(y[..., Cout:] == 0), "kernel wrote outside its channel view"
+
+
+POOL_CASES = [
+    # name, B, H, W, Cin, Cout, act, n_tile   (conv3x3 p1 + ReLU + MaxPool2d(2,2), the vgg / ResNet / TPS pattern)
+    ("vgg_c64", 1, 64, 96, 64, 64, 0, 0),
+    ("vgg_c128_m256", 2, 96, 128, 64, 128, 0, 0),
+    ("vgg_c256", 1, 40, 24, 128, 256, 0, 0),
+    ("vgg_c512_n256", 1, 20, 12, 64, 512, 1, 0),
+    ("crnn_32x100", 6, 32, 100, 32, 64, 0, 0),
+    ("crnn_16x50_odd_w", 9, 16, 50, 128, 128, 0, 0),
+    ("odd_hw", 3, 9, 25, 64, 64, 1, 0),
+    ("c32_sw64", 2, 16, 36, 32, 32, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=[c[0] for c in POOL_CASES])
+@pytest.mark.parametrize("want_full", [True, False])
+def test_conv_fused_maxpool(case, want_full):
+    """Pooled output == max_pool2d(kernel's own full-resolution output), bit for bit (max commutes with rounding),
+    and the full-resolution output is unchanged by the fusion."""
+    from lightly_ocr_b200 import bridge
+    name, B, H, W, Cin, Cout, act, n_tile = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    x = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+    w = (rng.standard_normal((Cout, 3, 3, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    plain = bridge.test_conv(x, w, bias, None, pad=(1, 1), relu=True, out_fp32=False, act_dtype=act, n_tile=n_tile)
+    y, yp = bridge.test_conv_pool(x, w, bias, pad=(1, 1), relu=True, act_dtype=act, n_tile=n_tile, want_full=want_full)
+    want = F.max_pool2d(torch.from_numpy(plain).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()
+    assert yp.shape == want.shape
+    assert np.array_equal(yp, want), "%s: %d pooled values differ" % (name, int((yp != want).sum()))
+    if want_full:
+        assert np.array_equal(y, plain)
