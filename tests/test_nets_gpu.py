@@ -5,11 +5,12 @@ Tolerances (floating point; north_star: score maps and logits within 1e-2 max-ab
   * CRAFT score maps: 1e-2 max-abs against the fp32 oracle with fp16 storage (measured 4.6e-3; maps span [-0.2, 3]).
     bf16 storage measures 3.4e-2 and does NOT meet the gate on random-init weights (SURVEY.md 7.4 predicted 4e-2 to
     6e-2), which is why fp16 is the default activation type; the bf16 case is kept as a bounded regression check.
-  * CRNN logits: the synthetic prediction head whitens the 37 leading principal directions of the contextual
-    features to logit std ~3 (oracle/weights.py), which amplifies 16-bit storage noise of the features by up to
-    ~60x.  Measured with fp16: max-abs 0.53 at std 2.95, arg-max agreement 99.2%.  The 1e-2 absolute gate is NOT met
-    on this recipe ("precision"); the test bounds the error at 0.25 * std and the arg-max agreement at
-    98%, and pins every intermediate (fiducials, rectified crop, visual and contextual features) layer-wise.
+  * CRNN logits: the default CTC checkpoint has a trained read-out (tools/train_synth_crnn.py) and therefore logits
+    of a trained recogniser's scale: std ~7.7, |logit| up to ~40.  Measured with fp16 storage: max-abs 0.092 (0.23% of
+    the logit range, 1.2% of the std), arg-max agreement 99.9%.  An absolute 1e-2 would need logits of unit scale;
+    the test bounds the error at 3% of the logit std (fp16), the arg-max agreement at 99.5%, and pins every
+    intermediate (fiducials, rectified crop, visual and contextual features) layer-wise.  The string gate of the
+    north star (>= 99.5% identical strings end to end) is tested in test_pipeline_gpu.py.
   * integer results (token ids, strings, confidences) are compared exactly GIVEN the CUDA logits (decode parity).
 """
 import os
@@ -75,7 +76,7 @@ def test_crnn_logits_and_decode(oracle_mods, act, head):
     with torch.no_grad():
         x = torch.cat([ocr_ref.crop_to_tensor(g)[1] for g in crops], 0)
         ref = ocr_ref.crnn_forward(sd, x, head, taps).numpy()
-    for name, tol in (("fiducials", 1e-3), ("rectified", 3e-2), ("visual", 5e-2), ("contextual", 5e-2)):
+    for name, tol in (("fiducials", 1e-4), ("rectified", 5e-3), ("visual", 1e-2), ("contextual", 1e-2)):
         g = eng.debug_read(name)
         r = taps[name].numpy().reshape(g.shape)
         rel = np.abs(g - r).max() / max(np.abs(r).max(), 1e-6)
@@ -110,8 +111,8 @@ def test_crnn_logits_and_decode(oracle_mods, act, head):
         same = np.mean([out["text"][i] == ocr_ref.ctc_decode(ref[i].argmax(1)) for i in range(len(crops))])
         print("%s CTC logits max-abs err %.4g (std %.3f), argmax agreement %.4f, string agreement %.3f" %
               (act, err, ref.std(), agree, same))
-        assert err < 0.25 * scale * (1 if act == "f16" else 8)
-        assert agree > (0.98 if act == "f16" else 0.80)
+        assert err < 0.03 * scale * (1 if act == "f16" else 8)
+        assert agree > (0.995 if act == "f16" else 0.97)
     else:
         # greedy feedback: compare the first step (no feedback yet) tightly, and report token agreement
         scale = max(1.0, float(ref.std()))
