@@ -59,6 +59,8 @@ struct ConvParams {
     int split_out;      // write hi / lo halves (split-precision outputs)
     int pool;           // fused 2x2/2 max-pool of the activated output (TMA-store epilogue only)
     int skip_full;      // pooled output only
+    const float* tail_w;   // fused 1x1 tail (see ConvCall)
+    float* tail_out;
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
@@ -129,7 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmap_x);
         ptx::tma_prefetch_desc(&tmap_w);
-        if (p.tma_store && !p.skip_full) ptx::tma_prefetch_desc(&tmap_y);
+        if (p.tma_store && !p.skip_full && p.tail_out == nullptr) ptx::tma_prefetch_desc(&tmap_y);
         if (p.pool) ptx::tma_prefetch_desc(&tmap_p);
     }
     if (warp == 1 && lane == 0) {
@@ -246,7 +248,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int chunks = (p.n_tile + 31) / 32;
-        if (p.tma_store) {
+        if (p.tail_out != nullptr) {
+            // ---- conv (Cout = 16) + ReLU + 1x1 (16->16) + ReLU + 1x1 (16->2), all in the registers of the pixel's thread.
+            // With M = 256 tiles the two warp groups take one 128-pixel half each.
+            float* tw = reinterpret_cast<float*>(staging);          // [256 W6 | 16 b6 | 32 W8 | 2 b8 | 16 conv bias]
+            const int etid = threadIdx.x - 128;
+            for (int i = etid; i < 306; i += 256) tw[i] = __ldg(&p.tail_w[i]);
+            if (etid < 16) tw[306 + etid] = __ldg(&p.bias[etid]);
+            ptx::named_bar_sync(1, 256);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                ptx::tc_fence_after();
+                const int hf = half;
+                const bool work = hf < p.halves;
+                uint32_t r[16];
+                if (work) {
+                    ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                           (uint32_t)((acc * p.halves + hf) * p.n_tile_alloc), r);
+                    ptx::tmem_ld_wait();
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (work) {
+                    const int oh0 = t.oh0 + (p.split_b ? 0 : hf * p.bh), b0 = t.b0 + (p.split_b ? hf * p.bb : 0);
+                    const int ow = t.ow0 + rw, oh = oh0 + rh, b = b0 + rb;
+                    float h1[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) h1[k] = fmaxf(__uint_as_float(r[k]) + tw[306 + k], 0.f);
+                    float o0 = tw[304], o1 = tw[305];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = tw[256 + j];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(&tw[j * 16 + q * 4]);
+                            a = fmaf(w4.x, h1[q * 4 + 0], a);
+                            a = fmaf(w4.y, h1[q * 4 + 1], a);
+                            a = fmaf(w4.z, h1[q * 4 + 2], a);
+                            a = fmaf(w4.w, h1[q * 4 + 3], a);
+                        }
+                        a = fmaxf(a, 0.f);
+                        o0 = fmaf(tw[272 + j], a, o0);
+                        o1 = fmaf(tw[288 + j], a, o1);
+                    }
+                    if ((ow < p.OW) && (oh < p.OH) && (b < p.B))
+                        reinterpret_cast<float2*>(p.tail_out)[((long)b * p.OH + oh) * p.OW + ow] = make_float2(o0, o1);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        } else if (p.tma_store) {
             // 8 epilogue warps: warp (ew, half) owns TMEM lanes [32*ew, +32) and one half of every staging chunk's
             // columns, so each scheduler overlaps two warps' worth of TMEM loads / conversions / smem stores.
             const int etid = threadIdx.x - 128;
@@ -721,6 +774,12 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, kTileM, n_tile);
     p.pool = pool;
     p.skip_full = (pool && c.skip_full) ? 1 : 0;
+    p.tail_w = c.tail_w;
+    p.tail_out = c.tail_out;
+    if (c.tail_out != nullptr && (c.tail_w == nullptr || n_tile != 16 || c.Cout != 16 || pool || c.residual != nullptr)) {
+        set_err(err, errlen, "conv_tc: the fused 1x1 tail needs Cout = 16 and no pooling / residual");
+        return cudaErrorInvalidValue;
+    }
     if (pool && !p.tma_store) {
         set_err(err, errlen, "conv_tc: fused max-pool needs the TMA-store epilogue (aligned 16-bit output)");
         return cudaErrorInvalidValue;
@@ -779,7 +838,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
 
     CUtensorMap my;
     memset(&my, 0, sizeof(my));
-    if (p.tma_store && !p.skip_full) {
+    if (p.tma_store && !p.skip_full && c.tail_out == nullptr) {
         const cuuint64_t eb = (cuuint64_t)elem;
         cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)c.OW, (cuuint64_t)c.OH,
                               (cuuint64_t)c.B};

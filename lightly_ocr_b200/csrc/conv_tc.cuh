@@ -38,6 +38,11 @@ struct ConvCall {
     void* pool_y = nullptr;
     long pool_pitch = 0;
     int skip_full = 0;  // 1: only the pooled tensor is written (y may be null)
+    // Fused 1x1 tail (CRAFT conv_cls.6 + ReLU + conv_cls.8 after conv_cls.4 + ReLU, model.py:33-36): with Cout = 16 the
+    // epilogue thread that owns a pixel applies relu(W6 h + b6) and W8 . + b8 in fp32 registers and writes the two
+    // score channels.  tail_w: fp32 [16*16 W6 row-major | 16 b6 | 2*16 W8 | 2 b8]; tail_out: fp32 [B][OH][OW][2].
+    const float* tail_w = nullptr;
+    float* tail_out = nullptr;
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).

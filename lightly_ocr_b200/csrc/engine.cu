@@ -140,6 +140,10 @@ struct Ctx {
     long pool_pitch = 0;
     int pool_only = 0;
     void pool(void* y, long pitch, int only) { pool_y = y; pool_pitch = pitch; pool_only = only; }
+    // fused 1x1 tail request for the NEXT tc() call (consumed by it)
+    const float* tail_w = nullptr;
+    float* tail_out = nullptr;
+    void tail(const float* w, float* out) { tail_w = w; tail_out = out; }
     // y = act(conv(x)) through the tensor-core kernel.  Shapes are those of the INPUT; returns output dims.
     void tc(const std::string& layer, const void* x, int B, int H, int W, long x_pitch, void* y, long y_pitch, int relu,
             int pad_h, int pad_w, int dil = 1, int stride_h = 1, int out_fp32 = 0, const void* res = nullptr,
@@ -165,6 +169,8 @@ struct Ctx {
         c.split_out = split_out;
         c.pool_y = pool_y; c.pool_pitch = pool_pitch; c.skip_full = pool_only;
         pool_y = nullptr; pool_pitch = 0; pool_only = 0;
+        c.tail_w = tail_w; c.tail_out = tail_out;
+        tail_w = nullptr; tail_out = nullptr;
         char err[256] = {0};
         cudaError_t e;
         {
@@ -222,8 +228,23 @@ int engine_finalize_craft(locr_handle* h) {
     int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16);
     if (rc != LOCR_OK) return rc;
     for (auto& e : kCraftBn) {
+        if (std::string(e[0]) == "conv_cls.6" || std::string(e[0]) == "conv_cls.8") continue;   // fused tail, fp32
         rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false);
         if (rc != LOCR_OK) return rc;
+    }
+    {
+        const HostTensor* w6 = find(h, LOCR_MODEL_CRAFT, "conv_cls.6.weight");
+        const HostTensor* b6 = find(h, LOCR_MODEL_CRAFT, "conv_cls.6.bias");
+        const HostTensor* w8 = find(h, LOCR_MODEL_CRAFT, "conv_cls.8.weight");
+        const HostTensor* b8 = find(h, LOCR_MODEL_CRAFT, "conv_cls.8.bias");
+        if (!w6 || !b6 || !w8 || !b8 || w6->numel() != 256 || b6->numel() != 16 || w8->numel() != 32 || b8->numel() != 2)
+            return h->fail(LOCR_ERR_STATE, "missing or malformed conv_cls.6 / conv_cls.8 tensors");
+        std::vector<float> tail;
+        tail.insert(tail.end(), w6->data.begin(), w6->data.end());
+        tail.insert(tail.end(), b6->data.begin(), b6->data.end());
+        tail.insert(tail.end(), w8->data.begin(), w8->data.end());
+        tail.insert(tail.end(), b8->data.begin(), b8->data.end());
+        if (upload_f32(h, "craft.cls_tail", tail) == nullptr) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
     }
     h->host[LOCR_MODEL_CRAFT].clear();
     h->ready[LOCR_MODEL_CRAFT] = true;
@@ -236,6 +257,7 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
                          float** score) {
     if (!h->ready[LOCR_MODEL_CRAFT]) return h->fail(LOCR_ERR_STATE, "CRAFT weights not finalized");
     if (H % 32 != 0 || W % 32 != 0 || img_h > H || img_w > W) return h->fail(LOCR_ERR_INVALID, "bad canvas size");
+    if ((long)B * H * W * 8 >= (1L << 31)) return h->fail(LOCR_ERR_CAPACITY, "CRAFT batch too large for 32-bit indices");
     Ctx c{h};
     const int f16 = h->is_f16();
     cudaStream_t s = h->stream;
@@ -265,8 +287,6 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     void* feat = c.buf("feature", px / 4 * 32 * 2);
     void* c0 = c.buf("c0", px / 4 * 32 * 2);
     void* c2 = c.buf("c2", px / 4 * 32 * 2);
-    void* c4 = c.buf("c4", px / 4 * 16 * 2);
-    void* c6 = c.buf("c6", px / 4 * 16 * 2);
     float* sc = (float*)c.buf("score", px / 4 * 2 * 4);
     if (c.rc != LOCR_OK) return c.rc;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
@@ -309,9 +329,9 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat, 32, 1, 1, 1);
     c.tc("conv_cls.0", feat, B, H2, W2, 32, c0, 32, 1, 1, 1);
     c.tc("conv_cls.2", c0, B, H2, W2, 32, c2, 32, 1, 1, 1);
-    c.tc("conv_cls.4", c2, B, H2, W2, 32, c4, 16, 1, 1, 1);
-    c.tc("conv_cls.6", c4, B, H2, W2, 16, c6, 16, 1, 0, 0);
-    c.tc("conv_cls.8", c6, B, H2, W2, 16, sc, 2, 0, 0, 0, 1, 1, /*out_fp32=*/1);
+    // conv_cls.4 + ReLU with conv_cls.6 + ReLU + conv_cls.8 (both 1x1) applied in the epilogue registers (fp32)
+    c.tail(h->f32["craft.cls_tail"], sc);
+    c.tc("conv_cls.4", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 1);
     h->launches += 4;  // 1 max-pool (3x3 s1) + 3 up-samplings
     if (c.rc != LOCR_OK) return c.rc;
     LOCR_CUDA_OK(cudaGetLastError());
@@ -322,7 +342,6 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     dbg(h, "relu5_3", cat1 + 1024, 0, {B, H16, W16, 512}, 1536);
     dbg(h, "fc7", cat1, 0, {B, H16, W16, 1024}, 1536);
     dbg(h, "feature", feat, 0, {B, H2, W2, 32}, 32);
-    dbg(h, "h16", c6, 0, {B, H2, W2, 16}, 16);
     dbg(h, "score", sc, 1, {B, H2, W2, 2}, 2);
     *score = sc;
     return LOCR_OK;
@@ -467,6 +486,7 @@ int engine_finalize_crnn(locr_handle* h) {
 int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits) {
     if (!h->ready[LOCR_MODEL_CRNN]) return h->fail(LOCR_ERR_STATE, "CRNN weights not finalized");
     if (B <= 0) return h->fail(LOCR_ERR_INVALID, "empty crop batch");
+    if (B > 65536) return h->fail(LOCR_ERR_CAPACITY, "more than 65536 crops in one recognition batch");  // 32-bit indices
     Ctx c{h};
     const int f16 = h->is_f16();
     cudaStream_t s = h->stream;
@@ -490,8 +510,8 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
 
     // ---- TPS localisation network (TPS_STN.py:38-58), split precision: tensors hold [hi | lo] channel halves
     const ConvW& l0 = h->conv[loc + "conv.0"];
-    { ProfScope ps_(h, "direct_conv.loc0", 0, false); launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sA, 128, 1, f16, s, 1); }
-    { ProfScope ps_(h, "maxpool.loc1", 0, false); launch_maxpool(sA, 128, B, 32, 100, 64, sB, 128, 2, 2, 2, 2, 0, 0, f16, s, 1); }
+    // conv.0 + BN + ReLU + MaxPool2d(2, 2) in one pass (split-precision output [hi | lo])
+    { ProfScope ps_(h, "direct_conv.loc0+pool", 0, false); launch_direct_conv3x3(d_x, 0, B, 32, 100, 32, 100, 0, 0, l0.w32, l0.bias, 1, 64, sB, 128, 1, f16, s, 1, 1); }
     c.pool(sC, 256, 1);
     c.tc(loc + "conv.4", sB, B, 16, 50, 128, nullptr, 256, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
     c.pool(sB, 512, 1);
@@ -499,7 +519,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     c.tc(loc + "conv.12", sB, B, 4, 12, 512, sA, 1024, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
     { ProfScope ps_(h, "loc_head", 0, false); launch_loc_head(sA, B, 48, h->f32["loc.w1t"], h->f32["loc.b1"], h->f32["loc.w2t"], h->f32["loc.b2"], fid, f16, s, 1); }
     { ProfScope ps_(h, "tps_sample", 0, false); launch_tps_sample(fid, h->f32["tps.inv"], h->f32["tps.phat_t"], d_x, xr, grid, B, s); }
-    h->launches += 4;
+    h->launches += 3;
 
     // ---- ResNet feature extractor (resnet50v1.py:101-135)
     const ConvW& r0 = h->conv[fe + "conv0_1"];

@@ -33,10 +33,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int f16) {
 }
 
 // ------------------------------------------------------------------------------------------- direct conv (tiny Cin)
-// One thread = one pixel x CPT output channels (CPT = 32): the 9*CIN inputs are loaded and converted once and reused
-// for 32 accumulators.  In u8 mode the weights arrive pre-divided by the per-channel std, so the normalisation
+// One thread = one output pixel x CPT output channels (CPT = 32): the 9*CIN inputs are loaded and converted once and
+// reused for 32 accumulators.  In u8 mode the weights arrive pre-divided by the per-channel std, so the normalisation
 // (x - mean)/std costs one subtraction per input (canvas padding reads as raw 0, i.e. -mean/std, conv padding as 0).
-template <int CIN, bool U8>
+// POOL: the thread owns one pixel of the MaxPool2d(2, 2) output instead and reduces its four conv results in registers
+// (conv + BN + ReLU + max-pool of TPS_STN.py:38-43 in one pass; the full-resolution tensor is never written).
+template <int CIN, bool U8, bool POOL>
 __global__ void __launch_bounds__(256)
 direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
                       long img_stride, const float* __restrict__ w, const float* __restrict__ bias, int Cout,
@@ -47,56 +49,66 @@ direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_
     for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias[i];
     __syncthreads();
-    const int groups = Cout / CPT;
-    const long total = (long)B * H * W * groups;
+    const uint32_t groups = (uint32_t)Cout / CPT;
+    const int OH = POOL ? H / 2 : H, OW = POOL ? W / 2 : W;
+    const uint32_t total = (uint32_t)B * OH * OW * groups;   // < 2^31, checked by the launcher
     const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
-    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(gid % groups);
-        const long pix = gid / groups;
-        const int x = (int)(pix % W);
-        const int y = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long)W * H));
-        float acc[CPT];
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        const uint32_t cg = gid % groups;
+        const uint32_t pix = gid / groups;
+        const int ox = (int)(pix % (uint32_t)OW);
+        const uint32_t rest = pix / (uint32_t)OW;
+        const int oy = (int)(rest % (uint32_t)OH);
+        const int b = (int)(rest / (uint32_t)OH);
+        float res[CPT];
+#pragma unroll 1
+        for (int sub = 0; sub < (POOL ? 4 : 1); ++sub) {
+            const int x = POOL ? 2 * ox + (sub & 1) : ox;
+            const int y = POOL ? 2 * oy + (sub >> 1) : oy;
+            float acc[CPT];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[j] = sw[nw + cg * CPT + j];
+            for (int j = 0; j < CPT; ++j) acc[j] = sw[nw + cg * CPT + j];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int yy = y + ky - 1;
-            if (yy < 0 || yy >= H) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = y + ky - 1;
+                if (yy < 0 || yy >= H) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = x + kx - 1;
-                if (xx < 0 || xx >= W) continue;
-                float v[CIN];
-                if (U8) {
-                    const bool inside = (yy < img_h) && (xx < img_w);
-                    const uint8_t* p =
-                        reinterpret_cast<const uint8_t*>(in) + (long)b * img_stride + (long)yy * row_stride + xx * 3;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = x + kx - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    float v[CIN];
+                    if (U8) {
+                        const bool inside = (yy < img_h) && (xx < img_w);
+                        const uint8_t* p =
+                            reinterpret_cast<const uint8_t*>(in) + (long)b * img_stride + (long)yy * row_stride + xx * 3;
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) v[c] = (inside ? (float)p[c] : 0.0f) - mean[c];
-                } else {
-                    v[0] = reinterpret_cast<const float*>(in)[((long)b * H + yy) * W + xx];
-                }
-                const float* wt = sw + ((ky * 3 + kx) * CIN) * Cout + cg * CPT;
+                        for (int c = 0; c < CIN; ++c) v[c] = (inside ? (float)p[c] : 0.0f) - mean[c];
+                    } else {
+                        v[0] = __ldg(reinterpret_cast<const float*>(in) + ((long)(b * H + yy) * W + xx));
+                    }
+                    const float* wt = sw + ((ky * 3 + kx) * CIN) * Cout + cg * CPT;
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) {
+                    for (int c = 0; c < CIN; ++c) {
 #pragma unroll
-                    for (int j = 0; j < CPT; j += 4) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(wt + c * Cout + j);
-                        acc[j] = fmaf(v[c], w4.x, acc[j]);
-                        acc[j + 1] = fmaf(v[c], w4.y, acc[j + 1]);
-                        acc[j + 2] = fmaf(v[c], w4.z, acc[j + 2]);
-                        acc[j + 3] = fmaf(v[c], w4.w, acc[j + 3]);
+                        for (int j = 0; j < CPT; j += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(wt + c * Cout + j);
+                            acc[j] = fmaf(v[c], w4.x, acc[j]);
+                            acc[j + 1] = fmaf(v[c], w4.y, acc[j + 1]);
+                            acc[j + 2] = fmaf(v[c], w4.z, acc[j + 2]);
+                            acc[j + 3] = fmaf(v[c], w4.w, acc[j + 3]);
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) res[j] = sub == 0 ? acc[j] : fmaxf(res[j], acc[j]);
         }
-        uint16_t* op = out + pix * out_pitch + cg * CPT;
+        uint16_t* op = out + (long)pix * out_pitch + cg * CPT;
 #pragma unroll
         for (int q = 0; q < CPT / 8; ++q) {
             float r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(acc[q * 8 + j], 0.f) : acc[q * 8 + j];
+            for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(res[q * 8 + j], 0.f) : res[q * 8 + j];
             const uint4 hi = pack8(r, f16);
             *reinterpret_cast<uint4*>(op + q * 8) = hi;
             if (split) {  // split precision: lo = v - hi goes to channel Cout + n
@@ -118,17 +130,18 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
                       long img_stride, uint16_t* __restrict__ out, int f16) {
     const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
     const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
-    const long total = (long)B * H * W;
-    for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
-        const int x = (int)(pix % W);
-        const int y = (int)((pix / W) % H);
-        const int b = (int)(pix / ((long)W * H));
+    const uint32_t total = (uint32_t)B * H * W;   // < 2^31, checked by the launcher
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+        const int x = (int)(pix % (uint32_t)W);
+        const uint32_t rest = pix / (uint32_t)W;
+        const int y = (int)(rest % (uint32_t)H);
+        const int b = (int)(rest / (uint32_t)H);
         const bool inside = (y < img_h) && (x < img_w);
         const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
-        uint4* o = reinterpret_cast<uint4*>(out + pix * 16);
+        uint4* o = reinterpret_cast<uint4*>(out + (long)pix * 16);
         o[0] = pack8(v, f16);
         o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -138,14 +151,16 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C, uint16_t* __restrict__ out,
                long out_pitch, int OH, int OW, int kh, int kw, int sh, int sw_, int ph, int pw, int f16, int split) {
-    const int groups = C >> 3;
-    const long total = (long)B * OH * OW * groups;
-    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(gid % groups);
-        const long pix = gid / groups;
-        const int ox = (int)(pix % OW);
-        const int oy = (int)((pix / OW) % OH);
-        const int b = (int)(pix / ((long)OW * OH));
+    // 32-bit index arithmetic (the launcher checks total < 2^31): 64-bit divisions would make this ALU-bound
+    const uint32_t groups = (uint32_t)C >> 3;
+    const uint32_t total = (uint32_t)B * OH * OW * groups;
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        const uint32_t cg = gid % groups;
+        const uint32_t pix = gid / groups;
+        const int ox = (int)(pix % (uint32_t)OW);
+        const uint32_t rest = pix / (uint32_t)OW;
+        const int oy = (int)(rest % (uint32_t)OH);
+        const int b = (int)(rest / (uint32_t)OH);
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
@@ -155,13 +170,12 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
             for (int kx = 0; kx < kw; ++kx) {
                 const int ix = ox * sw_ + kx - pw;
                 if (ix < 0 || ix >= W) continue;
-                const uint4 u =
-                    __ldg(reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * in_pitch + cg * 8));
+                const uint16_t* src = in + ((long)(b * H + iy) * W + ix) * in_pitch + cg * 8;
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
                 float f[8];
                 unpack8(u, f, f16);
                 if (split) {  // value = hi + lo (exact in fp32), lo lives C channels further
-                    const uint4 ul = __ldg(
-                        reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * in_pitch + C + cg * 8));
+                    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(src + C));
                     float l[8];
                     unpack8(ul, l, f16);
 #pragma unroll
@@ -172,13 +186,14 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
             }
         }
         const uint4 hi = pack8(m, f16);
-        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = hi;
+        uint16_t* dst = out + (long)pix * out_pitch + cg * 8;
+        *reinterpret_cast<uint4*>(dst) = hi;
         if (split) {
             float h[8];
             unpack8(hi, h, f16);
 #pragma unroll
             for (int j = 0; j < 8; ++j) m[j] -= h[j];
-            *reinterpret_cast<uint4*>(out + pix * out_pitch + C + cg * 8) = pack8(m, f16);
+            *reinterpret_cast<uint4*>(dst + C) = pack8(m, f16);
         }
     }
 }
@@ -187,15 +202,16 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C,
                   uint16_t* __restrict__ out, long out_pitch, int f16) {
-    const int groups = C >> 3;
+    const uint32_t groups = (uint32_t)C >> 3;
     const int OH = 2 * H, OW = 2 * W;
-    const long total = (long)B * OH * OW * groups;
-    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(gid % groups);
-        const long pix = gid / groups;
-        const int ox = (int)(pix % OW);
-        const int oy = (int)((pix / OW) % OH);
-        const int b = (int)(pix / ((long)OW * OH));
+    const uint32_t total = (uint32_t)B * OH * OW * groups;   // < 2^31, checked by the launcher
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        const uint32_t cg = gid % groups;
+        const uint32_t pix = gid / groups;
+        const int ox = (int)(pix % (uint32_t)OW);
+        const uint32_t rest = pix / (uint32_t)OW;
+        const int oy = (int)(rest % (uint32_t)OH);
+        const int b = (int)(rest / (uint32_t)OH);
         // PyTorch area_pixel_compute_source_index, align_corners=False, scale 0.5, negative sources clamp to 0
         float sy = 0.5f * (oy + 0.5f) - 0.5f;
         float sx = 0.5f * (ox + 0.5f) - 0.5f;
@@ -207,13 +223,13 @@ upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, 
         const float hy = 1.f - ly, hx = 1.f - lx;
         const uint16_t* base = in + (long)b * H * W * in_pitch + cg * 8;
         float a[8], bq[8], c[8], d[8], r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y0 * W + x0) * in_pitch)), a, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y0 * W + x1) * in_pitch)), bq, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y1 * W + x0) * in_pitch)), c, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long)y1 * W + x1) * in_pitch)), d, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y0 * W + x0) * in_pitch)), a, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y0 * W + x1) * in_pitch)), bq, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y1 * W + x0) * in_pitch)), c, f16);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y1 * W + x1) * in_pitch)), d, f16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * c[j] + lx * d[j]);
-        *reinterpret_cast<uint4*>(out + pix * out_pitch + cg * 8) = pack8(r, f16);
+        *reinterpret_cast<uint4*>(out + (long)pix * out_pitch + cg * 8) = pack8(r, f16);
     }
 }
 
@@ -546,16 +562,20 @@ inline int grid_for(long total, int block) {
 
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out) {
-    const long total = (long)B * H * W * (Cout / 32);
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out, int pool) {
+    const long total = (long)B * (pool ? H / 2 : H) * (pool ? W / 2 : W) * (Cout / 32);
     const int grid = grid_for(total, 256);
     const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
     if (u8_mode)
-        direct_conv3x3_kernel<3, true><<<grid, 256, smem, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride, w,
-                                                               bias, Cout, (uint16_t*)out, out_pitch, relu, is_f16, split_out);
+        direct_conv3x3_kernel<3, true, false><<<grid, 256, smem, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
+                                                                      w, bias, Cout, (uint16_t*)out, out_pitch, relu,
+                                                                      is_f16, split_out);
+    else if (pool)
+        direct_conv3x3_kernel<1, false, true><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
+                                                                      (uint16_t*)out, out_pitch, relu, is_f16, split_out);
     else
-        direct_conv3x3_kernel<1, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
-                                                                (uint16_t*)out, out_pitch, relu, is_f16, split_out);
+        direct_conv3x3_kernel<1, false, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
+                                                                       (uint16_t*)out, out_pitch, relu, is_f16, split_out);
 }
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,

@@ -18,7 +18,8 @@ namespace locr {
 //   f32 mode : `in` is fp32 [B][H][W] (Cin = 1).
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out = 0);
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out = 0, int pool = 0);
+//   pool     : f32 mode only; writes MaxPool2d(2, 2) of the activated output instead, [B][H/2][W/2][Cout]
 
 // CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
 // channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.

@@ -1,4 +1,6 @@
 // Kernel-level test hooks behind the C ABI.  They drive exactly the kernels the product path uses, on host data.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "conv_tc.cuh"
@@ -145,7 +147,9 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
     c.bias = db.as<float>();
     c.relu = d->relu; c.dtype = d->act_dtype; c.n_tile = d->n_tile;
     char err[256] = {0};
-    for (int i = 0; i < 3; ++i) {
+    const char* wenv = getenv("LOCR_BENCH_WARMUP");   // profiler runs: 0 warm-ups keep the capture to one launch per layer
+    const int warm = wenv ? atoi(wenv) : 3;
+    for (int i = 0; i < warm; ++i) {
         cudaError_t e = conv_tc_launch(c, 0, err, sizeof(err));
         if (e != cudaSuccess) return fail(LOCR_ERR_CUDA, err);
     }

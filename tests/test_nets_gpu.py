@@ -47,7 +47,7 @@ def test_craft_score_maps(oracle_mods, act):
         x = torch.cat([ocr_ref.craft_preproc(i, canvas_size=10 ** 6, mag_ratio=1.0)[0] for i in batch], 0)
         ref = ocr_ref.craft_forward(sd, x, taps).numpy()
     # layer-wise: relative error of every tap (normalised by the tap's own max) localises a broken layer
-    for name in ("slice1.0", "relu2_2", "relu3_2", "relu4_3", "relu5_3", "fc7", "feature", "h16"):
+    for name in ("slice1.0", "relu2_2", "relu3_2", "relu4_3", "relu5_3", "fc7", "feature"):
         g = eng.debug_read(name)
         r = taps[name].permute(0, 2, 3, 1).numpy()
         rel = np.abs(g - r).max() / max(np.abs(r).max(), 1e-6)
