@@ -164,11 +164,19 @@ def crnn_calibrated(seed=1, head="CTC", trained=True):
     assert seed == 1
     sd = crnn_state_dict(seed, head=head)
     sd.update(_overrides("calib_crnn_%s.npz" % head.lower()))
-    path = __import__("os").path.join(_HERE, "calib_crnn_ctc_trained.npz")
-    if head == "CTC" and trained and __import__("os").path.exists(path):
+    os_ = __import__("os")
+    path = os_.path.join(_HERE, "calib_crnn_ctc_trained.npz")
+    path_a = os_.path.join(_HERE, "calib_crnn_attention_trained.npz")
+    if trained and os_.path.exists(path) and (head == "CTC" or os_.path.exists(path_a)):
         for k, v in _overrides("calib_crnn_ctc_trained.npz").items():
+            if head != "CTC" and k.startswith("Prediction."):
+                continue                      # the Attention model shares the trained front end and BiLSTMs only
             assert tuple(v.shape) == tuple(sd[k].shape), k
             sd[k] = v.float()
+        if head != "CTC":
+            for k, v in _overrides("calib_crnn_attention_trained.npz").items():
+                assert tuple(v.shape) == tuple(sd[k].shape), k
+                sd[k] = v.float()
     return sd
 
 

@@ -159,3 +159,39 @@ def test_dropin_attention(tmp_path):
         ref_raw, _ = ocr_ref.crnn_get_preds(sd, gray, "Attention")
         agree.append(ref_raw[0] == raw[0])
     print("attention token-string agreement with the fp32 oracle: %.3f over %d crops" % (np.mean(agree), len(agree)))
+    assert np.mean(agree) >= 0.9
+
+
+def test_attention_string_gate():
+    """BASELINE config 5 (attention decoder end to end): all crops the GPU detects on 4 receipts, recognised by the CUDA
+    attention path and by the fp32 oracle (B = 1 semantics per crop); the strings cut at [s] must agree >= 99.5%."""
+    from lightly_ocr_b200 import bridge
+    from oracle import ocr_ref, receipts, weights
+    torch.set_num_threads(os.cpu_count())
+    sd = weights.crnn_calibrated(1, "Attention")
+    runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="Attention")
+    runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
+    runner.load_state_dict(bridge.MODEL_CRNN, sd)
+    images = [receipts.receipt(s) for s in range(16, 20)]
+    per_image, out = runner.ocr(images, want_logits=True)
+    xs = []
+    for img, rects in zip(images, per_image):
+        for r in rects:
+            xs.append(ocr_ref.crop_to_tensor(ocr_ref.bgr_to_gray(img[r[0]:r[2], r[1]:r[3], :]))[1])
+    want = []
+    with torch.no_grad():
+        for i in range(0, len(xs), 64):
+            lg = ocr_ref.crnn_forward(sd, torch.cat(xs[i:i + 64], 0), "Attention")
+            for row in lg:
+                s = ocr_ref.attn_decode_tokens(row.argmax(1))
+                want.append(s[:s.find("[s]")] if "[s]" in s else None)
+    got = [t if e == 1 else ("" if e == -1 else None) for t, e in zip(out["text"], out["has_eos"])]
+    assert len(got) == len(want) and len(got) > 250
+    same = sum(g == w for g, w in zip(got, want))
+    truth = []
+    for s in range(16, 20):
+        truth.extend(w[0] for w in receipts.receipt(s, return_words=True)[1])
+    print("attention string gate: %d / %d identical to the fp32 oracle (%.4f); %d are rendered words" %
+          (same, len(got), same / len(got), len(set(g for g in got if g) & set(truth))))
+    assert same / len(got) >= 0.995
+    runner.close()

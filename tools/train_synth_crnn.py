@@ -103,7 +103,7 @@ class Crnn(nn.Module):
         # BatchNorm folded into the conv exactly as the engine does it (weights rounded to 16 bits AFTER folding)
         s = self.p(FE + bn + ".weight") * torch.rsqrt(self.p(FE + bn + ".running_var") + 1e-5)
         w = self.p(FE + conv + ".weight") * s.view(-1, 1, 1, 1)
-        if self.mode != "fp32":
+        if not self.mode.startswith("fp32"):
             w = w + (w.half().float() - w).detach()
         y = F.conv2d(t, w, self.p(FE + bn + ".bias") - self.p(FE + bn + ".running_mean") * s, **kw)
         if res is not None:
@@ -115,7 +115,7 @@ class Crnn(nn.Module):
     def store(self, y):
         """Emulates the 16-bit activation storage of the CUDA path (straight-through rounding), with extra noise in
         training so that the learned decisions keep a margin over it."""
-        if self.mode == "fp32":
+        if self.mode.startswith("fp32"):
             return y
         if self.training:
             y = y + 2.0 ** -9 * y.detach().abs() * torch.randn_like(y)
@@ -147,7 +147,129 @@ class Crnn(nn.Module):
         v = h.squeeze(2).permute(0, 2, 1)                        # [B, 26, 512]
         s = self.store(self.lin0(self.rnn0(v)[0]))
         s = self.store(self.lin1(self.rnn1(s)[0]))
+        if mode.endswith("+ctx"):
+            return s
         return self.pred(s)
+
+
+class AttnDecoder(nn.Module):
+    """The reference's attention head (ocr/modules/attention.py:8-88) with per-sample (B = 1) semantics, batched."""
+
+    def __init__(self, ncls=38):
+        super().__init__()
+        self.ncls = ncls
+        self.i2h = nn.Linear(256, 256, bias=False)
+        self.h2h = nn.Linear(256, 256)
+        self.score = nn.Linear(256, 1, bias=False)
+        self.rnn = nn.LSTMCell(256 + ncls, 256)
+        self.generator = nn.Linear(256, ncls)
+
+    def forward(self, H, teacher=None, steps=26):
+        B = H.shape[0]
+        h = H.new_zeros(B, 256)
+        c = H.new_zeros(B, 256)
+        proj = self.i2h(H)
+        prev = torch.zeros(B, dtype=torch.long, device=H.device)     # [GO]
+        outs = []
+        for i in range(steps):
+            e = self.score(torch.tanh(proj + self.h2h(h).unsqueeze(1)))
+            alpha = torch.softmax(e, 1)
+            ctx = (alpha * H).sum(1)
+            x = torch.cat([ctx, F.one_hot(prev, self.ncls).float()], 1)
+            h, c = self.rnn(x, (h, c))
+            p = self.generator(h)
+            outs.append(p)
+            prev = teacher[:, i] if teacher is not None else p.argmax(1)
+        return torch.stack(outs, 1)
+
+
+def attn_tokens(ids):
+    tok = ["[GO]", "[s]"] + list(ALPHABET)
+    return ["".join(tok[t] for t in row) for row in ids]
+
+
+def train_attention():
+    """Second stage: the attention decoder on top of the (already trained, frozen) front end + BiLSTMs."""
+    torch.manual_seed(1)
+    base_sd = weights.crnn_calibrated(1, "CTC", trained=True)
+    runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
+    runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
+    runner.load_state_dict(bridge.MODEL_CRNN, base_sd)
+    rect, labels = collect(runner, N_RECEIPTS)
+    runner.close()
+    n = len(labels)
+    dev = torch.device("cuda", 0)
+    X = torch.from_numpy(rect).to(dev)
+    front = Crnn(base_sd, False).to(dev)
+    tr = weights._overrides("calib_crnn_ctc_trained.npz")
+    rnn_sd = {0: {}, 1: {}}
+    for k, v in tr.items():
+        if k.startswith("SequenceModeling."):
+            li = int(k.split(".")[1])
+            rest = k.split(".", 2)[2]
+            if rest.startswith("rnn."):
+                rnn_sd[li][rest[4:]] = v.float()
+    for li, (rnn, lin) in enumerate(((front.rnn0, front.lin0), (front.rnn1, front.lin1))):
+        rnn.load_state_dict(rnn_sd[li])
+        lin.weight.data.copy_(tr["SequenceModeling.%d.linear.weight" % li].float())
+        lin.bias.data.copy_(tr["SequenceModeling.%d.linear.bias" % li].float())
+    front.eval()
+    ctx = []
+    with torch.no_grad():
+        for i in range(0, n, 512):
+            ctx.append(front(X[i:i + 512].float().unsqueeze(1), "q16+ctx").half())
+    Hc = torch.cat(ctx)                                           # [n, 26, 256] as the CUDA path stores them
+    del front, X
+    tgt = torch.ones(n, 26, dtype=torch.long)                      # [s] everywhere after the text
+    for i, s in enumerate(labels):
+        tgt[i, :len(s)] = torch.tensor([ALPHABET.index(c) + 2 for c in s])
+    tgt = tgt.to(dev)
+    n_val = max(512, n // 10)
+    perm = torch.randperm(n, device=dev)
+    val, trn = perm[:n_val], perm[n_val:]
+    dec = AttnDecoder().to(dev)
+    opt = torch.optim.AdamW(dec.parameters(), lr=1e-3, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=2e-3, total_steps=STEPS, pct_start=0.1)
+    rms = float(Hc.float().pow(2).mean().sqrt())
+    bs = 256
+    t0 = time.time()
+    for step in range(STEPS):
+        b = trn[torch.randint(0, len(trn), (bs,), device=dev)]
+        Hb = Hc[b].float()
+        Hb = Hb + 0.01 * rms * torch.randn_like(Hb)
+        # teacher forcing with 20 % of the inputs replaced by the model's own previous guess (exposure to its errors)
+        logits = dec(Hb, teacher=tgt[b])
+        loss = F.cross_entropy(logits.reshape(-1, 38), tgt[b].reshape(-1))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        nn.utils.clip_grad_norm_(dec.parameters(), 5.0)
+        opt.step()
+        sched.step()
+        if step % 500 == 0 or step == STEPS - 1:
+            with torch.no_grad():
+                got = dec(Hc[val].float()).argmax(2)
+                acc = float((got == tgt[val]).all(1).float().mean())
+            print("step %5d loss %.4f val sequence acc (greedy, all 26 tokens) %.4f (%.0f s)" %
+                  (step, float(loss.detach()), acc, time.time() - t0), flush=True)
+    with torch.no_grad():
+        lg = dec(Hc[val].float())
+        base = lg.argmax(2)
+        for rel in (0.002, 0.005, 0.01):
+            lg2 = dec(Hc[val].float() + rel * rms * torch.randn_like(Hc[val].float()))
+            print("feature noise %.3f rms: token-string agreement %.4f, step-0 logit max-abs change %.3f" %
+                  (rel, float((lg2.argmax(2) == base).all(1).float().mean()), float((lg2[:, 0] - lg[:, 0]).abs().max())))
+        print("examples:", attn_tokens(base[:4].cpu().numpy()), [labels[i] for i in val[:4].cpu().numpy()])
+    sd = {}
+    m = {"i2h.weight": dec.i2h.weight, "h2h.weight": dec.h2h.weight, "h2h.bias": dec.h2h.bias,
+         "score.weight": dec.score.weight, "rnn.weight_ih": dec.rnn.weight_ih, "rnn.weight_hh": dec.rnn.weight_hh,
+         "rnn.bias_ih": dec.rnn.bias_ih, "rnn.bias_hh": dec.rnn.bias_hh}
+    for k, v in m.items():
+        sd["Prediction.attention_cell." + k] = v.detach().cpu().float().numpy()
+    sd["Prediction.generator.weight"] = dec.generator.weight.detach().cpu().float().numpy()
+    sd["Prediction.generator.bias"] = dec.generator.bias.detach().cpu().float().numpy()
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed("gpurun_out/calib_crnn_attention_trained.npz", **sd)
+    print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize("gpurun_out/calib_crnn_attention_trained.npz") / 1e6))
 
 
 def decode(ids):
@@ -254,4 +376,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if os.environ.get("LOCR_TRAIN_HEAD", "CTC") == "Attention":
+        train_attention()
+    else:
+        main()
