@@ -45,7 +45,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The sampler runs
+    from before the warm-up (nvidia-smi needs a few hundred ms to produce its first line); stop(t0, t1) keeps the
+    samples whose arrival time falls inside the timed window [t0, t1]."""
 
     def __init__(self, index):
         self.index = index
@@ -58,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -66,19 +68,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+            window = "whole run (no sample fell inside the timed region)"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w": statistics.median(pw) if pw else None, "reasons": reasons, "samples": len(sm),
+                "window": window}
 
 
 def make_receipts(rank, count):
@@ -141,7 +150,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -218,13 +227,13 @@ def main():
     launches_e2e = launches() - launches0
 
     # ---------------- value: the same path with the step's receipts already resident in HBM
-    e2e_step(0)                                          # leaves batch 0 resident (per_lane receipts on each lane)
-    for _ in range(3):
-        lanes(lambda i, r: r.ocr_resident(per_lane))
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()                                   # before the warm-up: nvidia-smi takes a while to start
+    e2e_step(0)                                          # leaves batch 0 resident (per_lane receipts on each lane)
+    for _ in range(max(args.warmup, 3)):
+        lanes(lambda i, r: r.ocr_resident(per_lane))
+    barrier()
     launches0 = launches()
     for r in runners:
         r.timer_start()
@@ -236,7 +245,7 @@ def main():
     dev_ms = max(r.timer_stop() for r in runners)
     wall = time.perf_counter() - t0
     barrier()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t0, t0 + wall) if rank == 0 else None
     elapsed = shard.max_over_ranks(max(dev_ms / 1e3, wall), dev)
     n_launches = launches() - launches0
     # ---------------- roofline pass: the same steps on ONE lane with per-launch CUDA events around every conv_tc_kernel

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("LOCR_NVCC_EXTRA", "").split()
 # Translation units whose float arithmetic must match cv2 / PIL / numpy bit for bit: no FMA contraction.
 EXACT_UNITS = {"postproc.cu", "imgops.cu"}
 

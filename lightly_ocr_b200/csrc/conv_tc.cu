@@ -28,6 +28,10 @@ namespace locr {
 
 namespace {
 
+// -DLOCR_CONV_EXPERIMENTS=1 (tools only): LOCR_CONV_DBG bit 1 skips the MMAs, 2 the A loads, 4 the B loads, 8 the stores
+#ifndef LOCR_CONV_EXPERIMENTS
+#define LOCR_CONV_EXPERIMENTS 0
+#endif
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 384;
 constexpr int kTileM = 128;
@@ -114,15 +118,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+    // all stage sizes are multiples of 1024 bytes, so the epilogue staging tiles that follow stay 1024-aligned
+    uint8_t* staging = smem_b + (size_t)p.stages * p.b_stage_bytes;                            // 2 x [128][stage_rb]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * 128 * 128 + (p.pool ? 2 * 32 * 128 : 0));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kMaxStages;
     uint64_t* tfull_bar = bars + 2 * kMaxStages;
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);                       // [256]
-    uint8_t* staging = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(bias_s + 256) + 1023) & ~(uintptr_t)1023);                // 2 x [128][stage_rb]
     uint8_t* pool_staging = staging + 2 * 128 * 128;                                           // 2 x [32][stage_rb]
 
     const int warp = threadIdx.x >> 5;
@@ -155,11 +159,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (single thread)
-        // The loop body is kept to a handful of instructions: a lone thread issues ~one instruction per 4-6 cycles, so
-        // index arithmetic (divisions, 64-bit address math) in here directly bounds the k-block rate.
-        if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+        // ------------------------------------------------------------ TMA producer
+        // The WHOLE warp runs the loop on warp-uniform values and one elected lane issues the TMA instructions.  With
+        // the loop inside `if (lane == 0)` ptxas cannot prove uniformity: every UTMALDG / UTCHMMA then gets wrapped in
+        // a per-thread election loop with R2UR moves (~10 extra instructions per issue), which bounded the k-block
+        // rate of every layer with N <= 128.
+        {
+            uint32_t tx_bytes = (uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+            if (LOCR_CONV_EXPERIMENTS && (p.dbg & 2)) tx_bytes -= (uint32_t)(p.halves * kTileM * SWZ);
+            if (LOCR_CONV_EXPERIMENTS && (p.dbg & 4)) tx_bytes -= (uint32_t)(p.n_tile * SWZ);
             const uint32_t a0 = ptx::smem_u32(smem_a), b0s = ptx::smem_u32(smem_b);
             const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
             const uint32_t a_end = a0 + (uint32_t)p.stages * p.a_stage_bytes;
@@ -175,11 +183,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     for (int kw = 0; kw < p.KW; ++kw, iw0 += p.dil_w) {
                         for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
                             ptx::mbar_wait_a(empty_s, phase, 100);
-                            ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
                             int cch = cc * BLOCK_K;
                             if (cch >= p.cin_wrap) cch -= p.cin_wrap;   // [hi | lo | hi] of a split-precision input
-                            ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
-                            ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
+                            if (ptx::elect_one()) {
+                                if (LOCR_CONV_EXPERIMENTS && tx_bytes == 0) ptx::mbar_arrive(&full_bar[(full_s - full0) >> 3]);
+                                else ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
+                                if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 2)))
+                                    ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
+                                if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 4)))
+                                    ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
+                            }
                             a_s += p.a_stage_bytes; b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
                             if (a_s == a_end) {
                                 a_s = a0; b_s = b0s; full_s = full0; empty_s = empty0;
@@ -191,8 +204,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
+        {
             // descriptors as 32-bit running values: hi word constant, lo word = (addr >> 4) | LBO field
             const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, SWZ) >> 32);
             const uint32_t lo_flag = 1u << 16;
@@ -215,24 +228,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 for (int kb = 0; kb < p.num_kblocks; ++kb) {
                     ptx::mbar_wait_a(full_s, phase, 300);
                     ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k) {
 #pragma unroll
-                        for (int hf = 0; hf < HALVES; ++hf) {
-                            // independent accumulators (M = 256 tiles) alternate, hiding the MMA pipeline latency
-                            ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
-                                               desc_hi, b_lo + k * 2, desc_hi, idesc, accum);
+                            for (int hf = 0; hf < HALVES; ++hf) {
+                                // independent accumulators (M = 256 tiles) alternate, hiding the MMA pipeline latency
+                                if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 1)))
+                                ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
+                                                   desc_hi, b_lo + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
+                            }
                         }
-                        accum = 1;
+                        ptx::umma_commit_a(empty_s);  // frees the smem slot once these MMAs retire
                     }
-                    ptx::umma_commit_a(empty_s);  // frees the smem slot once these MMAs retire
+                    accum = 1;
                     a_lo += a_step; b_lo += b_step; full_s += 8; empty_s += 8;
                     if (full_s == full_end) {
                         a_lo = a_lo0; b_lo = b_lo0; full_s = full0; empty_s = empty0;
                         phase ^= 1u;
                     }
                 }
-                ptx::umma_commit_a(tfull0 + acc * 8u);  // accumulators complete -> epilogue
+                if (ptx::elect_one()) ptx::umma_commit_a(tfull0 + acc * 8u);  // accumulators complete -> epilogue
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -332,6 +348,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 ptx::tc_fence_after();
+                if (LOCR_CONV_EXPERIMENTS && (p.dbg & 16)) {   // epilogue reduced to the TMEM hand-shake
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int hf = 0; hf < p.halves; ++hf) {
                 const int oh0 = t.oh0 + (p.split_b ? 0 : hf * p.bh), b0 = t.b0 + (p.split_b ? hf * p.bb : 0);
                 const int ow = t.ow0 + rw, oh = oh0 + rh, b = b0 + rb;
@@ -483,7 +507,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     ptx::fence_proxy_async();
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) {
-                        if (!p.skip_full) {
+                        if (!p.skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
                             ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
                             if (p.split_out)
                                 ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
@@ -765,7 +789,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.tma_store = ((c.y_pitch * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
                    n_tile % p.stage_cols == 0 && (p.stage_rb == 32 || p.stage_rb == 64 || p.stage_rb == 128))
                       ? 1 : 0;
-    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 1024 + 2 * 128 * 128 + (pool ? 2 * 32 * 128 : 0);
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 2 * 128 * 128 + (pool ? 2 * 32 * 128 : 0);
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
@@ -776,6 +800,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.skip_full = (pool && c.skip_full) ? 1 : 0;
     p.tail_w = c.tail_w;
     p.tail_out = c.tail_out;
+    if (c.y_row_px > 0 && (!p.tma_store || c.residual != nullptr || pool)) {
+        set_err(err, errlen, "conv_tc: row-padded outputs need the plain TMA-store epilogue");
+        return cudaErrorInvalidValue;
+    }
     if (c.tail_out != nullptr && (c.tail_w == nullptr || n_tile != 16 || c.Cout != 16 || pool || c.residual != nullptr)) {
         set_err(err, errlen, "conv_tc: the fused 1x1 tail needs Cout = 16 and no pooling / residual");
         return cudaErrorInvalidValue;
@@ -806,7 +834,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         cuuint64_t dims[5] = {(cuuint64_t)(c.cin_wrap > 0 ? c.cin_wrap : c.Cin), (cuuint64_t)c.W, (cuuint64_t)S, (cuuint64_t)(c.H / S),
                               (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.x_pitch * 2;
-        cuuint64_t strides[4] = {pb, pb * c.W, pb * c.W * S, pb * c.W * c.H};
+        const cuuint64_t xw = (cuuint64_t)(c.x_row_px > 0 ? c.x_row_px : c.W);
+        cuuint64_t strides[4] = {pb, pb * xw, pb * xw * S, pb * xw * c.H};
         cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)full_bh, (cuuint32_t)full_bb};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&mx, dt, 5, const_cast<void*>(c.x), dims, strides, box, estr,
@@ -843,7 +872,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)c.OW, (cuuint64_t)c.OH,
                               (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.y_pitch * eb;
-        cuuint64_t strides[3] = {pb, pb * c.OW, pb * c.OW * c.OH};
+        const cuuint64_t yw = (cuuint64_t)(c.y_row_px > 0 ? c.y_row_px : c.OW);
+        cuuint64_t strides[3] = {pb, pb * yw, pb * yw * c.OH};
         cuuint32_t box[4] = {(cuuint32_t)p.stage_cols, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bb};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUtensorMapDataType ydt = c.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;

@@ -43,6 +43,14 @@ struct ConvCall {
     // score channels.  tail_w: fp32 [16*16 W6 row-major | 16 b6 | 2*16 W8 | 2 b8]; tail_out: fp32 [B][OH][OW][2].
     const float* tail_w = nullptr;
     float* tail_out = nullptr;
+    // Row-padded tensors and the "window" input view (small-Cin 3x3 layers).  The TMA unit spends ~2.5 cycles per box
+    // row whatever the row's size, so a 3x3 conv over 16 or 32 channels (32/64-byte rows, 9 taps) is bound by the
+    // row rate.  With x_row_px = W + 3 (one zero pixel left, two right of every row) the three horizontal taps of an
+    // output pixel are ONE contiguous run of memory: the tensor map's innermost dimension becomes Cin = 4 pixels x
+    // channels (window starting at pixel x - 1; the 4th pixel meets zero weights) with the pixel pitch as its stride,
+    // KW = 1 and pad_w = 0: 3 (or 6) k-blocks of 128-byte rows instead of 9.
+    long x_row_px = 0;  // pixels per memory row of x (0 = W)
+    long y_row_px = 0;  // pixels per memory row of y (0 = OW); TMA-store epilogue only
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).

@@ -25,7 +25,7 @@ T* dev_upload(locr_handle* h, const std::vector<T>& v) {
 
 // Conv (+ optional BatchNorm, eval mode, eps 1e-5) -> weights with the BN scale folded in and a single fp32 bias.
 int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct,
-              bool fold_image_std = false, int cin_pad = 0, bool split3 = false) {
+              bool fold_image_std = false, int cin_pad = 0, bool split3 = false, bool window = false) {
     const HostTensor* w = find(h, model, prefix + ".weight");
     if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
         return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
@@ -95,6 +95,26 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
             h->conv[prefix] = cw;
             return LOCR_OK;
         }
+        if (window) {
+            // 3x3 conv as KH = 3 taps over a 4-pixel window (conv_tc.cuh: x_row_px): K per tap = 4 * cpp with
+            // k = dx * cpp + c for the pixel x - 1 + dx; the 4th pixel and padded channels get zero weights
+            const int cpp = cin_pad > 0 ? cin_pad : cin;
+            if (kh != 3 || kw != 3 || (4 * cpp) % 64 != 0)
+                return h->fail(LOCR_ERR_INVALID, prefix + ": window view needs a 3x3 conv with 16 or 32 channels per pixel");
+            const int K = 4 * cpp;
+            std::vector<uint16_t> w16((size_t)cw.cout_pad * 3 * K, 0);
+            for (int n = 0; n < cout; ++n)
+                for (int c = 0; c < cin; ++c)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int dx = 0; dx < 3; ++dx)
+                            w16[((size_t)n * 3 + ky) * K + dx * cpp + c] = f32_to_act(
+                                (float)(w->data[((size_t)n * cin + c) * 9 + ky * 3 + dx] * scale[n]), h->cfg.act_dtype);
+            cw.cin = K; cw.cin_real = cin * 3; cw.kh = 3; cw.kw = 1; cw.window = 1;
+            cw.w = dev_upload(h, w16);
+            if (!cw.w || !cw.bias) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+            h->conv[prefix] = cw;
+            return LOCR_OK;
+        }
         const int cp = cin_pad > 0 ? cin_pad : cin;   // input channels as laid out in memory (zero-padded)
         if (cp % 16 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": Cin must be a multiple of 16");
         std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * cp, 0);
@@ -140,6 +160,9 @@ struct Ctx {
     long pool_pitch = 0;
     int pool_only = 0;
     void pool(void* y, long pitch, int only) { pool_y = y; pool_pitch = pitch; pool_only = only; }
+    // row-padded input / output (pixels per memory row) for the NEXT tc() call (consumed by it)
+    long x_row_px = 0, y_row_px = 0;
+    void rows(long xr, long yr) { x_row_px = xr; y_row_px = yr; }
     // fused 1x1 tail request for the NEXT tc() call (consumed by it)
     const float* tail_w = nullptr;
     float* tail_out = nullptr;
@@ -171,6 +194,8 @@ struct Ctx {
         pool_y = nullptr; pool_pitch = 0; pool_only = 0;
         c.tail_w = tail_w; c.tail_out = tail_out;
         tail_w = nullptr; tail_out = nullptr;
+        c.x_row_px = x_row_px; c.y_row_px = y_row_px;
+        x_row_px = 0; y_row_px = 0;
         char err[256] = {0};
         cudaError_t e;
         {
@@ -179,6 +204,19 @@ struct Ctx {
         }
         h->launches++;
         if (e != cudaSuccess) rc = h->fail(LOCR_ERR_CUDA, layer + ": " + err);
+    }
+    // Row-padded buffer whose pad pixels must read as zero: zero-filled whenever it is (re)allocated or its size changes
+    // (the producers only ever write the interior).
+    void* zbuf(const std::string& name, size_t bytes) {
+        void* p = buf(name, bytes);
+        if (p == nullptr) return p;
+        auto& z = h->zeroed[name];
+        if (z.first != p || z.second != bytes) {
+            if (cudaMemsetAsync(p, 0, bytes, h->stream) != cudaSuccess && rc == LOCR_OK)
+                rc = h->fail(LOCR_ERR_CUDA, "memset failed for " + name);
+            z.first = p; z.second = bytes;
+        }
+        return p;
     }
     void* buf(const std::string& name, size_t bytes) {
         void* p = engine_buffer(h, name, bytes);
@@ -225,11 +263,13 @@ static const char* kCraftBn[][2] = {
 };
 
 int engine_finalize_craft(locr_handle* h) {
-    int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16);
+    int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16, false, true);
     if (rc != LOCR_OK) return rc;
     for (auto& e : kCraftBn) {
         if (std::string(e[0]) == "conv_cls.6" || std::string(e[0]) == "conv_cls.8") continue;   // fused tail, fp32
-        rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false);
+        const bool window = std::string(e[0]) == "conv_cls.0" || std::string(e[0]) == "conv_cls.2" ||
+                            std::string(e[0]) == "conv_cls.4";
+        rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false, false, 0, false, window);
         if (rc != LOCR_OK) return rc;
     }
     {
@@ -284,18 +324,22 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     void* u3a = c.buf("u3a", px / 16 * 128 * 2);
     void* y3 = c.buf("y3", px / 16 * 64 * 2);
     void* u4a = c.buf("u4a", px / 4 * 64 * 2);
-    void* feat = c.buf("feature", px / 4 * 32 * 2);
-    void* c0 = c.buf("c0", px / 4 * 32 * 2);
-    void* c2 = c.buf("c2", px / 4 * 32 * 2);
+    // inputs of the 32-channel 3x3 head convs: rows padded to W/2 + 3 pixels (zero pixel left, two right), see conv_tc.cuh
+    const long W2p = W / 2 + 3;
+    const size_t padded32 = (size_t)B * (H / 2) * W2p * 32 * 2;
+    uint16_t* feat = (uint16_t*)c.zbuf("feature", padded32);
+    uint16_t* c0 = (uint16_t*)c.zbuf("c0", padded32);
+    uint16_t* c2 = (uint16_t*)c.zbuf("c2", padded32);
     float* sc = (float*)c.buf("score", px / 4 * 2 * 4);
     if (c.rc != LOCR_OK) return c.rc;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
 
-    void* x16 = c.buf("x16", px * 16 * 2);
+    void* x16 = c.buf("x16", (size_t)B * H * (W + 3) * 16 * 2);   // rows padded: [zero | W pixels | zero zero]
     if (c.rc != LOCR_OK) return c.rc;
     { ProfScope ps_(h, "preproc_nhwc16", 0, false); launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s); }
     h->launches++;
-    c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 1);
+    c.rows(W + 3, 0);
+    c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 0);   // 4-pixel window view: KW taps are one TMA row
     c.pool(p1, 64, 1);   // MaxPool2d(2, 2) fused into the epilogue; the full-resolution tensor is never needed
     c.tc("basenet.slice1.3", a0, B, H, W, 64, nullptr, 64, 1, 1, 1);
     c.tc("basenet.slice1.7", p1, B, H2, W2, 64, a2, 128, 1, 1, 1);
@@ -326,12 +370,16 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     c.tc("upconv3.conv.3", u3a, B, H4, W4, 128, y3, 64, 1, 1, 1);
     { ProfScope ps_(h, "upsample.3", 0, false); launch_upsample2x(y3, 64, B, H4, W4, 64, cat4, 192, f16, s); }
     c.tc("upconv4.conv.0", cat4, B, H2, W2, 192, u4a, 64, 1, 0, 0);
-    c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat, 32, 1, 1, 1);
-    c.tc("conv_cls.0", feat, B, H2, W2, 32, c0, 32, 1, 1, 1);
-    c.tc("conv_cls.2", c0, B, H2, W2, 32, c2, 32, 1, 1, 1);
+    c.rows(0, W2p);
+    c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat + 32, 32, 1, 1, 1);
+    c.rows(W2p, W2p);
+    c.tc("conv_cls.0", feat, B, H2, W2, 32, c0 + 32, 32, 1, 1, 0);
+    c.rows(W2p, W2p);
+    c.tc("conv_cls.2", c0, B, H2, W2, 32, c2 + 32, 32, 1, 1, 0);
+    c.rows(W2p, 0);
     // conv_cls.4 + ReLU with conv_cls.6 + ReLU + conv_cls.8 (both 1x1) applied in the epilogue registers (fp32)
     c.tail(h->f32["craft.cls_tail"], sc);
-    c.tc("conv_cls.4", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 1);
+    c.tc("conv_cls.4", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 0);
     h->launches += 4;  // 1 max-pool (3x3 s1) + 3 up-samplings
     if (c.rc != LOCR_OK) return c.rc;
     LOCR_CUDA_OK(cudaGetLastError());
@@ -341,7 +389,7 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     dbg(h, "relu4_3", cat2 + 256, 0, {B, H8, W8, 512}, 768);
     dbg(h, "relu5_3", cat1 + 1024, 0, {B, H16, W16, 512}, 1536);
     dbg(h, "fc7", cat1, 0, {B, H16, W16, 1024}, 1536);
-    dbg(h, "feature", feat, 0, {B, H2, W2, 32}, 32);
+    dbg(h, "feature", feat, 0, {B, H2, (int)W2p, 32}, 32);   // row-padded: columns 1 .. W/2 hold the tensor
     dbg(h, "score", sc, 1, {B, H2, W2, 2}, 2);
     *score = sc;
     return LOCR_OK;

@@ -29,6 +29,7 @@ struct ConvW {
     int cin = 0, cout = 0, cout_pad = 0, kh = 1, kw = 1;
     int cin_real = 0;        // input channels of the reference layer (cin may be zero-padded to 16)
     int cin_wrap = 0;        // split-precision input: K channels [hi|lo|hi] = 3C read from a 2C-channel tensor
+    int window = 0;          // 1: weights packed for the 4-pixel window view of a 3x3 conv (conv_tc.cuh: x_row_px)
 };
 
 struct DebugTensor {
@@ -57,6 +58,7 @@ struct locr_handle {
     std::map<std::string, float*> f32;   // misc fp32 device arrays (TPS buffers, FC weights, attention weights)
     void* lstm_whh[2] = {nullptr, nullptr};
     std::map<std::string, std::pair<void*, size_t>> buffers;  // named activation buffers, grown on demand
+    std::map<std::string, std::pair<void*, size_t>> zeroed;   // row-padded buffers: (pointer, bytes) last zero-filled
     std::map<std::string, locr::DebugTensor> dbg;
     std::vector<void*> owned;  // weight allocations
     // per-launch profiling of the tensor-core conv kernel (bench.py roofline): event pairs + algorithmic FLOPs

@@ -130,20 +130,27 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
                       long img_stride, uint16_t* __restrict__ out, int f16) {
     const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
     const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
-    const uint32_t total = (uint32_t)B * H * W;   // < 2^31, checked by the launcher
+    // output rows are padded to W + 3 pixels: column 0 and columns W + 1, W + 2 are zero (conv_tc.cuh: x_row_px)
+    const uint32_t Wp = (uint32_t)W + 3;
+    const uint32_t total = (uint32_t)B * H * Wp;   // < 2^31, checked by the caller
     for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
-        const int x = (int)(pix % (uint32_t)W);
-        const uint32_t rest = pix / (uint32_t)W;
+        const int xp = (int)(pix % Wp);
+        const uint32_t rest = pix / Wp;
         const int y = (int)(rest % (uint32_t)H);
         const int b = (int)(rest / (uint32_t)H);
+        const int x = xp - 1;
+        uint4* o = reinterpret_cast<uint4*>(out + (long)pix * 16);
+        o[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (x < 0 || x >= W) {
+            o[0] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         const bool inside = (y < img_h) && (x < img_w);
         const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
-        uint4* o = reinterpret_cast<uint4*>(out + (long)pix * 16);
         o[0] = pack8(v, f16);
-        o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -580,7 +587,7 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, void* out, int is_f16, cudaStream_t s) {
-    const long total = (long)B * H * W;
+    const long total = (long)B * H * (W + 3);
     preproc_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
                                                                (uint16_t*)out, is_f16);
 }

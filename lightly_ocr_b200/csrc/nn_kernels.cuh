@@ -22,7 +22,8 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
 //   pool     : f32 mode only; writes MaxPool2d(2, 2) of the activated output instead, [B][H/2][W/2][Cout]
 
 // CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
-// channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.
+// channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.  Output rows are padded to W + 3
+// pixels (one zero pixel on the left, two on the right): out is [B][H][W + 3][16] (conv_tc.cuh: x_row_px).
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, void* out, int is_f16, cudaStream_t s);
 

@@ -50,6 +50,9 @@ def test_craft_score_maps(oracle_mods, act):
     for name in ("slice1.0", "relu2_2", "relu3_2", "relu4_3", "relu5_3", "fc7", "feature"):
         g = eng.debug_read(name)
         r = taps[name].permute(0, 2, 3, 1).numpy()
+        if g.shape[2] == r.shape[2] + 3:       # row-padded tensor: one zero pixel left, two right
+            assert not g[:, :, 0].any() and not g[:, :, -2:].any()
+            g = g[:, :, 1:-2]
         rel = np.abs(g - r).max() / max(np.abs(r).max(), 1e-6)
         print("%s %-9s rel max err %.4g" % (act, name, rel))
         assert rel < (0.05 if act == "bf16" else 0.01), (name, rel)

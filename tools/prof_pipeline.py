@@ -10,9 +10,10 @@ from lightly_ocr_b200.synth import receipts, weights
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-r = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
+head = sys.argv[3] if len(sys.argv) > 3 else "CTC"
+r = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head=head)
 r.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
-r.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, "CTC"))
+r.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, head))
 batch = [receipts.receipt(i) for i in range(n)]
 for _ in range(2):
     _, out = r.ocr(batch)
