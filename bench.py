@@ -25,10 +25,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-RECEIPTS_PER_STEP = 16
-LANES = 2                      # host threads per GPU, each with its own liblocr handle/stream: while one lane sorts
-                               # rects / copies results on the host, the other lane's kernels keep the GPU busy
-POOL = 32                      # distinct receipts cycled through (118 MB of pixels)
+LANES = int(os.environ.get("LOCR_BENCH_LANES", "2"))   # host threads per GPU, each with its own liblocr handle/stream:
+                               # while one lane sorts rects / copies results on the host, the other lanes' kernels
+                               # keep the GPU busy
+RECEIPTS_PER_STEP = 8 * LANES  # 8 receipts per lane and step (one CRAFT launch sequence over 8 canvases)
+POOL = 2 * RECEIPTS_PER_STEP   # distinct receipts cycled through (3.7 MB of pixels each)
 METRIC = "receipts_per_sec_1280px_craft_crnn_ctc"
 UNIT = "receipts/s"
 CRAFT_FLOPS = 874.217e9        # per 1280x960 canvas
