@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 LANES = int(os.environ.get("LOCR_BENCH_LANES", "2"))   # host threads per GPU, each with its own liblocr handle/stream:
                                # while one lane sorts rects / copies results on the host, the other lanes' kernels
                                # keep the GPU busy
-RECEIPTS_PER_STEP = 8 * LANES  # 8 receipts per lane and step (one CRAFT launch sequence over 8 canvases)
+PER_LANE = int(os.environ.get("LOCR_BENCH_PER_LANE", "8"))
+RECEIPTS_PER_STEP = PER_LANE * LANES  # receipts per lane and step (one CRAFT launch sequence over that many canvases)
 POOL = 2 * RECEIPTS_PER_STEP   # distinct receipts cycled through (3.7 MB of pixels each)
 METRIC = "receipts_per_sec_1280px_craft_crnn_ctc"
 UNIT = "receipts/s"

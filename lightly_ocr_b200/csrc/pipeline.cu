@@ -1,5 +1,6 @@
 // The product entry points of the C ABI: locr_detect, locr_recognize, locr_recognize_boxes.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -12,7 +13,18 @@ using namespace locr;
 namespace {
 
 constexpr int kTextStride = 128;
-constexpr int kMaxChunk = 8;  // images per CRAFT forward (activations: ~0.6 GB per 1280x960 image)
+constexpr int kMaxChunkCap = 32;
+// images per CRAFT forward (activations: ~0.6 GB per 1280x960 image); LOCR_CRAFT_CHUNK overrides (experiments)
+int max_chunk() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("LOCR_CRAFT_CHUNK");
+        v = e ? atoi(e) : 8;
+        if (v < 1) v = 1;
+        if (v > kMaxChunkCap) v = kMaxChunkCap;
+    }
+    return v;
+}
 
 struct Pinned {
     void* p = nullptr;
@@ -127,7 +139,7 @@ static int detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, 
     int i0 = 0;
     while (i0 < n) {
         int i1 = i0 + 1;
-        while (i1 < n && i1 - i0 < kMaxChunk && heights[i1] == heights[i0] && widths[i1] == widths[i0] &&
+        while (i1 < n && i1 - i0 < max_chunk() && heights[i1] == heights[i0] && widths[i1] == widths[i0] &&
                img_off[i1] - img_off[i1 - 1] == (size_t)heights[i0] * widths[i0] * 3)
             ++i1;
         const int B = i1 - i0, ih = heights[i0], iw = widths[i0];
@@ -167,7 +179,7 @@ static int detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, 
         if (nl < 0) return h->fail(LOCR_ERR_INVALID, "locr_detect: score map larger than 1024 x 1024");
         h->launches += nl;
         LOCR_CUDA_OK(cudaGetLastError());
-        int32_t counts[kMaxChunk * 2];
+        int32_t counts[kMaxChunkCap * 2];
         LOCR_CUDA_OK(cudaMemcpyAsync(counts, d_counts, (size_t)B * 2 * 4, cudaMemcpyDeviceToHost, s));
         LOCR_CUDA_OK(cudaStreamSynchronize(s));
         for (int b = 0; b < B; ++b) {
