@@ -90,26 +90,100 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     }
 }
 
-// text_score = text > low_text, link_score = link > link_threshold (cv2.threshold THRESH_BINARY is strict);
-// foreground = clip(text_score + link_score, 0, 1).
-__global__ void pp_init(const float2* __restrict__ score, long npix, float low_text, float link_thr,
-                        int* __restrict__ parent, uint8_t* __restrict__ flags) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
-        const float2 v = __ldg(&score[i]);
-        const int f = (v.x > low_text ? 1 : 0) | (v.y > link_thr ? 2 : 0);
-        flags[i] = (uint8_t)f;
-        parent[i] = f ? (int)i : -1;
+// Thresholds + tile-local labelling with shared-memory staging.
+//   text_score = text > low_text, link_score = link > link_threshold (cv2.threshold THRESH_BINARY is strict);
+//   foreground = clip(text_score + link_score, 0, 1)                                   (det_utils.py:37-44)
+// One CTA = one 32 x 32 tile of one score map: the flags and a union-find over LOCAL indices live in shared memory
+// (4-connectivity, atomicMin so that the smallest raster index becomes the root, which is also the smallest global
+// index of the tile's part of the component), then every pixel is written to the global parent array already
+// flattened to its tile root.  pp_merge_borders afterwards unites across tile edges only (1/16 of the pixels).
+constexpr int kTile = 32;
+
+__device__ __forceinline__ int uf_find_s(const int* parent, int i) {
+    int p = parent[i];
+    while (p != i) {
+        i = p;
+        p = parent[i];
+    }
+    return i;
+}
+__device__ __forceinline__ void uf_unite_s(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find_s(parent, a);
+        b = uf_find_s(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
     }
 }
 
-__global__ void pp_merge(int* __restrict__ parent, const uint8_t* __restrict__ flags, int B, int H, int W) {
-    const long npix = (long)B * H * W;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
-        if (!flags[i]) continue;
-        const int x = (int)(i % W);
-        const int y = (int)((i / W) % H);
-        if (x > 0 && flags[i - 1]) uf_unite(parent, (int)i, (int)i - 1);
-        if (y > 0 && flags[i - W]) uf_unite(parent, (int)i, (int)i - W);
+__global__ void __launch_bounds__(256)
+pp_label_tiles(const float2* __restrict__ score, int H, int W, float low_text, float link_thr,
+               int* __restrict__ parent, uint8_t* __restrict__ flags) {
+    __shared__ int lab[kTile * kTile];
+    __shared__ uint8_t fl[kTile * kTile];
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int img = blockIdx.z * H * W;
+    for (int l = threadIdx.x; l < kTile * kTile; l += 256) {
+        const int x = x0 + (l & (kTile - 1)), y = y0 + (l >> 5);
+        int f = 0;
+        if (x < W && y < H) {
+            const float2 v = __ldg(&score[img + y * W + x]);
+            f = (v.x > low_text ? 1 : 0) | (v.y > link_thr ? 2 : 0);
+        }
+        fl[l] = (uint8_t)f;
+        lab[l] = f ? l : -1;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < kTile * kTile; l += 256) {
+        if (!fl[l]) continue;
+        if ((l & (kTile - 1)) > 0 && fl[l - 1]) uf_unite_s(lab, l, l - 1);
+        if (l >= kTile && fl[l - kTile]) uf_unite_s(lab, l, l - kTile);
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < kTile * kTile; l += 256) {
+        const int x = x0 + (l & (kTile - 1)), y = y0 + (l >> 5);
+        if (x >= W || y >= H) continue;
+        const int g = img + y * W + x;
+        flags[g] = fl[l];
+        if (fl[l]) {
+            const int r = uf_find_s(lab, l);
+            parent[g] = img + (y0 + (r >> 5)) * W + x0 + (r & (kTile - 1));
+        } else {
+            parent[g] = -1;
+        }
+    }
+}
+
+// Unites the tile-local components across tile edges: only pixels of a tile's first column / first row have a
+// neighbour in another tile.  One thread per edge pixel.
+__global__ void __launch_bounds__(256)
+pp_merge_borders(int* __restrict__ parent, const uint8_t* __restrict__ flags, int B, int H, int W) {
+    const int tx = (W + kTile - 1) / kTile, ty = (H + kTile - 1) / kTile;
+    const int per_img = (tx - 1) * H + (ty - 1) * W;      // vertical seams, then horizontal seams
+    const int total = B * per_img;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / per_img;
+        int r = i - b * per_img;
+        int x, y, other;
+        if (r < (tx - 1) * H) {               // pixel (x = k * 32, y) against its left neighbour
+            x = (r / H + 1) * kTile;
+            y = r % H;
+            other = -1;
+        } else {                              // pixel (x, y = k * 32) against its upper neighbour
+            r -= (tx - 1) * H;
+            y = (r / W + 1) * kTile;
+            x = r % W;
+            other = -W;
+        }
+        const int g = b * H * W + y * W + x;
+        if (flags[g] && flags[g + other]) uf_unite(parent, g, g + other);
     }
 }
 
@@ -653,8 +727,12 @@ int launch_postproc(const float* score, const PostprocParams& p, void* workspace
     const int HW = p.H * p.W;
     const int bpi = (HW + kScanBlock - 1) / kScanBlock;
     const float2* sc = reinterpret_cast<const float2*>(score);
-    pp_init<<<grid_for(npix, 256), 256, 0, s>>>(sc, npix, p.low_text, p.link_threshold, w.parent, w.flags);
-    pp_merge<<<grid_for(npix, 256), 256, 0, s>>>(w.parent, w.flags, p.B, p.H, p.W);
+    {
+        const dim3 tiles((p.W + kTile - 1) / kTile, (p.H + kTile - 1) / kTile, p.B);
+        pp_label_tiles<<<tiles, 256, 0, s>>>(sc, p.H, p.W, p.low_text, p.link_threshold, w.parent, w.flags);
+        const long seams = (long)p.B * ((long)(tiles.x - 1) * p.H + (long)(tiles.y - 1) * p.W);
+        pp_merge_borders<<<grid_for(seams > 0 ? seams : 1, 256), 256, 0, s>>>(w.parent, w.flags, p.B, p.H, p.W);
+    }
     pp_flatten_count<<<dim3(bpi, p.B), 256, 0, s>>>(w.parent, HW, bpi, w.blocksum);
     pp_scan<<<p.B, 1024, 0, s>>>(w.blocksum, bpi, w.ncomp);
     pp_assign<<<dim3(bpi, p.B), 1024, 0, s>>>(w.parent, HW, bpi, w.blocksum, w.rootid, w.area, w.minx, w.miny, w.maxx,
