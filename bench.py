@@ -121,22 +121,24 @@ def cpu_oracle_sample(n_threads, full=False):
 
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference cannot travel to
-    the GPU box) on the box's host cores, all threads, one quarter receipt per step."""
+    the GPU box) on the box's host cores, all threads, one whole 1280x960 receipt per step."""
     if rank != 0:
         return
     import torch
+    from lightly_ocr_b200.synth import receipts
     from oracle import ocr_ref
     cores = os.cpu_count() or 1
-    _, _, (craft_sd, crnn_sd, img) = cpu_oracle_sample(cores)          # also serves as first warm-up
-    for _ in range(max(args.warmup - 1, 0)):
-        ocr_ref.get_text(craft_sd, crnn_sd, img, "CTC")
+    _, _, (craft_sd, crnn_sd, img) = cpu_oracle_sample(cores)          # quarter receipt: first warm-up
+    pool = [receipts.receipt(i) for i in range(4)]
+    for w in range(max(args.warmup - 1, 0)):
+        ocr_ref.get_text(craft_sd, crnn_sd, pool[w % len(pool)], "CTC")
     t0 = time.perf_counter()
     crops = 0
-    for _ in range(args.steps):
-        crops += len(ocr_ref.get_text(craft_sd, crnn_sd, img, "CTC"))
+    for k in range(args.steps):
+        crops += len(ocr_ref.get_text(craft_sd, crnn_sd, pool[k % len(pool)], "CTC"))
     dt = time.perf_counter() - t0
-    value = 0.25 * args.steps / dt
-    sample = "one 640x480 window (1/4 of a 1280x960 receipt, ~%d crops) per step" % (crops // max(args.steps, 1))
+    value = args.steps / dt
+    sample = "one whole 1280x960 receipt (~%d crops) per step, %d steps" % (crops // max(args.steps, 1), args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
