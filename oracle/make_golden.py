@@ -155,15 +155,22 @@ def main():
             out["crnn_rectified"] = tr.numpy()
             out["crnn_visual"] = vf.numpy().astype(np.float32)
 
-            if head == "CTC":
-                # -- end to end: getText on one full receipt through the reference pipeline (pipeline.py:65-87)
-                import cv2
-                path = os.path.join(scratch, "receipt1.png")
-                cv2.imwrite(path, receipts.receipt(1))
+            # -- end to end: getText on full receipts through the reference pipeline (pipeline.py:65-87)
+            import cv2
+            texts, confs, counts = [], [], []
+            for rid in ((1, 2, 3) if head == "CTC" else (2,)):
+                path = os.path.join(scratch, "receipt%d.png" % rid)
+                cv2.imwrite(path, receipts.receipt(rid))
                 with contextlib.redirect_stdout(io.StringIO()):
                     res = ref_pipeline.getText(path, detector, recognizer, write=False)
-                out["e2e_text"] = np.array([v[0] for v in res.values()])
-                out["e2e_conf"] = np.array([float(k) for k in res.keys()], np.float32)
+                vals = [v[0] if isinstance(v, list) else v for v in res.values()]
+                texts.extend(vals)
+                confs.extend(float(k) for k in res.keys())
+                counts.append(len(vals))
+            out["e2e_receipts"] = np.array((1, 2, 3) if head == "CTC" else (2,), np.int32)
+            out["e2e_counts"] = np.array(counts, np.int32)
+            out["e2e_text"] = np.array(texts)
+            out["e2e_conf"] = np.array(confs, np.float32)
             np.savez_compressed(os.path.join(GOLDEN, "ref_%s.npz" % head.lower()), **out)
             print(head, {k: getattr(v, "shape", None) for k, v in out.items()})
         finally:

@@ -88,12 +88,48 @@ def test_dropin_ctc_end_to_end(tmp_path, eager):
     assert abs(len(got) - len(want)) <= 2
     if eager == "1":
         # the same receipt through the LIVE reference pipeline (pipeline.getText, recorded by oracle/make_golden.py)
-        gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ctc.npz"))["e2e_text"].tolist()
+        gz = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ctc.npz"))
+        gold = gz["e2e_text"][:int(gz["e2e_counts"][0])].tolist()
         gmatch = sum(g == w for g, w in zip(got, gold)) / max(len(gold), 1)
         print("strings vs the live reference's getText on receipt(1): %d / %d identical" %
               (sum(g == w for g, w in zip(got, gold)), len(gold)))
         assert len(got) == len(gold) and gmatch >= 0.985
     assert match >= 0.985
+
+
+@pytest.mark.parametrize("head", ["CTC", "Attention"])
+def test_strings_and_confidences_match_live_reference_goldens(head):
+    """The receipts whose `pipeline.getText` output was recorded from the LIVE reference (tests/golden, made by
+    oracle/make_golden.py): the CUDA path must return the same number of results, >= 99.5% identical strings, and
+    confidences (products of 26 soft-max maxima) within 0.5% at the median and 3% at the 95th percentile where the strings
+    agree (fp16 storage against the reference's fp32; the maximum is reported only: a rect that moves by one pixel
+    because a score-map pixel crossed the threshold gives the same string from a different crop)."""
+    from lightly_ocr_b200 import bridge
+    from oracle import receipts, weights
+    gz = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_%s.npz" % head.lower()))
+    runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head=head)
+    runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
+    runner.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, head))
+    images = [receipts.receipt(int(r)) for r in gz["e2e_receipts"]]
+    per_image, out = runner.ocr(images)
+    got_t, got_c, k = [], [], 0
+    for rects in per_image:
+        for _ in rects:
+            # the reference's result dict only holds crops whose decode produced an entry (Attention: an [s] was found)
+            if head == "CTC" or out["has_eos"][k] == 1:
+                got_t.append(out["text"][k])
+                got_c.append(float(out["conf"][k]))
+            k += 1
+    want_t, want_c = [str(t) for t in gz["e2e_text"]], gz["e2e_conf"].astype(np.float64)
+    assert len(got_t) == len(want_t) == int(gz["e2e_counts"].sum())
+    same = [g == w for g, w in zip(got_t, want_t)]
+    rel = np.array([abs(c - w) / w for c, w, s in zip(got_c, want_c, same) if s])
+    ab = np.array([abs(c - w) for c, w, s in zip(got_c, want_c, same) if s])
+    print("%s: %d / %d strings identical to the live reference; confidence error: max abs %.4f, median rel %.5f, "
+          "95th percentile rel %.4f" % (head, sum(same), len(same), ab.max(), np.median(rel), np.quantile(rel, 0.95)))
+    assert sum(same) / len(same) >= 0.995
+    assert np.median(rel) < 0.005 and np.quantile(rel, 0.95) < 0.03
+    runner.close()
 
 
 def test_string_gate_many_receipts():
