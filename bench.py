@@ -93,8 +93,15 @@ class ClockSampler:
 
 
 def make_receipts(rank, count):
+    """Decoded BGR receipts in PINNED host memory (the e2e leg copies them to the device every step)."""
+    import torch
     from lightly_ocr_b200.synth import receipts
-    return [receipts.receipt(1000 * rank + i) for i in range(count)]
+    out = []
+    for i in range(count):
+        t = torch.from_numpy(receipts.receipt(1000 * rank + i)).pin_memory()
+        out.append(t.numpy())
+    make_receipts.keep = getattr(make_receipts, "keep", []) + out     # the arrays view the pinned tensors' storage
+    return out
 
 
 def cpu_oracle_sample(n_threads, full=False):

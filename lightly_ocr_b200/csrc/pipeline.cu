@@ -222,15 +222,29 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
         total_bytes += (size_t)heights[i] * widths[i] * 3;
     }
     uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
-    uint8_t* h_img = (uint8_t*)staging(0).get(total_bytes);
-    if (!d_img || !h_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
+    if (!d_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
+    // Images that already live in pinned (page-locked) host memory with packed rows are copied straight from the
+    // caller's buffer; everything else goes through the per-thread pinned staging buffer first.
+    uint8_t* h_img = nullptr;
     for (int i = 0; i < n; ++i) {
         const size_t row = (size_t)widths[i] * 3;
         const size_t st = strides ? (size_t)strides[i] : row;
+        cudaPointerAttributes attr;
+        const bool pinned = st == row && cudaPointerGetAttributes(&attr, bgr[i]) == cudaSuccess &&
+                            attr.type == cudaMemoryTypeHost;
+        if (pinned) {
+            LOCR_CUDA_OK(cudaMemcpyAsync(d_img + img_off[i], bgr[i], row * heights[i], cudaMemcpyHostToDevice, s));
+            continue;
+        }
+        cudaGetLastError();   // cudaPointerGetAttributes on plain pageable memory may leave an error behind
+        if (h_img == nullptr) {
+            h_img = (uint8_t*)staging(0).get(total_bytes);
+            if (!h_img) return h->fail(LOCR_ERR_CUDA, "pinned staging allocation failed");
+        }
         if (st == row) memcpy(h_img + img_off[i], bgr[i], row * heights[i]);
         else for (int y = 0; y < heights[i]; ++y) memcpy(h_img + img_off[i] + y * row, bgr[i] + y * st, row);
+        LOCR_CUDA_OK(cudaMemcpyAsync(d_img + img_off[i], h_img + img_off[i], row * heights[i], cudaMemcpyHostToDevice, s));
     }
-    LOCR_CUDA_OK(cudaMemcpyAsync(d_img, h_img, total_bytes, cudaMemcpyHostToDevice, s));
     h->resident.clear();
     for (int i = 0; i < n; ++i) h->resident.push_back({d_img + img_off[i], heights[i], widths[i]});
     return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
