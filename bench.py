@@ -37,6 +37,16 @@ CRAFT_FLOPS = 874.217e9        # per 1280x960 canvas
 CRNN_FLOPS_PER_CROP = 10.593e9
 
 
+def conv_traffic():
+    """DRAM bytes per conv_tc launch (mean over one 8-receipt pass) from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_conv_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["bytes_per_launch"]), "profiles/r01c_conv_traffic.json: %s" % t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -300,7 +310,9 @@ def main():
             "gpu_launches": n_launches,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all layers)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": conv_traffic()[0],
+                         "traffic_unit": "DRAM bytes per launch (mean over the conv launches of one 8-receipt pass)",
+                         "traffic_source": conv_traffic()[1],
                          "peak_source": "bf16_tflops_sustained, %s (fp16 and bf16 share the tensor rate)" % which,
                          "launches": conv_launches,
                          "timed_region": "separate single-lane pass of %d steps x %d receipts right after the timed "
