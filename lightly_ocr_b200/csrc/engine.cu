@@ -505,20 +505,33 @@ int engine_finalize_crnn(locr_handle* h) {
         if (!h2h || !h2hb || !sw || !wih || !whh || !bih || !bhh || !gw || !gb || wih->shape[1] != 256 + C ||
             gw->shape[0] != C)
             return h->fail(LOCR_ERR_STATE, "missing or malformed attention tensors");
-        upload_f32(h, "att.h2h_wt", transpose(h2h->data, 256, 256));
+        // the decoder's big matrices are stored in 16 bits like every other weight of the path (the kernel is bound by
+        // streaming them from L2 once per step); biases, the score vector, the one-hot rows and the generator stay fp32
+        {
+            std::vector<uint16_t> h2h16((size_t)256 * 256);
+            for (int k = 0; k < 256; ++k)
+                for (int j = 0; j < 256; ++j)
+                    h2h16[(size_t)k * 256 + j] = f32_to_act(h2h->data[(size_t)j * 256 + k], h->cfg.act_dtype);
+            h->u16["att.h2h_wt"] = dev_upload(h, h2h16);
+        }
         upload_f32(h, "att.h2h_b", h2hb->data);
         upload_f32(h, "att.score", sw->data);
         const int K = 256 + C;
-        std::vector<float> wih_t((size_t)K * 256 * 4), whh_t((size_t)256 * 256 * 4), gbias(1024);
-        for (int k = 0; k < K; ++k)
-            for (int j = 0; j < 256; ++j)
-                for (int q = 0; q < 4; ++q) wih_t[((size_t)k * 256 + j) * 4 + q] = wih->data[(size_t)(q * 256 + j) * K + k];
+        std::vector<uint16_t> wg((size_t)256 * 256 * 8);
+        std::vector<float> woh((size_t)C * 256 * 4), gbias(1024);
         for (int k = 0; k < 256; ++k)
             for (int j = 0; j < 256; ++j)
-                for (int q = 0; q < 4; ++q) whh_t[((size_t)k * 256 + j) * 4 + q] = whh->data[(size_t)(q * 256 + j) * 256 + k];
+                for (int q = 0; q < 4; ++q) {
+                    wg[((size_t)k * 256 + j) * 8 + q] = f32_to_act(wih->data[(size_t)(q * 256 + j) * K + k], h->cfg.act_dtype);
+                    wg[((size_t)k * 256 + j) * 8 + 4 + q] = f32_to_act(whh->data[(size_t)(q * 256 + j) * 256 + k], h->cfg.act_dtype);
+                }
+        for (int v = 0; v < C; ++v)
+            for (int j = 0; j < 256; ++j)
+                for (int q = 0; q < 4; ++q) woh[((size_t)v * 256 + j) * 4 + q] = wih->data[(size_t)(q * 256 + j) * K + 256 + v];
         for (int i = 0; i < 1024; ++i) gbias[i] = bih->data[i] + bhh->data[i];
-        upload_f32(h, "att.wih_t", wih_t);
-        upload_f32(h, "att.whh_t", whh_t);
+        h->u16["att.wg"] = dev_upload(h, wg);
+        upload_f32(h, "att.woh", woh);
+        if (!h->u16["att.h2h_wt"] || !h->u16["att.wg"]) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
         upload_f32(h, "att.gate_b", gbias);
         upload_f32(h, "att.gen_w", gw->data);
         upload_f32(h, "att.gen_b", gb->data);
@@ -642,8 +655,8 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
         c.tc("Prediction.attention_cell.i2h", s1, 1, 1, R, 256, fproj, 256, 0, 0, 0, 1, 1, 1);
         if (c.rc == LOCR_OK) {
             AttnWeights w;
-            w.h2h_wt = h->f32["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
-            w.wih_t = h->f32["att.wih_t"]; w.whh_t = h->f32["att.whh_t"]; w.gate_b = h->f32["att.gate_b"];
+            w.h2h_wt = (const uint16_t*)h->u16["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
+            w.wg = (const uint16_t*)h->u16["att.wg"]; w.woh = h->f32["att.woh"]; w.gate_b = h->f32["att.gate_b"];
             w.gen_w = h->f32["att.gen_w"]; w.gen_b = h->f32["att.gen_b"];
             { ProfScope ps_(h, "attention", 0, false); launch_attention(s1, fproj, w, lg, B, C, f16, s); }
             h->launches++;

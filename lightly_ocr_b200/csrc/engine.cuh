@@ -57,6 +57,7 @@ struct locr_handle {
     std::map<std::string, locr::ConvW> conv;
     std::map<std::string, float*> f32;   // misc fp32 device arrays (TPS buffers, FC weights, attention weights)
     void* lstm_whh[2] = {nullptr, nullptr};
+    std::map<std::string, void*> u16;    // misc 16-bit device arrays (attention decoder weights)
     std::map<std::string, std::pair<void*, size_t>> buffers;  // named activation buffers, grown on demand
     std::map<std::string, std::pair<void*, size_t>> zeroed;   // row-padded buffers: (pointer, bytes) last zero-filled
     std::map<std::string, locr::DebugTensor> dbg;

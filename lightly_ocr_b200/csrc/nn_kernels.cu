@@ -353,8 +353,9 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
         float hp[kAttG];
 #pragma unroll
         for (int g = 0; g < kAttG; ++g) hp[g] = w.h2h_b[j];
+#pragma unroll 8
         for (int k = 0; k < 256; ++k) {
-            const float wv = __ldg(&w.h2h_wt[k * 256 + j]);
+            const float wv = act2f(__ldg(&w.h2h_wt[k * 256 + j]), f16);
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) hp[g] = fmaf(wv, hs[g][k], hp[g]);
         }
@@ -405,15 +406,19 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
         float acc[kAttG][4];
 #pragma unroll
         for (int g = 0; g < kAttG; ++g) {
-            const float4 oh = __ldg(reinterpret_cast<const float4*>(w.wih_t + ((size_t)(256 + prev[g]) * 256 + j) * 4));
+            const float4 oh = __ldg(reinterpret_cast<const float4*>(w.woh + ((size_t)prev[g] * 256 + j) * 4));
             acc[g][0] = w.gate_b[j] + oh.x;
             acc[g][1] = w.gate_b[256 + j] + oh.y;
             acc[g][2] = w.gate_b[512 + j] + oh.z;
             acc[g][3] = w.gate_b[768 + j] + oh.w;
         }
+#pragma unroll 4
         for (int k = 0; k < 256; ++k) {
-            const float4 wi = __ldg(reinterpret_cast<const float4*>(w.wih_t + ((size_t)k * 256 + j) * 4));
-            const float4 wh = __ldg(reinterpret_cast<const float4*>(w.whh_t + ((size_t)k * 256 + j) * 4));
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(w.wg + ((size_t)k * 256 + j) * 8));
+            float wf[8];
+            unpack8(u, wf, f16);
+            const float4 wi = make_float4(wf[0], wf[1], wf[2], wf[3]);
+            const float4 wh = make_float4(wf[4], wf[5], wf[6], wf[7]);
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) {
                 const float cv = ctx[g][k], hv = hs[g][k];

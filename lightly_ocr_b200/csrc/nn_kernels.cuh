@@ -52,12 +52,12 @@ cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, 
                            cudaStream_t s);
 
 struct AttnWeights {
-    const float* h2h_wt;   // [256 k][256 j]
-    const float* h2h_b;    // [256]
-    const float* score_w;  // [256]
-    const float* wih_t;    // [256+C k][256 j][4 gates]   (LSTMCell weight_ih, context part then one-hot part)
-    const float* whh_t;    // [256 k][256 j][4 gates]
-    const float* gate_b;   // [4][256]  b_ih + b_hh
+    const uint16_t* h2h_wt;  // 16-bit [256 k][256 j]
+    const float* h2h_b;      // [256]
+    const float* score_w;    // [256]
+    const uint16_t* wg;      // 16-bit [256 k][256 j][8] = LSTMCell weight_ih (context part) gates i,f,g,o then weight_hh
+    const float* woh;        // fp32 [C][256 j][4 gates]: the one-hot part of weight_ih (one row is read per step)
+    const float* gate_b;     // [4][256]  b_ih + b_hh
     const float* gen_w;    // [C][256]
     const float* gen_b;    // [C]
 };

@@ -264,9 +264,9 @@ def train_attention():
          "score.weight": dec.score.weight, "rnn.weight_ih": dec.rnn.weight_ih, "rnn.weight_hh": dec.rnn.weight_hh,
          "rnn.bias_ih": dec.rnn.bias_ih, "rnn.bias_hh": dec.rnn.bias_hh}
     for k, v in m.items():
-        sd["Prediction.attention_cell." + k] = v.detach().cpu().float().numpy()
-    sd["Prediction.generator.weight"] = dec.generator.weight.detach().cpu().float().numpy()
-    sd["Prediction.generator.bias"] = dec.generator.bias.detach().cpu().float().numpy()
+        sd["Prediction.attention_cell." + k] = v.detach().cpu().half().numpy()      # fp16-representable
+    sd["Prediction.generator.weight"] = dec.generator.weight.detach().cpu().half().numpy()
+    sd["Prediction.generator.bias"] = dec.generator.bias.detach().cpu().half().numpy()
     os.makedirs("gpurun_out", exist_ok=True)
     np.savez_compressed("gpurun_out/calib_crnn_attention_trained.npz", **sd)
     print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize("gpurun_out/calib_crnn_attention_trained.npz") / 1e6))
