@@ -199,7 +199,7 @@ def test_dropin_attention(tmp_path):
 
 
 def test_attention_string_gate():
-    """BASELINE config 5 (attention decoder end to end): all crops the GPU detects on 4 receipts, recognised by the CUDA
+    """BASELINE config 5 (attention decoder end to end): all crops the GPU detects on 8 receipts, recognised by the CUDA
     attention path and by the fp32 oracle (B = 1 semantics per crop); the strings cut at [s] must agree >= 99.5%."""
     from lightly_ocr_b200 import bridge
     from oracle import ocr_ref, receipts, weights
@@ -208,7 +208,7 @@ def test_attention_string_gate():
     runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="Attention")
     runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
     runner.load_state_dict(bridge.MODEL_CRNN, sd)
-    images = [receipts.receipt(s) for s in range(16, 20)]
+    images = [receipts.receipt(s) for s in range(16, 24)]
     per_image, out = runner.ocr(images, want_logits=True)
     xs = []
     for img, rects in zip(images, per_image):
@@ -222,10 +222,10 @@ def test_attention_string_gate():
                 s = ocr_ref.attn_decode_tokens(row.argmax(1))
                 want.append(s[:s.find("[s]")] if "[s]" in s else None)
     got = [t if e == 1 else ("" if e == -1 else None) for t, e in zip(out["text"], out["has_eos"])]
-    assert len(got) == len(want) and len(got) > 250
+    assert len(got) == len(want) and len(got) > 500
     same = sum(g == w for g, w in zip(got, want))
     truth = []
-    for s in range(16, 20):
+    for s in range(16, 24):
         truth.extend(w[0] for w in receipts.receipt(s, return_words=True)[1])
     print("attention string gate: %d / %d identical to the fp32 oracle (%.4f); %d are rendered words" %
           (same, len(got), same / len(got), len(set(g for g in got if g) & set(truth))))
