@@ -206,37 +206,48 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
 }
 
 // ------------------------------------------------------------------------------------------- bilinear 2x
+// F.interpolate(scale 2, mode='bilinear', align_corners=False) (model.py:47,51,55).  One thread = 8 channels of one
+// SOURCE pixel (k, l) and its 2 x 2 block of output pixels: output row 2k + dy mixes source rows k - 1 + dy and k + dy
+// with weights 0.25 / 0.75 (dy = 0) or 0.75 / 0.25 (dy = 1), same for columns; rows / columns outside the tensor
+// clamp to the edge, which reproduces PyTorch's clamping of negative source coordinates and of the last index.  Nine
+// source loads feed four outputs (the plain per-output form needs sixteen) and the index arithmetic is shared.
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C,
                   uint16_t* __restrict__ out, long out_pitch, int f16) {
     const uint32_t groups = (uint32_t)C >> 3;
-    const int OH = 2 * H, OW = 2 * W;
-    const uint32_t total = (uint32_t)B * OH * OW * groups;   // < 2^31, checked by the launcher
+    const uint32_t total = (uint32_t)B * H * W * groups;   // < 2^31, checked by the launcher
+    const int OW = 2 * W;
     for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
         const uint32_t cg = gid % groups;
         const uint32_t pix = gid / groups;
-        const int ox = (int)(pix % (uint32_t)OW);
-        const uint32_t rest = pix / (uint32_t)OW;
-        const int oy = (int)(rest % (uint32_t)OH);
-        const int b = (int)(rest / (uint32_t)OH);
-        // PyTorch area_pixel_compute_source_index, align_corners=False, scale 0.5, negative sources clamp to 0
-        float sy = 0.5f * (oy + 0.5f) - 0.5f;
-        float sx = 0.5f * (ox + 0.5f) - 0.5f;
-        if (sy < 0.f) sy = 0.f;
-        if (sx < 0.f) sx = 0.f;
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-        const float ly = sy - y0, lx = sx - x0;
-        const float hy = 1.f - ly, hx = 1.f - lx;
+        const int l = (int)(pix % (uint32_t)W);
+        const uint32_t rest = pix / (uint32_t)W;
+        const int k = (int)(rest % (uint32_t)H);
+        const int b = (int)(rest / (uint32_t)H);
+        const int ks[3] = {k > 0 ? k - 1 : 0, k, k < H - 1 ? k + 1 : H - 1};
+        const int ls[3] = {l > 0 ? l - 1 : 0, l, l < W - 1 ? l + 1 : W - 1};
         const uint16_t* base = in + (long)b * H * W * in_pitch + cg * 8;
-        float a[8], bq[8], c[8], d[8], r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y0 * W + x0) * in_pitch)), a, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y0 * W + x1) * in_pitch)), bq, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y1 * W + x0) * in_pitch)), c, f16);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(y1 * W + x1) * in_pitch)), d, f16);
+        float v[3][3][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = hy * (hx * a[j] + lx * bq[j]) + ly * (hx * c[j] + lx * d[j]);
-        *reinterpret_cast<uint4*>(out + (long)pix * out_pitch + cg * 8) = pack8(r, f16);
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(ks[i] * W + ls[j]) * in_pitch)), v[i][j], f16);
+        uint16_t* obase = out + ((long)b * 2 * H * OW) * out_pitch + cg * 8;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            // PyTorch: y0 = floor(src), ly = src - y0, value = hy * row(y0) + ly * row(y1)
+            const float ly = dy == 0 ? 0.75f : 0.25f, hy = 1.f - ly;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const float lx = dx == 0 ? 0.75f : 0.25f, hx = 1.f - lx;
+                float r[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    r[c] = hy * (hx * v[dy][dx][c] + lx * v[dy][dx + 1][c]) + ly * (hx * v[dy + 1][dx][c] + lx * v[dy + 1][dx + 1][c]);
+                *reinterpret_cast<uint4*>(obase + ((long)(2 * k + dy) * OW + 2 * l + dx) * out_pitch) = pack8(r, f16);
+            }
+        }
     }
 }
 
@@ -607,7 +618,7 @@ void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, v
 
 void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch,
                        int is_f16, cudaStream_t s) {
-    const long total = (long)B * 4 * H * W * (C / 8);
+    const long total = (long)B * H * W * (C / 8);
     upsample2x_kernel<<<grid_for(total, 256), 256, 0, s>>>((const uint16_t*)in, in_pitch, B, H, W, C, (uint16_t*)out,
                                                            out_pitch, is_f16);
 }
