@@ -105,17 +105,22 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     ptx::cluster_wait_acquire();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // Producer and MMA-issuer warps run their loops on warp-uniform values; one elected lane issues the TMA / MMA
+    // instructions (a loop inside `if (lane == 0)` makes ptxas wrap every UTMALDG / UTCHMMA in an election loop).
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(wfull_bar, kWBytes);
             for (int kc = 0; kc < 4; ++kc)
                 ptx::tma_load_2d(w_buf + kc * kChunkBytes, &tmap_w, wfull_bar, kc * 64, dir * 1024 + rank * 128);
-            for (int step = 1; step < T; ++step) {
-                const int b = step & 1;
-                const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
-                const int t_prev = dir == 0 ? step - 1 : T - step;
-                ptx::mbar_wait_cluster(&hready_bar[b], par, 500);
+        }
+        for (int step = 1; step < T; ++step) {
+            const int b = step & 1;
+            const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
+            const int t_prev = dir == 0 ? step - 1 : T - step;
+            ptx::mbar_wait_cluster(&hready_bar[b], par, 500);
+            if (ptx::elect_one()) {
                 ptx::fence_proxy_async_all();
+#pragma unroll
                 for (int kc = 0; kc < 4; ++kc) {
                     ptx::mbar_arrive_expect_tx(&afull_bar[b * 4 + kc], kChunkBytes);
                     ptx::tma_load_3d(a_buf + b * kABytes + kc * kChunkBytes, &tmap_h, &afull_bar[b * 4 + kc],
@@ -124,27 +129,26 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, 128) >> 32);
-            const uint32_t a_lo0 = ((ptx::smem_u32(a_buf) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t w_lo0 = ((ptx::smem_u32(w_buf) & 0x3FFFFu) >> 4) | (1u << 16);
-            ptx::mbar_wait(wfull_bar, 0, 600);
-            for (int step = 1; step < T; ++step) {
-                const int b = step & 1;
-                const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
-                uint32_t accum = 0;
-                for (int kc = 0; kc < 4; ++kc) {
-                    ptx::mbar_wait(&afull_bar[b * 4 + kc], par, 610);
-                    ptx::tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + (uint32_t)((b * kABytes + kc * kChunkBytes) >> 4);
-                    const uint32_t w_lo = w_lo0 + (uint32_t)((kc * kChunkBytes) >> 4);
+        const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, 128) >> 32);
+        const uint32_t a_lo0 = ((ptx::smem_u32(a_buf) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t w_lo0 = ((ptx::smem_u32(w_buf) & 0x3FFFFu) >> 4) | (1u << 16);
+        ptx::mbar_wait(wfull_bar, 0, 600);
+        for (int step = 1; step < T; ++step) {
+            const int b = step & 1;
+            const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        ptx::umma_f16_lohi(tmem_base, a_lo + k * 2, desc_hi, w_lo + k * 2, desc_hi, p.idesc, accum);
-                        accum = 1;
-                    }
+            for (int kc = 0; kc < 4; ++kc) {
+                ptx::mbar_wait(&afull_bar[b * 4 + kc], par, 610);
+                ptx::tc_fence_after();
+                const uint32_t a_lo = a_lo0 + (uint32_t)((b * kABytes + kc * kChunkBytes) >> 4);
+                const uint32_t w_lo = w_lo0 + (uint32_t)((kc * kChunkBytes) >> 4);
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16_lohi(tmem_base, a_lo + k * 2, desc_hi, w_lo + k * 2, desc_hi, p.idesc,
+                                           (kc | k) ? 1u : 0u);
+                    if (kc == 3) ptx::umma_commit(tfull_bar);
                 }
-                ptx::umma_commit(tfull_bar);
             }
         }
     } else if (warp >= 4) {
