@@ -24,7 +24,19 @@
 #include "nn_kernels.cuh"
 #include "ptx.cuh"
 
+#ifndef LOCR_LSTM_TRACE
+#define LOCR_LSTM_TRACE 0   // tools only: per-step clock64 stamps of CTA (0, 0) into g_lstm_trace (locr_debug_lstm_trace)
+#endif
+
 namespace locr {
+
+#if LOCR_LSTM_TRACE
+__device__ long long g_lstm_trace[64 * 8];
+#define LSTM_STAMP(step, slot) \
+    do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) g_lstm_trace[(step) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define LSTM_STAMP(step, slot) do {} while (0)
+#endif
 
 namespace {
 
@@ -118,6 +130,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
             const int t_prev = dir == 0 ? step - 1 : T - step;
             ptx::mbar_wait_cluster(&hready_bar[b], par, 500);
+            LSTM_STAMP(step, 0);                      // all 64 arrivals seen
             if (ptx::elect_one()) {
                 ptx::fence_proxy_async_all();
 #pragma unroll
@@ -149,6 +162,8 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                                            (kc | k) ? 1u : 0u);
                     if (kc == 3) ptx::umma_commit(tfull_bar);
                 }
+                if (kc == 0) LSTM_STAMP(step, 1);     // first h chunk landed
+                if (kc == 3) LSTM_STAMP(step, 2);     // last chunk landed, MMAs issued
             }
         }
     } else if (warp >= 4) {
@@ -181,6 +196,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                 ptx::mbar_wait(tfull_bar, (uint32_t)((step - 1) & 1), 700);
                 ptx::tc_fence_after();
             }
+            if (warp == 4) LSTM_STAMP(step, 3);       // accumulator complete
             uint32_t hp[8];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -207,6 +223,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) hp[hf * 4 + q] = pack2h(hv[q * 2], hv[q * 2 + 1], p.is_f16);
             }
+            if (warp == 4) LSTM_STAMP(step, 4);       // gate math done
             if (valid) {
                 uint4* o = reinterpret_cast<uint4*>(out_base + (size_t)t * 512);
                 o[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
@@ -218,6 +235,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane < kCluster) ptx::mbar_arrive_remote_release(hready_remote[(step + 1) & 1]);
+                if (warp == 4) LSTM_STAMP(step, 5);   // h stored, peers signalled
                 // gate inputs of the next step: in flight while the cluster exchanges h_t and the MMAs run
                 const int tn = dir == 0 ? step + 1 : T - 2 - step;
                 const float4* xp4 = reinterpret_cast<const float4*>(xp_base + (size_t)tn * 2048);
@@ -292,5 +310,11 @@ cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, 
     lstm_cluster_kernel<<<grid, kThreadsLstm, smem, s>>>(mw, mh, p);
     return cudaGetLastError();
 }
+
+#if LOCR_LSTM_TRACE
+extern "C" __attribute__((visibility("default"))) int locr_debug_lstm_trace(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_lstm_trace, sizeof(long long) * 64 * 8);
+}
+#endif
 
 }  // namespace locr
