@@ -69,7 +69,8 @@ LOCR_API int locr_finalize(locr_handle* h, int model);
 
 /* CRAFT.process up to the rect list (net.py:100-107 = preproc :71-80, VGG_UNet forward model.py:39-61,
  * getDetBoxes det_utils.py:248-256, adjustResultCoordinates :259-265, getCoords net.py:82-98) for n images.
- *   bgr[i]     : uint8 HxWx3 (cv2.imread layout), row stride strides[i] bytes
+ *   bgr[i]     : uint8 HxWx3 (cv2.imread layout), row stride strides[i] bytes; packed images in pinned (page-locked)
+ *                host memory are copied to the device straight from the caller's buffer, others are staged first
  *   rects      : [max_boxes_total][4] = (min_y, min_x, max_y, max_x) in image pixels, label order (unsorted; the
  *                reading-order sort compare_rects stays on the host), images concatenated
  *   boxes      : [max_boxes_total][4][2] float32 score-map-space corners as det_boxes_core returns them (may be NULL)
