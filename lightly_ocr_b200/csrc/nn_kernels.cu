@@ -335,10 +335,15 @@ tps_sample_kernel(const float* __restrict__ fid, const float* __restrict__ inv_d
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------- attention decoder
-constexpr int kAttG = 4;  // crops per CTA (8 was measured slower: 2.6 vs 1.9 ms at 635 crops, too few CTAs)
 constexpr int kAttT = 26;
 
-__global__ void __launch_bounds__(256)
+// 512 threads: thread (j = tid & 255, kh = tid >> 8) owns hidden unit j and one half of every reduction over k (the
+// kernel is issue-bound on those loops: twice the warps per crop group, half the trip count each), the 26 attention
+// scores are split between the halves by time step and the context vectors by crop.
+// kAttG = crops per CTA, chosen by the launcher so that all CTAs are resident at once (one CTA of 512 threads per SM):
+// a second, nearly empty wave would double the kernel time.
+template <int kAttG>
+__global__ void __launch_bounds__(512)
 attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ fproj, AttnWeights w,
                  float* __restrict__ preds, int B, int C, int f16) {
     __shared__ float hs[kAttG][256];
@@ -346,35 +351,56 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
     __shared__ float e[kAttG][32];
     __shared__ float red[kAttG][kAttT][8];
     __shared__ float logit[kAttG][64];
+    __shared__ float part[kAttG][256];            // upper-half partial sums of h2h
+    __shared__ float gpart[kAttG][4][256];        // upper-half partial sums of the LSTMCell gates
     __shared__ int prev[kAttG];
-    const int j = threadIdx.x;
-    const int lane = j & 31, wp = j >> 5;
+    const int tid = threadIdx.x;
+    const int j = tid & 255, kh = tid >> 8;
+    const int lane = tid & 31, wp = (tid >> 5) & 7;
     const int b0 = blockIdx.x * kAttG;
+    const int k0 = kh * 128;
     float c[kAttG];
 #pragma unroll
     for (int g = 0; g < kAttG; ++g) {
         c[g] = 0.f;
-        hs[g][j] = 0.f;
+        if (kh == 0) hs[g][j] = 0.f;
     }
-    if (j < kAttG) prev[j] = 0;  // [GO]
+    if (tid < kAttG) prev[tid] = 0;  // [GO]
     __syncthreads();
     const float sc = w.score_w[j];
     for (int step = 0; step < kAttT; ++step) {
-        // (a) hp = h2h(h)
+        // (a) hp = h2h(h): each half sums its 128 k, the upper half hands its part over
         float hp[kAttG];
 #pragma unroll
-        for (int g = 0; g < kAttG; ++g) hp[g] = w.h2h_b[j];
+        for (int g = 0; g < kAttG; ++g) hp[g] = kh == 0 ? w.h2h_b[j] : 0.f;
 #pragma unroll 8
-        for (int k = 0; k < 256; ++k) {
+        for (int k = k0; k < k0 + 128; ++k) {
             const float wv = act2f(__ldg(&w.h2h_wt[k * 256 + j]), f16);
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) hp[g] = fmaf(wv, hs[g][k], hp[g]);
         }
-        // (b) e[t] = score . tanh(i2h(H)[t] + hp)
+        if (kh == 1) {
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) part[g][j] = hp[g];
+        }
+        __syncthreads();
+        if (kh == 0) {
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) {
+                hp[g] += part[g][j];
+                part[g][j] = hp[g];      // the total, for the upper half
+            }
+        }
+        __syncthreads();
+        if (kh == 1) {
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) hp[g] = part[g][j];
+        }
+        // (b) e[t] = score . tanh(i2h(H)[t] + hp): time steps 0..12 on the lower half, 13..25 on the upper
 #pragma unroll
         for (int g = 0; g < kAttG; ++g) {
             const int b = b0 + g;
-            for (int t = 0; t < kAttT; ++t) {
+            for (int t = kh * 13; t < kh * 13 + 13; ++t) {
                 float v = 0.f;
                 if (b < B) v = sc * tanhf(fproj[((long)b * kAttT + t) * 256 + j] + hp[g]);
 #pragma unroll
@@ -383,8 +409,8 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
             }
         }
         __syncthreads();
-        if (j < kAttG * 32) {
-            const int g = j >> 5, t = j & 31;
+        if (tid < kAttG * 32) {
+            const int g = tid >> 5, t = tid & 31;
             float v = -INFINITY;
             if (t < kAttT) {
                 v = 0.f;
@@ -402,9 +428,12 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
             e[g][t] = ex / s;
         }
         __syncthreads();
-        // (d) context = alpha^T H
+        // (d) context = alpha^T H: the first half of the crops on the lower half of the threads, the rest on the upper
+        constexpr int kSplit = (kAttG + 1) / 2;
 #pragma unroll
-        for (int g = 0; g < kAttG; ++g) {
+        for (int gg = 0; gg < kSplit; ++gg) {
+            const int g = kh * kSplit + gg;
+            if (g >= kAttG) break;
             const int b = b0 + g;
             float v = 0.f;
             if (b < B) {
@@ -413,43 +442,53 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
             ctx[g][j] = v;
         }
         __syncthreads();
-        // (e) LSTMCell gates
+        // (e) LSTMCell gates: each half sums its 128 k of [context | h]
         float acc[kAttG][4];
 #pragma unroll
         for (int g = 0; g < kAttG; ++g) {
-            const float4 oh = __ldg(reinterpret_cast<const float4*>(w.woh + ((size_t)prev[g] * 256 + j) * 4));
-            acc[g][0] = w.gate_b[j] + oh.x;
-            acc[g][1] = w.gate_b[256 + j] + oh.y;
-            acc[g][2] = w.gate_b[512 + j] + oh.z;
-            acc[g][3] = w.gate_b[768 + j] + oh.w;
+            if (kh == 0) {
+                const float4 oh = __ldg(reinterpret_cast<const float4*>(w.woh + ((size_t)prev[g] * 256 + j) * 4));
+                acc[g][0] = w.gate_b[j] + oh.x;
+                acc[g][1] = w.gate_b[256 + j] + oh.y;
+                acc[g][2] = w.gate_b[512 + j] + oh.z;
+                acc[g][3] = w.gate_b[768 + j] + oh.w;
+            } else {
+                acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+            }
         }
 #pragma unroll 4
-        for (int k = 0; k < 256; ++k) {
+        for (int k = k0; k < k0 + 128; ++k) {
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(w.wg + ((size_t)k * 256 + j) * 8));
             float wf[8];
             unpack8(u, wf, f16);
-            const float4 wi = make_float4(wf[0], wf[1], wf[2], wf[3]);
-            const float4 wh = make_float4(wf[4], wf[5], wf[6], wf[7]);
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) {
                 const float cv = ctx[g][k], hv = hs[g][k];
-                acc[g][0] = fmaf(wi.x, cv, fmaf(wh.x, hv, acc[g][0]));
-                acc[g][1] = fmaf(wi.y, cv, fmaf(wh.y, hv, acc[g][1]));
-                acc[g][2] = fmaf(wi.z, cv, fmaf(wh.z, hv, acc[g][2]));
-                acc[g][3] = fmaf(wi.w, cv, fmaf(wh.w, hv, acc[g][3]));
+                acc[g][0] = fmaf(wf[0], cv, fmaf(wf[4], hv, acc[g][0]));
+                acc[g][1] = fmaf(wf[1], cv, fmaf(wf[5], hv, acc[g][1]));
+                acc[g][2] = fmaf(wf[2], cv, fmaf(wf[6], hv, acc[g][2]));
+                acc[g][3] = fmaf(wf[3], cv, fmaf(wf[7], hv, acc[g][3]));
             }
         }
-        __syncthreads();  // all reads of hs done
+        if (kh == 1) {
 #pragma unroll
-        for (int g = 0; g < kAttG; ++g) {
-            const float ig = sigmoidf_(acc[g][0]), fg = sigmoidf_(acc[g][1]);
-            const float gg = tanhf(acc[g][2]), og = sigmoidf_(acc[g][3]);
-            c[g] = fg * c[g] + ig * gg;
-            hs[g][j] = og * tanhf(c[g]);
+            for (int g = 0; g < kAttG; ++g)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gpart[g][q][j] = acc[g][q];
+        }
+        __syncthreads();  // all reads of hs done, upper-half partial sums visible
+        if (kh == 0) {
+#pragma unroll
+            for (int g = 0; g < kAttG; ++g) {
+                const float ig = sigmoidf_(acc[g][0] + gpart[g][0][j]), fg = sigmoidf_(acc[g][1] + gpart[g][1][j]);
+                const float gt = tanhf(acc[g][2] + gpart[g][2][j]), og = sigmoidf_(acc[g][3] + gpart[g][3][j]);
+                c[g] = fg * c[g] + ig * gt;
+                hs[g][j] = og * tanhf(c[g]);
+            }
         }
         __syncthreads();
         // (g) generator: one warp per class
-        for (int idx = wp; idx < kAttG * C; idx += 8) {
+        for (int idx = tid >> 5; idx < kAttG * C; idx += 16) {
             const int g = idx / C, v = idx - g * C;
             float s = 0.f;
             for (int k = lane; k < 256; k += 32) s = fmaf(__ldg(&w.gen_w[v * 256 + k]), hs[g][k], s);
@@ -459,19 +498,19 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
         }
         __syncthreads();
         // (h) store + greedy argmax (first maximum wins, like torch.max)
-        for (int idx = j; idx < kAttG * C; idx += 256) {
+        for (int idx = tid; idx < kAttG * C; idx += 512) {
             const int g = idx / C, v = idx - g * C;
             if (b0 + g < B) preds[((long)(b0 + g) * kAttT + step) * C + v] = logit[g][v];
         }
-        if (j < kAttG) {
-            float best = logit[j][0];
+        if (tid < kAttG) {
+            float best = logit[tid][0];
             int bi = 0;
             for (int v = 1; v < C; ++v)
-                if (logit[j][v] > best) {
-                    best = logit[j][v];
+                if (logit[tid][v] > best) {
+                    best = logit[tid][v];
                     bi = v;
                 }
-            prev[j] = bi;
+            prev[tid] = bi;
         }
         __syncthreads();
     }
@@ -635,7 +674,16 @@ void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* 
 
 void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
                       cudaStream_t s) {
-    attention_kernel<<<(B + kAttG - 1) / kAttG, 256, 0, s>>>((const uint16_t*)feats, fproj, w, preds, B, C, is_f16);
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint16_t* f = (const uint16_t*)feats;
+    // 5 crops per CTA when that brings the grid down to one resident wave (148 < B / 4, B / 5 <= 148), else 4
+    if ((B + 3) / 4 > sms && (B + 4) / 5 <= sms) attention_kernel<5><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16);
+    else attention_kernel<4><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16);
 }
 
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,
