@@ -91,3 +91,70 @@ def test_sharding_two_process_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0]
+
+
+def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
+    """Host logic of lightly_ocr_b200/serve.py (request batching, per-request fan-out, the `k > thresh` filter of
+    pipeline.serveModel.predict, error isolation) with the GPU runner replaced by a stub."""
+    import threading
+    import cv2
+    import yaml
+    d = tmp_path / "ocr"
+    d.mkdir()
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "lightly_ocr_b200", "config.yml")))
+    cfg["prediction"], cfg["num_classes"] = "CTC", 37
+    yaml.safe_dump(cfg, open(str(d / "config.yml"), "w"))
+    monkeypatch.setenv("LOCR_OCR_DIR", str(d))
+    import importlib
+    import lightly_ocr_b200.net as net
+    importlib.reload(net)
+    import lightly_ocr_b200.serve as serve
+    importlib.reload(serve)
+
+    class StubRunner:
+        def __init__(self):
+            self.calls = []
+
+        def ocr(self, images):
+            # one "crop" per 100 rows of the image; text = image height, confidence alternates around the threshold
+            self.calls.append(len(images))
+            per_image, text, conf, eos = [], [], [], []
+            for im in images:
+                n = im.shape[0] // 100
+                per_image.append([[0, 0, 1, 1]] * n)
+                for k in range(n):
+                    text.append("h%dk%d" % (im.shape[0], k))
+                    conf.append(0.9 if k % 2 == 0 else 0.5)
+                    eos.append(1)
+            return per_image, dict(text=text, conf=np.array(conf, np.float32), has_eos=np.array(eos, np.int32))
+
+        def close(self):
+            pass
+
+    def fake_load(self):
+        self.head = "CTC"
+        self.runner = StubRunner()
+        self.detector = self.recognizer = self.runner
+
+    monkeypatch.setattr(serve.serveModel, "loadModel", fake_load)
+    m = serve.serveModel(config_file="config.yml", thresh=0.7, docker=True, max_batch=4, max_wait_ms=200)
+    paths = []
+    for i, h in enumerate((100, 200, 300, 400, 500, 600)):
+        p = str(d / ("u%d.png" % i))
+        cv2.imwrite(p, np.full((h, 50, 3), 255, np.uint8))
+        paths.append(p)
+    got = [None] * len(paths)
+    th = [threading.Thread(target=lambda i=i: got.__setitem__(i, serve.api_response(m, paths[i]))) for i in range(len(paths))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=30)
+    for i, h in enumerate((100, 200, 300, 400, 500, 600)):
+        body, status = got[i]
+        want = [["h%dk%d" % (h, k)] for k in range(h // 100) if k % 2 == 0]     # CTC values are one-element lists
+        assert status == 200 and body == {"status": "OK", "results": {k: v for k, v in enumerate(want)}}
+    assert sum(m.batches) == 6 and max(m.batches) <= 4 and len(m.batches) < 6      # requests were batched
+    with pytest.raises(ValueError):
+        m.predict(str(d / "missing.png"))
+    assert m.predict(paths[0]) == [["h100k0"]]
+    m.close()
