@@ -39,7 +39,7 @@ constexpr int kTileM = 128;
 struct ConvParams {
     int B, OH, OW, Cout;
     int bw, bh, bb;      // 128-pixel half box
-    int halves;          // 1 or 2 half boxes per tile (M = 128 or 256), stacked along h (split_b = 0) or b (1)
+    int halves;          // 1 or 2 half boxes per tile (M = 128 or 256), stacked along h (split_b = 0), b (1) or w (2)
     int split_b;
     int tiles_w, tiles_h, tiles_n, num_tiles;
     int n_tile, n_tile_alloc, tmem_cols;
@@ -61,6 +61,8 @@ struct ConvParams {
     int n_chunks;       // n_tile / stage_cols
     int cin_wrap;       // channel coordinate wraps at this value (split-precision inputs), huge when unused
     int split_out;      // write hi / lo halves (split-precision outputs)
+    int halo;           // 3x3 / 64-channel layers: one haloed input patch per tile, the nine taps are descriptor offsets
+    int halo_pool;      // halo tiles whose only output is the 2x2 max-pooled tensor: pooling by warp shuffles
     int pool;           // fused 2x2/2 max-pool of the activated output (TMA-store epilogue only)
     int skip_full;      // pooled output only
     const float* tail_w;   // fused 1x1 tail (see ConvCall)
@@ -81,9 +83,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     int th = rest % p.tiles_h;
     int tb = rest / p.tiles_h;
     t.n0 = n_idx * p.n_tile;
-    t.ow0 = tw * p.bw;
-    t.oh0 = th * p.bh * (p.split_b ? 1 : p.halves);
-    t.b0 = tb * p.bb * (p.split_b ? p.halves : 1);
+    t.ow0 = tw * p.bw * (p.split_b == 2 ? p.halves : 1);
+    t.oh0 = th * p.bh * (p.split_b == 0 ? p.halves : 1);
+    t.b0 = tb * p.bb * (p.split_b == 1 ? p.halves : 1);
     return t;
 }
 
@@ -94,6 +96,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
     } else {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+// element-wise max of two packed 16-bit pairs
+__device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b, int is_f16) {
+    if (is_f16) {
+        __half2 m = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+        return *reinterpret_cast<uint32_t*>(&m);
+    } else {
+        __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+        return *reinterpret_cast<uint32_t*>(&m);
     }
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
@@ -147,6 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             ptx::mbar_init(&tfull_bar[a], 1);
             ptx::mbar_init(&tempty_bar[a], 8);
         }
+        if (p.halo) ptx::mbar_init(&full_bar[kMaxStages - 1], 1);   // resident weights landed
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -173,6 +186,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint32_t a_end = a0 + (uint32_t)p.stages * p.a_stage_bytes;
             uint32_t a_s = a0, b_s = b0s, full_s = full0, empty_s = empty0, phase = 1;
             const int KH = p.num_kblocks / (p.KW * p.cin_chunks);
+            if (p.halo) {
+                // resident weights: nine [64 x 64] tap slabs, once; then ONE haloed patch (18 rows x 24 pixels) per tile
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx_a(full0 + 8u * (kMaxStages - 1), 9u * 8192u);
+                    for (int tp = 0; tp < 9; ++tp)
+                        ptx::tma_load_2d_a(b0s + (uint32_t)tp * 8192u, &tmap_w, full0 + 8u * (kMaxStages - 1), tp * 64, 0);
+                }
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                    const TileCoord t = decode_tile(p, tile);
+                    ptx::mbar_wait_a(empty_s, phase, 110);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx_a(full_s, p.a_stage_bytes);
+                        ptx::tma_load_5d_a(a_s, &tmap_x, full_s, 0, t.ow0 - 1, 0, t.oh0 - 1, t.b0);
+                    }
+                    a_s += p.a_stage_bytes; full_s += 8; empty_s += 8;
+                    if (a_s == a_end) {
+                        a_s = a0; full_s = full0; empty_s = empty0;
+                        phase ^= 1u;
+                    }
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 int kcoord = 0;
@@ -220,6 +254,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint32_t acc_cols = (uint32_t)(HALVES * p.n_tile_alloc);
             const uint32_t idesc = p.idesc;
             constexpr uint32_t kHalfStep = (uint32_t)(kTileM * SWZ) >> 4;
+            if (p.halo) {
+                // A patch in smem: [18 rows][24 pixels][128 B], 128B-swizzled by the TMA unit.  Tap (kh, kw) of half hf is
+                // the same patch read from pixel (kh, kw + 8 hf) on: start address + (kh * 24 + kw + 8 hf) * 128 B,
+                // 8-pixel core groups one image row (3072 B) apart.  The tensor core applies the 128B swizzle to the
+                // absolute shared-memory address (measured: the descriptor's base-offset field must stay 0), which is
+                // exactly where the TMA unit put the data.
+                ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
+                const uint32_t hi_common = (3072u >> 4) | (1u << 14) | (2u << 29);
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                    ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                    ptx::mbar_wait_a(full_s, phase, 300);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const uint32_t a_hi = hi_common;
+                                const uint32_t b_tap = b_lo0 + (uint32_t)((kh * 3 + kw) * 8192 >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                                    for (int hf = 0; hf < 2; ++hf) {
+                                        const uint32_t a_tap = a_lo + (uint32_t)(((kh * 24 + kw + 8 * hf) * 128) >> 4) + k * 2;
+                                        ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_tap, a_hi, b_tap + k * 2,
+                                                           desc_hi, idesc, (kh | kw | k) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                        }
+                        ptx::umma_commit_a(empty_s);
+                        ptx::umma_commit_a(tfull0 + acc * 8u);
+                    }
+                    a_lo += a_step; full_s += 8; empty_s += 8;
+                    if (full_s == full_end) {
+                        a_lo = a_lo0; full_s = full0; empty_s = empty0;
+                        phase ^= 1u;
+                    }
+                    acc ^= 1u;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
                 ptx::tc_fence_after();
@@ -288,8 +365,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
                 if (work) {
-                    const int oh0 = t.oh0 + (p.split_b ? 0 : hf * p.bh), b0 = t.b0 + (p.split_b ? hf * p.bb : 0);
-                    const int ow = t.ow0 + rw, oh = oh0 + rh, b = b0 + rb;
+                    const int oh0 = t.oh0 + (p.split_b == 0 ? hf * p.bh : 0), b0 = t.b0 + (p.split_b == 1 ? hf * p.bb : 0);
+                    const int ow = t.ow0 + (p.split_b == 2 ? hf * p.bw : 0) + rw, oh = oh0 + rh, b = b0 + rb;
                     float h1[16];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) h1[k] = fmaxf(__uint_as_float(r[k]) + tw[306 + k], 0.f);
@@ -356,9 +433,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
                 }
+                if (p.halo_pool) {
+                    // 16 x 16 pixel tile = two 8-wide halves, lane = 8 * (row & 3) + column: the 2x2 window of a pixel
+                    // is lanes {l, l ^ 1, l ^ 8} x their combination, so the pool is two shuffles on the packed 16-bit
+                    // pairs (max commutes with the rounding) and the full-resolution tile never touches shared
+                    // memory — the N = 64 MMAs of this layer already use most of its bandwidth.  The 8 x 8 pooled
+                    // tile leaves through one TMA store; it has a whole tile time to drain before its buffer is reused.
+                    if (etid == 0) ptx::tma_store_wait_read<0>();
+                    ptx::named_bar_sync(1, 256);
+                    uint32_t r0[32], r1[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                           (uint32_t)(acc * 2 * p.n_tile_alloc + half * 32);
+                    ptx::tmem_ld_32x32(taddr, r0);
+                    ptx::tmem_ld_32x32(taddr + (uint32_t)p.n_tile_alloc, r1);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t hv[16];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[half * 32 + q * 4]);
+                            float v0 = __uint_as_float(hf ? r1[q * 4 + 0] : r0[q * 4 + 0]) + b4.x;
+                            float v1 = __uint_as_float(hf ? r1[q * 4 + 1] : r0[q * 4 + 1]) + b4.y;
+                            float v2 = __uint_as_float(hf ? r1[q * 4 + 2] : r0[q * 4 + 2]) + b4.z;
+                            float v3 = __uint_as_float(hf ? r1[q * 4 + 3] : r0[q * 4 + 3]) + b4.w;
+                            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                            hv[q * 2 + 0] = pack2(v0, v1, p.is_f16);
+                            hv[q * 2 + 1] = pack2(v2, v3, p.is_f16);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t m = max2_16(hv[j], __shfl_xor_sync(0xffffffffu, hv[j], 1), p.is_f16);
+                            hv[j] = max2_16(m, __shfl_xor_sync(0xffffffffu, m, 8), p.is_f16);
+                        }
+                        if ((lane & 9) == 0) {
+                            const uint32_t pr = (uint32_t)((2 * ew + (lane >> 4)) * 8 + hf * 4 + ((lane >> 1) & 3));
+                            uint8_t* prow = pool_staging + pr * 128u;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<uint4*>(prow + ((((uint32_t)(half * 4 + q)) ^ (pr & 7u)) << 4)) =
+                                    make_uint4(hv[q * 4 + 0], hv[q * 4 + 1], hv[q * 4 + 2], hv[q * 4 + 3]);
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(1, 256);
+                    if (etid == 0) {
+                        ptx::tma_store_4d(&tmap_p, pool_staging, t.n0, t.ow0 >> 1, t.oh0 >> 1, t.b0);
+                        ptx::tma_store_commit();
+                    }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
                 for (int hf = 0; hf < p.halves; ++hf) {
-                const int oh0 = t.oh0 + (p.split_b ? 0 : hf * p.bh), b0 = t.b0 + (p.split_b ? hf * p.bb : 0);
-                const int ow = t.ow0 + rw, oh = oh0 + rh, b = b0 + rb;
+                const int oh0 = t.oh0 + (p.split_b == 0 ? hf * p.bh : 0), b0 = t.b0 + (p.split_b == 1 ? hf * p.bb : 0);
+                const int ow0 = t.ow0 + (p.split_b == 2 ? hf * p.bw : 0);
+                const int ow = ow0 + rw, oh = oh0 + rh, b = b0 + rb;
                 const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
                 const long pix = ((long)b * p.OH + oh) * p.OW + ow;
                 for (int c = 0; c < p.n_chunks; ++c) {
@@ -508,14 +641,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) {
                         if (!p.skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
-                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, ow0, oh0, b0);
                             if (p.split_out)
-                                ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0, oh0, b0);
+                                ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, ow0, oh0, b0);
                         }
                         if (p.pool) {
-                            ptx::tma_store_4d(&tmap_p, pbuf, t.n0 + c * p.stage_cols, t.ow0 >> 1, oh0 >> 1, b0);
+                            ptx::tma_store_4d(&tmap_p, pbuf, t.n0 + c * p.stage_cols, ow0 >> 1, oh0 >> 1, b0);
                             if (p.split_out)
-                                ptx::tma_store_4d(&tmap_p, pbuf_lo, p.Cout + t.n0 + c * p.stage_cols, t.ow0 >> 1, oh0 >> 1, b0);
+                                ptx::tma_store_4d(&tmap_p, pbuf_lo, p.Cout + t.n0 + c * p.stage_cols, ow0 >> 1, oh0 >> 1, b0);
                         }
                         ptx::tma_store_commit();
                     }
@@ -753,13 +886,30 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         }
     }
 
+    // Halo mode (3x3, stride 1, pad 1, 64 -> 64 channels): the A operand of all nine taps comes from ONE haloed patch
+    // per 16 x 16 output tile (18 rows x 24 pixels x 128 B, one TMA load instead of nine boxes of twice the tile:
+    // 55 KB instead of 360 KB of L2 -> SM traffic per 256 pixels) and the weights stay resident in shared memory.
+    static int allow_halo = -1;
+    if (allow_halo < 0) { const char* e = getenv("LOCR_CONV_HALO"); allow_halo = e ? atoi(e) : 1; }
+    const int elem_h = 2;
+    const bool halo = allow_halo && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
+                      c.pad_w == 1 && c.stride_h == 1 && c.Cin == 64 && c.cin_wrap == 0 && c.Cout_pad == 64 &&
+                      n_tile == 64 && !c.out_fp32 && !c.split_out && c.x_row_px == 0 && c.y_row_px == 0 &&
+                      c.tail_out == nullptr && c.residual == nullptr && (c.y_pitch * elem_h) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(c.y) % 16) == 0;
+    if (halo) {
+        halves = 2; split_b = 2;
+        best_bw = 8; best_bh = 16; best_bb = 1;
+    }
+
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.B = c.B; p.OH = c.OH; p.OW = c.OW; p.Cout = c.Cout;
     p.bw = best_bw; p.bh = best_bh; p.bb = best_bb;
     p.halves = halves; p.split_b = split_b;
-    const int full_bh = p.bh * (split_b ? 1 : halves), full_bb = p.bb * (split_b ? halves : 1);
-    p.tiles_w = (c.OW + p.bw - 1) / p.bw;
+    p.halo = halo ? 1 : 0;
+    const int full_bh = p.bh * (split_b == 0 ? halves : 1), full_bb = p.bb * (split_b == 1 ? halves : 1);
+    p.tiles_w = (c.OW + p.bw * (split_b == 2 ? halves : 1) - 1) / (p.bw * (split_b == 2 ? halves : 1));
     p.tiles_h = (c.OH + full_bh - 1) / full_bh;
     const int tiles_b = (c.B + full_bb - 1) / full_bb;
     p.tiles_n = c.Cout_pad / n_tile;
@@ -780,6 +930,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.num_kblocks = c.KH * c.KW * p.cin_chunks;
     p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
     p.b_stage_bytes = (uint32_t)((n_tile * swz + 1023) / 1024 * 1024);
+    if (halo) {
+        p.a_stage_bytes = 18u * 24u * 128u;          // haloed patch
+        p.b_stage_bytes = 9u * 8192u / 2u;           // x 2 "stages" = the nine resident [64 x 64] tap slabs
+    }
     const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     // epilogue staging: only when the output rows keep 16-byte alignment and the n-tile splits into whole chunks
     const int elem = c.out_fp32 ? 4 : 2;
@@ -793,11 +947,12 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
-    if (stages < 2) stages = 2;
+    if (stages < 2 || halo) stages = 2;
     p.stages = stages;
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, kTileM, n_tile);
     p.pool = pool;
     p.skip_full = (pool && c.skip_full) ? 1 : 0;
+    p.halo_pool = (halo && p.skip_full) ? 1 : 0;
     p.tail_w = c.tail_w;
     p.tail_out = c.tail_out;
     if (c.y_row_px > 0 && (!p.tma_store || c.residual != nullptr || pool)) {
@@ -837,6 +992,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const cuuint64_t xw = (cuuint64_t)(c.x_row_px > 0 ? c.x_row_px : c.W);
         cuuint64_t strides[4] = {pb, pb * xw, pb * xw * S, pb * xw * c.H};
         cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)full_bh, (cuuint32_t)full_bb};
+        if (halo) { box[1] = 24; box[3] = 18; box[4] = 1; }
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&mx, dt, 5, const_cast<void*>(c.x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -902,6 +1058,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const cuuint64_t pb = (cuuint64_t)c.pool_pitch * 2;
         cuuint64_t strides[3] = {pb, pb * PW, pb * PW * PH};
         cuuint32_t box[4] = {(cuuint32_t)p.stage_cols, (cuuint32_t)(p.bw / 2), (cuuint32_t)(p.bh / 2), (cuuint32_t)p.bb};
+        if (p.halo_pool) box[1] = (cuuint32_t)p.bw;   // both halves of the tile in one 8 x 8 pooled box
         cuuint32_t estr[4] = {1, 1, 1, 1};
         const CUtensorMapSwizzle psw = p.stage_rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                          : (p.stage_rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B

@@ -146,6 +146,14 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
     c.y = dy.p; c.OH = OH; c.OW = OW; c.y_pitch = d->y_pitch; c.out_fp32 = d->out_fp32;
     c.bias = db.as<float>();
     c.relu = d->relu; c.dtype = d->act_dtype; c.n_tile = d->n_tile;
+    DevBuf dp;
+    const char* penv = getenv("LOCR_BENCH_POOL");     // 1: fused 2x2 max-pool + full output, 2: pooled output only
+    if (penv && atoi(penv) > 0 && !d->out_fp32) {
+        LOCR_CUDA_OK(dp.alloc((size_t)d->B * (OH / 2) * (OW / 2) * d->Cout * 2));
+        c.pool_y = dp.p;
+        c.pool_pitch = d->Cout;
+        c.skip_full = atoi(penv) == 2 ? 1 : 0;
+    }
     char err[256] = {0};
     const char* wenv = getenv("LOCR_BENCH_WARMUP");   // profiler runs: 0 warm-ups keep the capture to one launch per layer
     const int warm = wenv ? atoi(wenv) : 3;

@@ -86,6 +86,7 @@ POOL_CASES = [
     ("crnn_32x100", 6, 32, 100, 32, 64, 0, 0),
     ("crnn_16x50_odd_w", 9, 16, 50, 128, 128, 0, 0),
     ("odd_hw", 3, 9, 25, 64, 64, 1, 0),
+    ("vgg_c64_ragged", 2, 50, 70, 64, 64, 0, 0),
     ("c32_sw64", 2, 16, 36, 32, 32, 0, 0),
 ]
 
@@ -109,3 +110,22 @@ def test_conv_fused_maxpool(case, want_full):
     assert np.array_equal(yp, want), "%s: %d pooled values differ" % (name, int((yp != want).sum()))
     if want_full:
         assert np.array_equal(y, plain)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 160, 120), (3, 20, 100)], ids=str)
+@pytest.mark.parametrize("act", [0, 1])
+def test_conv_halo_mode_64_to_64(shape, act):
+    """3x3 / pad 1 / 64 -> 64 layers take the haloed-patch path (one TMA patch per 16 x 16 tile, the nine taps are
+    shared-memory descriptor offsets): same tolerance as every other layer, incl. image borders and ragged edges."""
+    from lightly_ocr_b200 import bridge
+    B, H, W = shape
+    rng = np.random.default_rng(B * 1000 + H * 10 + W + act)
+    x = rng.standard_normal((B, H, W, 64)).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 3, 64)) / 24.0).astype(np.float32)
+    bias = rng.standard_normal(64).astype(np.float32)
+    y = bridge.test_conv(x, w, bias, None, pad=(1, 1), relu=True, out_fp32=False, act_dtype=act)
+    ref = _ref(x, w, bias, None, (1, 1), (1, 1), 1, True, act)
+    scale = float(np.abs(ref).max())
+    tol = 2e-3 * scale + scale * (2.0 ** -8 if act == 1 else 2.0 ** -11)
+    err = float(np.abs(y - ref).max())
+    assert err <= tol, "max abs err %g > tol %g" % (err, tol)
