@@ -163,6 +163,10 @@ LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int s
 
 /* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);
+/* In-kernel timeline of the conv kernel (tools/conv_trace.py): only a library built with -DLOCR_CONV_EXPERIMENTS=1 and
+ * run with LOCR_CONV_DBG bit 32 records anything.  out [3][8192] = (clock64 << 4 | event) of block 0's TMA producer,
+ * MMA issuer and first epilogue warp; counts [3] = valid entries per role.  Resets the counters. */
+LOCR_API int locr_conv_trace(unsigned long long* out, int* counts);
 
 #ifdef __cplusplus
 }

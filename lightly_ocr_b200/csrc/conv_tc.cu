@@ -32,6 +32,20 @@ namespace {
 #ifndef LOCR_CONV_EXPERIMENTS
 #define LOCR_CONV_EXPERIMENTS 0
 #endif
+// LOCR_CONV_DBG bit 32 (experiments build): block 0 stamps clock64 at the hand-over points of its producer (role 0),
+// MMA-issuer (1) and first epilogue warp (2) into g_conv_trace; read with conv_tc_trace_read (tools/conv_trace.py).
+#if LOCR_CONV_EXPERIMENTS
+__device__ unsigned long long g_conv_trace[3][8192];
+#define LOCR_TRACE(role, ev)                                                                          \
+    do {                                                                                              \
+        if ((p.dbg & 32) && blockIdx.x == 0 && lane == 0 && trace_n < 8192) {                         \
+            g_conv_trace[role][trace_n] = ((unsigned long long)clock64() << 4) | (unsigned)(ev);      \
+            ++trace_n;                                                                                \
+        }                                                                                             \
+    } while (0)
+#else
+#define LOCR_TRACE(role, ev) do { } while (0)
+#endif
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 384;
 constexpr int kTileM = 128;
@@ -143,6 +157,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#if LOCR_CONV_EXPERIMENTS
+    int trace_n = 0;
+#endif
 
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmap_x);
@@ -195,11 +212,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                     const TileCoord t = decode_tile(p, tile);
+                    LOCR_TRACE(0, 0);
                     ptx::mbar_wait_a(empty_s, phase, 110);
+                    LOCR_TRACE(0, 1);
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx_a(full_s, p.a_stage_bytes);
                         ptx::tma_load_5d_a(a_s, &tmap_x, full_s, 0, t.ow0 - 1, 0, t.oh0 - 1, t.b0);
                     }
+                    LOCR_TRACE(0, 2);
                     a_s += p.a_stage_bytes; full_s += 8; empty_s += 8;
                     if (a_s == a_end) {
                         a_s = a0; full_s = full0; empty_s = empty0;
@@ -209,6 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
+                LOCR_TRACE(0, 0);
                 int kcoord = 0;
                 for (int kh = 0; kh < KH; ++kh) {
                     const int c2 = p.stride2 ? kh : 0;
@@ -217,6 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     for (int kw = 0; kw < p.KW; ++kw, iw0 += p.dil_w) {
                         for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
                             ptx::mbar_wait_a(empty_s, phase, 100);
+                            LOCR_TRACE(0, 1);
                             int cch = cc * BLOCK_K;
                             if (cch >= p.cin_wrap) cch -= p.cin_wrap;   // [hi | lo | hi] of a split-precision input
                             if (ptx::elect_one()) {
@@ -227,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 4)))
                                     ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
                             }
+                            LOCR_TRACE(0, 2);
                             a_s += p.a_stage_bytes; b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
                             if (a_s == a_end) {
                                 a_s = a0; b_s = b0s; full_s = full0; empty_s = empty0;
@@ -263,8 +286,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
                 const uint32_t hi_common = (3072u >> 4) | (1u << 14) | (2u << 29);
                 for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                    LOCR_TRACE(1, 0);
                     ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                    LOCR_TRACE(1, 1);
                     ptx::mbar_wait_a(full_s, phase, 300);
+                    LOCR_TRACE(1, 2);
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * acc_cols;
                     if (ptx::elect_one()) {
@@ -288,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         ptx::umma_commit_a(empty_s);
                         ptx::umma_commit_a(tfull0 + acc * 8u);
                     }
+                    LOCR_TRACE(1, 4);
                     a_lo += a_step; full_s += 8; empty_s += 8;
                     if (full_s == full_end) {
                         a_lo = a_lo0; full_s = full0; empty_s = empty0;
@@ -298,12 +325,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
             } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                LOCR_TRACE(1, 0);
                 ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                LOCR_TRACE(1, 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * acc_cols;
                 uint32_t accum = 0;
                 for (int kb = 0; kb < p.num_kblocks; ++kb) {
                     ptx::mbar_wait_a(full_s, phase, 300);
+                    LOCR_TRACE(1, 2);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
 #pragma unroll
@@ -316,8 +346,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                                    desc_hi, b_lo + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
                             }
                         }
+                        if (LOCR_CONV_EXPERIMENTS && (p.dbg & 64))   // skeleton runs: plain arrive instead of the commit
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s) : "memory");
+                        else
                         ptx::umma_commit_a(empty_s);  // frees the smem slot once these MMAs retire
                     }
+                    LOCR_TRACE(1, 3);
                     accum = 1;
                     a_lo += a_step; b_lo += b_step; full_s += 8; empty_s += 8;
                     if (full_s == full_end) {
@@ -326,6 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     }
                 }
                 if (ptx::elect_one()) ptx::umma_commit_a(tfull0 + acc * 8u);  // accumulators complete -> epilogue
+                LOCR_TRACE(1, 4);
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -422,8 +457,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
+                if (etid == 0) LOCR_TRACE(2, 0);
                 for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                if (etid == 0) LOCR_TRACE(2, 1);
                 ptx::tc_fence_after();
                 if (LOCR_CONV_EXPERIMENTS && (p.dbg & 16)) {   // epilogue reduced to the TMEM hand-shake
                     ptx::tc_fence_before();
@@ -441,12 +478,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     // tile leaves through one TMA store; it has a whole tile time to drain before its buffer is reused.
                     if (etid == 0) ptx::tma_store_wait_read<0>();
                     ptx::named_bar_sync(1, 256);
+                    if (etid == 0) LOCR_TRACE(2, 2);
                     uint32_t r0[32], r1[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
                                            (uint32_t)(acc * 2 * p.n_tile_alloc + half * 32);
                     ptx::tmem_ld_32x32(taddr, r0);
                     ptx::tmem_ld_32x32(taddr + (uint32_t)p.n_tile_alloc, r1);
                     ptx::tmem_ld_wait();
+                    if (etid == 0) LOCR_TRACE(2, 3);
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
@@ -478,12 +517,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                     make_uint4(hv[q * 4 + 0], hv[q * 4 + 1], hv[q * 4 + 2], hv[q * 4 + 3]);
                         }
                     }
+                    if (etid == 0) LOCR_TRACE(2, 5);
                     ptx::fence_proxy_async();
                     ptx::named_bar_sync(1, 256);
+                    if (etid == 0) LOCR_TRACE(2, 7);
                     if (etid == 0) {
                         ptx::tma_store_4d(&tmap_p, pool_staging, t.n0, t.ow0 >> 1, t.oh0 >> 1, t.b0);
                         ptx::tma_store_commit();
                     }
+                    if (etid == 0) LOCR_TRACE(2, 8);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
@@ -502,6 +544,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         else ptx::tma_store_wait_read<1>();        // the store that used this buffer two chunks ago
                     }
                     ptx::named_bar_sync(1, 256);                    // ... is done; bias_s of this tile is visible
+                    if (etid == 0) LOCR_TRACE(2, 2);
                     const int col0 = c * p.stage_cols + half * cpw;  // first column (within the n-tile) of this warp
                     const uint32_t taddr =
                         tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * p.halves + hf) * p.n_tile_alloc + col0);
@@ -525,6 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
                     }
+                    if (etid == 0) LOCR_TRACE(2, 3);
                     if (c == p.n_chunks - 1 && hf == p.halves - 1) {  // accumulators fully read: hand the TMEM stage back to the MMA warp
                         ptx::tc_fence_before();
                         __syncwarp();
@@ -593,6 +637,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             }
                         }
                     }
+                    if (etid == 0) LOCR_TRACE(2, 4);
                     uint8_t* pbuf = pool_staging + (size_t)((p.split_out ? 0u : chunk_ctr) & 1u) * 32 * p.stage_rb;
                     uint8_t* pbuf_lo = pool_staging + (size_t)32 * p.stage_rb;
                     if (p.pool) {
@@ -637,8 +682,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             }
                         }
                     }
+                    if (etid == 0) LOCR_TRACE(2, 5);
                     ptx::fence_proxy_async();
+                    if (etid == 0) LOCR_TRACE(2, 6);
                     ptx::named_bar_sync(1, 256);
+                    if (etid == 0) LOCR_TRACE(2, 7);
                     if (etid == 0) {
                         if (!p.skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
                             ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, ow0, oh0, b0);
@@ -652,6 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         }
                         ptx::tma_store_commit();
                     }
+                    if (etid == 0) LOCR_TRACE(2, 8);
                     ++chunk_ctr;
                 }
                 }
@@ -1073,6 +1122,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         }
     }
     const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
+    if (LOCR_CONV_EXPERIMENTS && getenv("LOCR_CONV_VERBOSE"))
+        fprintf(stderr, "conv_tc: %dx%dx%d cin %d cout %d k%dx%d: swz %d halves %d split %d box %dx%dx%d n_tile %d stages %d "
+                "kblocks %d tiles %d halo %d pool %d smem %zu\n", c.B, c.OH, c.OW, c.Cin, c.Cout, c.KH, c.KW, swz, halves,
+                split_b, p.bw, p.bh, p.bb, n_tile, p.stages, p.num_kblocks, p.num_tiles, p.halo, p.pool, smem);
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
     if (halves == 2) {
@@ -1086,6 +1139,26 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     }
     if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
     return e;
+}
+
+int conv_tc_trace_read(unsigned long long* out, int* counts) {
+#if LOCR_CONV_EXPERIMENTS
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out, g_conv_trace, sizeof(unsigned long long) * 3 * 8192) != cudaSuccess) return -1;
+    for (int r = 0; r < 3; ++r) {
+        int n = 0;
+        while (n < 8192 && out[r * 8192 + n] != 0) ++n;
+        counts[r] = n;
+    }
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_conv_trace) != cudaSuccess) return -1;
+    if (cudaMemset(sym, 0, sizeof(unsigned long long) * 3 * 8192) != cudaSuccess) return -1;
+    return 0;
+#else
+    (void)out;
+    counts[0] = counts[1] = counts[2] = 0;
+    return 0;
+#endif
 }
 
 }  // namespace locr

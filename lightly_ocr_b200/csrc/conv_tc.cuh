@@ -56,6 +56,10 @@ struct ConvCall {
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).
 cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, int errlen);
 
+// Experiments build (-DLOCR_CONV_EXPERIMENTS=1, LOCR_CONV_DBG bit 32): clock64 stamps of block 0's producer / MMA issuer /
+// first epilogue warp, [3][8192] entries of (clock << 4 | event); counts[3] entries are valid.  Resets the counters.
+int conv_tc_trace_read(unsigned long long* out, int* counts);
+
 // Number of SMs used for the persistent grid (queried once).
 int device_sm_count();
 

@@ -176,6 +176,12 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
     return LOCR_OK;
 }
 
+/* Experiments build only: the conv kernel's in-kernel timeline (see conv_tc.cuh); out [3*8192], counts [3]. */
+LOCR_API int locr_conv_trace(unsigned long long* out, int* counts) {
+    if (out == nullptr || counts == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
+    return conv_tc_trace_read(out, counts) == 0 ? LOCR_OK : fail(LOCR_ERR_CUDA, "trace read failed");
+}
+
 /* The BiLSTM recurrence kernel alone.  xproj [B][T][2048] fp32 and whh [2][1024][256] fp32 come in PyTorch's row order
  * (dir*1024 + gate*256 + unit); out [B][T][512] fp32.  iters > 0 additionally times `iters` launches (ms per launch). */
 LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
