@@ -105,6 +105,22 @@ LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, co
 LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, float* boxes,
                                   int32_t* box_counts, float* score_maps);
 
+/* cv2.imread(path) / cv2.imdecode(buf, IMREAD_COLOR) for baseline JPEG files (pipeline.py:68), bit-exact
+ * with OpenCV's libjpeg defaults (ISLOW inverse DCT, fancy up-sampling, 16-bit fixed-point YCbCr -> BGR).  The Huffman
+ * entropy decoding runs on host threads, everything else on the GPU.  Covered: 8-bit baseline / extended sequential
+ * Huffman files with 1 or 3 components in one interleaved scan, any integral sampling ratios, restart intervals.
+ * Progressive, arithmetic-coded, CMYK files and EXIF orientations other than 1 return LOCR_ERR_INVALID (the caller
+ * falls back to its own reader and hands the pixels to locr_detect). */
+LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components);
+/* One file -> packed uint8 [height][width][3] BGR in the caller's host buffer (capacity in bytes). */
+LOCR_API int locr_imdecode(locr_handle* h, const uint8_t* jpeg, int64_t nbytes, uint8_t* bgr, int64_t capacity,
+                           int* height, int* width);
+/* locr_detect on n encoded files: decoded on the GPU, the pixels never visit the host and stay resident for
+ * locr_recognize_boxes.  heights / widths (optional, [n]) receive the image sizes. */
+LOCR_API int locr_detect_encoded(locr_handle* h, const uint8_t* const* jpeg, const int64_t* nbytes, int n,
+                                 int max_boxes_total, int32_t* rects, float* boxes, int32_t* box_counts,
+                                 float* score_maps, int* heights, int* widths);
+
 /* CUDA-event timing on the handle's own stream (bench.py; torch.cuda.Event only sees torch's streams). */
 LOCR_API int locr_timer_start(locr_handle* h);
 LOCR_API int locr_timer_stop(locr_handle* h, float* ms);
@@ -160,6 +176,11 @@ LOCR_API int locr_debug_postproc(locr_handle* h, const float* score, int B, int 
                                  int32_t* counts, int32_t* labels);
 /* cv2.resize(src [sh][sw][3], (dw, dh), INTER_LINEAR) alone. */
 LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
+
+/* Host half of the JPEG reader alone (parsing + Huffman entropy decoding, no GPU): out = int16
+ * [component][block row][block col][64] quantised coefficients in natural order (NULL: geometry only), info[19] = H, W,
+ * components, hmax, vmax, MCUs per row, MCU rows, then (h, v, blocks per row, block rows) per component. */
+LOCR_API int locr_test_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* out, int64_t capacity, int* info);
 
 /* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);

@@ -43,6 +43,11 @@ def lib():
         _lib.locr_test_lstm.restype = C.c_int
         _lib.locr_test_lstm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.POINTER(C.c_float)]
+        _lib.locr_test_jpeg_coefficients.restype = C.c_int
+        _lib.locr_test_jpeg_coefficients.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        _lib.locr_jpeg_info.restype = C.c_int
+        _lib.locr_jpeg_info.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int)]
     return _lib
 
 
@@ -54,6 +59,34 @@ def _check(rc, handle=None):
 
 def _fptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def jpeg_info(data):
+    """(height, width, components) of a baseline JPEG file from its header (host only)."""
+    data = bytes(data)
+    h, w, c = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().locr_jpeg_info(data, len(data), C.byref(h), C.byref(w), C.byref(c)))
+    return h.value, w.value, c.value
+
+
+def jpeg_coefficients(data):
+    """Host half of the JPEG reader (marker parsing + Huffman entropy decoding; no GPU): list of int16 arrays
+    [block rows][blocks per row][64] (natural order) per component, and the geometry dict."""
+    data = bytes(data)
+    info = np.zeros(19, np.int32)
+    L = lib()
+    _check(L.locr_test_jpeg_coefficients(data, len(data), None, 0, _fptr(info)))
+    shapes = [(int(info[10 + 4 * k]), int(info[9 + 4 * k])) for k in range(int(info[2]))]
+    total = sum(a * b * 64 for a, b in shapes)
+    out = np.zeros(total, np.int16)
+    _check(L.locr_test_jpeg_coefficients(data, len(data), _fptr(out), total, _fptr(info)))
+    planes, base = [], 0
+    for a, b in shapes:
+        planes.append(out[base:base + a * b * 64].reshape(a, b, 64))
+        base += a * b * 64
+    geo = dict(height=int(info[0]), width=int(info[1]), hmax=int(info[3]), vmax=int(info[4]), mcux=int(info[5]),
+               mcuy=int(info[6]), sampling=[(int(info[7 + 4 * k]), int(info[8 + 4 * k])) for k in range(int(info[2]))])
+    return planes, geo
 
 
 def test_conv(x, w, bias=None, residual=None, *, dil=(1, 1), pad=(0, 0), stride_h=1, relu=False, out_fp32=False,
@@ -232,6 +265,10 @@ def _bind_pipeline(L):
                                       vp, vp]
     L.locr_debug_resize.restype = C.c_int
     L.locr_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
+    L.locr_imdecode.restype = C.c_int
+    L.locr_imdecode.argtypes = [vp, C.c_char_p, C.c_int64, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.locr_detect_encoded.restype = C.c_int
+    L.locr_detect_encoded.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     L._pipeline_bound = True
 
 
@@ -327,6 +364,22 @@ class Pipeline(Engine):
         o["u8"] = u8
         return o
 
+    def imdecode(self, data):
+        """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a baseline JPEG file, decoded on the GPU
+        (Huffman on the host, the rest in CUDA): uint8 [H][W][3] BGR.  Raises LocrError for files outside the covered
+        subset (progressive, CMYK, EXIF-rotated ...)."""
+        data = bytes(data)
+        h, w, _ = jpeg_info(data)
+        out = np.empty((h, w, 3), np.uint8)
+        hh, ww = C.c_int(), C.c_int()
+        _check(self.L.locr_imdecode(self.h, data, len(data), _fptr(out), out.nbytes, C.byref(hh), C.byref(ww)), self.h)
+        return out
+
+    def imread(self, path):
+        """cv2.imread(path) for baseline JPEG files (reference ocr/pipeline.py:68)."""
+        with open(path, "rb") as f:
+            return self.imdecode(f.read())
+
     def postproc(self, score, ratio_w=1.0, ratio_h=1.0, max_boxes=4096, want_labels=True):
         """score: fp32 [B,H,W,2] -> per image (boxes [k,4,2], rects [k,4], box labels [k], n components, labels)."""
         score = np.ascontiguousarray(score, np.float32)
@@ -417,6 +470,20 @@ class OcrRunner(Pipeline):
                                   _int_array([i.shape[1] for i in imgs]), None, n, self._cap, _fptr(rects), None,
                                   _fptr(counts), None), self.h)
         return self._sort_and_recognize(n, rects, counts, want_logits)
+
+    def ocr_encoded(self, blobs, want_logits=False):
+        """getText on encoded (baseline JPEG) files: decoded on the GPU straight into the resident image buffer, so the
+        pixels never visit the host.  Returns (sorted rects per image, recognition outputs, [(height, width)])."""
+        blobs = [bytes(b) for b in blobs]
+        n = len(blobs)
+        rects, counts = self._buffers(n)
+        ptrs = (C.c_char_p * n)(*blobs)
+        sizes = (C.c_int64 * n)(*[len(b) for b in blobs])
+        hs, ws = (C.c_int * n)(), (C.c_int * n)()
+        _check(self.L.locr_detect_encoded(self.h, ptrs, sizes, n, self._cap, _fptr(rects), None, _fptr(counts), None,
+                                          hs, ws), self.h)
+        per_image, out = self._sort_and_recognize(n, rects, counts, want_logits)
+        return per_image, out, [(int(hs[i]), int(ws[i])) for i in range(n)]
 
     def ocr_resident(self, n, want_logits=False):
         """Same, on the images the previous ocr()/detect() call left resident in HBM (no host-to-device copy)."""

@@ -6,6 +6,7 @@
 
 #include "engine.cuh"
 #include "imgops.cuh"
+#include "jpeg.cuh"
 #include "postproc.cuh"
 
 using namespace locr;
@@ -247,6 +248,70 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
     }
     h->resident.clear();
     for (int i = 0; i < n; ++i) h->resident.push_back({d_img + img_off[i], heights[i], widths[i]});
+    return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
+}
+
+/* cv2.imread / cv2.imdecode(IMREAD_COLOR) of one baseline JPEG file (pipeline.py:68): header only. */
+LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components) {
+    if (data == nullptr || nbytes <= 0 || height == nullptr || width == nullptr || components == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_jpeg_info: bad argument");
+    std::string err;
+    const int rc = jpeg_probe(data, (size_t)nbytes, height, width, components, &err);
+    return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
+}
+
+/* Decodes n JPEG files on the GPU and leaves the BGR images resident (packed) like locr_detect does. */
+static int decode_resident(locr_handle* h, const uint8_t* const* jpeg, const int64_t* nbytes, int n, int* heights,
+                           int* widths) {
+    std::vector<size_t> img_off(n);
+    std::vector<int> hh(n), ww(n);
+    size_t total_bytes = 0;
+    for (int i = 0; i < n; ++i) {
+        int comps = 0;
+        std::string err;
+        if (jpeg[i] == nullptr || nbytes[i] <= 0) return h->fail(LOCR_ERR_INVALID, "JPEG: empty input");
+        const int rc = jpeg_probe(jpeg[i], (size_t)nbytes[i], &hh[i], &ww[i], &comps, &err);
+        if (rc != LOCR_OK) return h->fail(rc, err);
+        img_off[i] = total_bytes;
+        total_bytes += (size_t)hh[i] * ww[i] * 3;
+    }
+    uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
+    if (!d_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
+    std::vector<uint8_t*> outs(n);
+    for (int i = 0; i < n; ++i) outs[i] = d_img + img_off[i];
+    const int rc = jpeg_decode_to_device(h, jpeg, nbytes, n, outs.data());
+    if (rc != LOCR_OK) return rc;
+    h->resident.clear();
+    for (int i = 0; i < n; ++i) {
+        h->resident.push_back({d_img + img_off[i], hh[i], ww[i]});
+        if (heights) heights[i] = hh[i];
+        if (widths) widths[i] = ww[i];
+    }
+    return LOCR_OK;
+}
+
+LOCR_API int locr_imdecode(locr_handle* h, const uint8_t* jpeg, int64_t nbytes, uint8_t* bgr, int64_t capacity,
+                           int* height, int* width) {
+    if (h == nullptr || jpeg == nullptr || nbytes <= 0 || bgr == nullptr || height == nullptr || width == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_imdecode: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    const int rc = decode_resident(h, &jpeg, &nbytes, 1, height, width);
+    if (rc != LOCR_OK) return rc;
+    const size_t bytes = (size_t)*height * *width * 3;
+    if ((int64_t)bytes > capacity) return h->fail(LOCR_ERR_CAPACITY, "locr_imdecode: output buffer too small");
+    LOCR_CUDA_OK(cudaMemcpyAsync(bgr, h->resident[0].p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return LOCR_OK;
+}
+
+LOCR_API int locr_detect_encoded(locr_handle* h, const uint8_t* const* jpeg, const int64_t* nbytes, int n,
+                                 int max_boxes_total, int32_t* rects, float* boxes, int32_t* box_counts,
+                                 float* score_maps, int* heights, int* widths) {
+    if (h == nullptr || jpeg == nullptr || nbytes == nullptr || n <= 0 || rects == nullptr || box_counts == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_detect_encoded: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    const int rc = decode_resident(h, jpeg, nbytes, n, heights, widths);
+    if (rc != LOCR_OK) return rc;
     return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
 }
 

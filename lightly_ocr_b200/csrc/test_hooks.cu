@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "jpeg.cuh"
 #include "nn_kernels.cuh"
 #include "util.cuh"
 
@@ -174,6 +175,14 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return LOCR_OK;
+}
+
+/* Host half of the JPEG reader alone (no GPU): see jpeg.cuh jpeg_host_coefficients. */
+LOCR_API int locr_test_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* out, int64_t capacity, int* info) {
+    if (data == nullptr || nbytes <= 0 || info == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
+    std::string err;
+    const int rc = jpeg_host_coefficients(data, (size_t)nbytes, out, (size_t)(capacity < 0 ? 0 : capacity), info, &err);
+    return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
 }
 
 /* Experiments build only: the conv kernel's in-kernel timeline (see conv_tc.cuh); out [3*8192], counts [3]. */

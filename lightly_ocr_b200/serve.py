@@ -26,11 +26,12 @@ from . import net as _net
 
 
 class _Request:
-    __slots__ = ("path", "image", "done", "result", "error")
+    __slots__ = ("path", "image", "blob", "done", "result", "error")
 
     def __init__(self, path):
         self.path = path
         self.image = None
+        self.blob = None
         self.done = threading.Event()
         self.result = None
         self.error = None
@@ -50,6 +51,7 @@ class serveModel:
         self.max_wait = float(max_wait_ms) / 1e3
         self.device_id = device_id
         self.batches = []               # sizes of the batches served so far (observability / tests)
+        self.encoded_batches = 0        # batches that went through the GPU JPEG decoder without touching host pixels
         self.loadModel()
         self._q = queue.Queue()
         self._stop = False
@@ -117,22 +119,46 @@ class serveModel:
                 batch.append(r)
             self._serve(batch)
 
+    @staticmethod
+    def _read(r):
+        """pipeline.py:68 `cv2.imread(path)`.  Baseline JPEG uploads stay encoded (r.blob): liblocr decodes them on the
+        GPU, bit-identical to OpenCV (include/locr.h locr_detect_encoded).  Everything else - PNG, progressive or
+        EXIF-rotated JPEG ... - is read by OpenCV itself."""
+        with open(r.path, "rb") as f:
+            data = f.read()
+        if data[:2] == b"\xff\xd8":
+            try:
+                bridge.jpeg_info(data)
+                r.blob = data
+                return
+            except bridge.LocrError:
+                pass
+        r.image = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        if r.image is None:
+            raise ValueError("cv2.imread could not read %r" % (r.path,))
+
     def _serve(self, batch):
         good = []
         for r in batch:
             try:
-                r.image = cv2.imread(r.path)          # pipeline.py:68
-                if r.image is None:
-                    raise ValueError("cv2.imread could not read %r" % (r.path,))
+                self._read(r)
                 good.append(r)
             except Exception as e:                     # noqa: BLE001 - handed to the caller of predict()
-                r.error = e
+                r.error = ValueError("cv2.imread could not read %r" % (r.path,)) if isinstance(e, OSError) else e
                 r.done.set()
         if not good:
             return
         self.batches.append(len(good))
         try:
-            per_image, out = self.runner.ocr([r.image for r in good])
+            if all(r.blob is not None for r in good) and hasattr(self.runner, "ocr_encoded"):
+                self.encoded_batches += 1
+                per_image, out, _ = self.runner.ocr_encoded([r.blob for r in good])
+            else:
+                for r in good:                         # mixed batch: the JPEG members are decoded on the GPU as well
+                    if r.image is None:
+                        r.image = (self.runner.imdecode(r.blob) if hasattr(self.runner, "imdecode") else
+                                   cv2.imdecode(np.frombuffer(r.blob, np.uint8), cv2.IMREAD_COLOR))
+                per_image, out = self.runner.ocr([r.image for r in good])
         except Exception as e:                         # noqa: BLE001 - the whole batch failed (e.g. CUDA error)
             for r in good:
                 r.error = e

@@ -83,4 +83,22 @@ def test_batched_serving_equals_one_at_a_time(tmp_path):
     with pytest.raises(ValueError):
         m.predict(str(d / "missing.png"))
     assert m.predict(paths[0]) == want[0]
+    # --- JPEG uploads: decoded on the GPU (locr_detect_encoded), same answer as cv2.imread + the serial path
+    jpgs = []
+    for i in range(3):
+        p = str(d / ("photo%d.jpg" % i))
+        cv2.imwrite(p, receipts.receipt(60 + i), [cv2.IMWRITE_JPEG_QUALITY, 90])
+        jpgs.append(p)
+    pp = str(d / "progressive.jpg")
+    cv2.imwrite(pp, receipts.receipt(63)[:640, :480], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])     # not covered: OpenCV reads it
+    jpgs.append(pp)
+    for p in jpgs:
+        res = {}
+        image = cv2.imread(p)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for crop in detector.process(image):
+                _, res = recognizer.process(res, cv2.cvtColor(crop, cv2.COLOR_BGR2GRAY))
+        before = m.encoded_batches
+        assert m.predict(p) == [v for k, v in res.items() if k > thresh], p
+        assert (m.encoded_batches == before + 1) == (p != pp)
     m.close()
