@@ -130,7 +130,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
     }
 }
 
-template <int SWZ, int HALVES>
+// EPI = 0: generic epilogue (every option is a run-time switch).  EPI = 32 / 16: plain 16-bit TMA-store epilogue with
+// 64- / 32-column staging chunks (32 / 16 columns per warp) and no residual, pooling, split-precision, fp32 or fused-tail
+// option: the switches fold away at compile time, which matters for the layers whose tiles are epilogue-bound.
+template <int SWZ, int HALVES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_p,
@@ -376,7 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         const int chunks = (p.n_tile + 31) / 32;
-        if (p.tail_out != nullptr) {
+        if (EPI == 0 && p.tail_out != nullptr) {
             // ---- conv (Cout = 16) + ReLU + 1x1 (16->16) + ReLU + 1x1 (16->2), all in the registers of the pixel's thread.
             // With M = 256 tiles the two warp groups take one 128-pixel half each.
             float* tw = reinterpret_cast<float*>(staging);          // [256 W6 | 16 b6 | 32 W8 | 2 b8 | 16 conv bias]
@@ -427,38 +430,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
-        } else if (p.tma_store) {
+        } else if (EPI != 0 || p.tma_store) {
+            const bool e_res = EPI == 0 && p.res != nullptr;
+            const int e_fp32 = EPI == 0 ? p.out_fp32 : 0, e_split = EPI == 0 ? p.split_out : 0;
+            const int e_pool = EPI == 0 ? p.pool : 0, e_halo_pool = EPI == 0 ? p.halo_pool : 0;
+            const int e_skip_full = EPI == 0 ? p.skip_full : 0;
+            const int stage_cols = EPI ? 2 * EPI : p.stage_cols, stage_rb = EPI ? 4 * EPI : p.stage_rb;
             // 8 epilogue warps: warp (ew, half) owns TMEM lanes [32*ew, +32) and one half of every staging chunk's
             // columns, so each scheduler overlaps two warps' worth of TMEM loads / conversions / smem stores.
             const int etid = threadIdx.x - 128;
-            const int cpw = p.stage_cols >> 1;             // columns per warp per chunk: 32, 16 or 8
-            const uint32_t xor_term = ((((uint32_t)row * (uint32_t)p.stage_rb) >> 7) &
-                                       (uint32_t)(p.stage_rb / 16 - 1)) << 4;
-            const uint32_t row_off = (uint32_t)row * (uint32_t)p.stage_rb;
+            const int cpw = EPI ? EPI : (stage_cols >> 1);            // columns per warp per chunk: 32, 16 or 8
+            const uint32_t xor_term = ((((uint32_t)row * (uint32_t)stage_rb) >> 7) &
+                                       (uint32_t)(stage_rb / 16 - 1)) << 4;
+            const uint32_t row_off = (uint32_t)row * (uint32_t)stage_rb;
             uint32_t chunk_ctr = 0;
             // fused 2x2 max-pool: thread = (pooled pixel, 16-byte piece); its four source rows of the staged tile
             const int pool_pr = etid >> 3;
             const uint32_t pool_piece = (uint32_t)(etid & 7) << 4;
-            const bool pool_active = p.pool && (int)pool_piece < p.stage_rb;
+            const bool pool_active = e_pool && (int)pool_piece < stage_rb;
             uint32_t pool_src[4] = {0, 0, 0, 0}, pool_dst = 0;
             if (pool_active) {
                 const int pw2 = p.bw >> 1, ph2 = p.bh >> 1;
                 const int qw = pool_pr % pw2, qh = (pool_pr / pw2) % ph2, qb = pool_pr / (pw2 * ph2);
                 const int r00 = (qb * p.bh + 2 * qh) * p.bw + 2 * qw;
                 const int rows[4] = {r00, r00 + 1, r00 + p.bw, r00 + p.bw + 1};
-                const uint32_t msk = (uint32_t)(p.stage_rb / 16 - 1);
+                const uint32_t msk = (uint32_t)(stage_rb / 16 - 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint32_t off = (uint32_t)rows[i] * (uint32_t)p.stage_rb;
+                    const uint32_t off = (uint32_t)rows[i] * (uint32_t)stage_rb;
                     pool_src[i] = off + (pool_piece ^ (((off >> 7) & msk) << 4));
                 }
-                const uint32_t offp = (uint32_t)pool_pr * (uint32_t)p.stage_rb;
+                const uint32_t offp = (uint32_t)pool_pr * (uint32_t)stage_rb;
                 pool_dst = offp + (pool_piece ^ (((offp >> 7) & msk) << 4));
             }
+            // one n-tile: the bias slice is the same for every tile of this CTA (the first chunk's barrier publishes it)
+            const bool bias_once = p.tiles_n == 1;
+            if (bias_once)
+                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[i]);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 if (etid == 0) LOCR_TRACE(2, 0);
-                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
+                if (!bias_once)
+                    for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 if (etid == 0) LOCR_TRACE(2, 1);
                 ptx::tc_fence_after();
@@ -470,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
                 }
-                if (p.halo_pool) {
+                if (e_halo_pool) {
                     // 16 x 16 pixel tile = two 8-wide halves, lane = 8 * (row & 3) + column: the 2x2 window of a pixel
                     // is lanes {l, l ^ 1, l ^ 8} x their combination, so the pool is two shuffles on the packed 16-bit
                     // pairs (max commutes with the rounding) and the full-resolution tile never touches shared
@@ -537,15 +550,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
                 const long pix = ((long)b * p.OH + oh) * p.OW + ow;
                 for (int c = 0; c < p.n_chunks; ++c) {
-                    uint8_t* sbuf = staging + (size_t)((p.split_out ? 0u : chunk_ctr) & 1u) * 128 * p.stage_rb;
-                    uint8_t* sbuf_lo = staging + (size_t)128 * p.stage_rb;   // split-precision: second tile = lo parts
+                    uint8_t* sbuf = staging + (size_t)((e_split ? 0u : chunk_ctr) & 1u) * 128 * stage_rb;
+                    uint8_t* sbuf_lo = staging + (size_t)128 * stage_rb;   // split-precision: second tile = lo parts
                     if (etid == 0) {
-                        if (p.split_out) ptx::tma_store_wait_read<0>();
+                        if (e_split) ptx::tma_store_wait_read<0>();
                         else ptx::tma_store_wait_read<1>();        // the store that used this buffer two chunks ago
                     }
                     ptx::named_bar_sync(1, 256);                    // ... is done; bias_s of this tile is visible
                     if (etid == 0) LOCR_TRACE(2, 2);
-                    const int col0 = c * p.stage_cols + half * cpw;  // first column (within the n-tile) of this warp
+                    const int col0 = c * stage_cols + half * cpw;  // first column (within the n-tile) of this warp
                     const uint32_t taddr =
                         tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * p.halves + hf) * p.n_tile_alloc + col0);
                     float v[32];
@@ -581,7 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             v[q * 4 + 0] += b4.x; v[q * 4 + 1] += b4.y; v[q * 4 + 2] += b4.z; v[q * 4 + 3] += b4.w;
                         }
                     }
-                    if (p.res != nullptr && valid) {
+                    if (e_res && valid) {
                         const int nb = t.n0 + col0;
                         const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.res) + pix * p.res_pitch + nb;
 #pragma unroll
@@ -602,7 +615,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
                     }
                     // swizzled staging write: 16-byte piece k of this row lands at (k*16) ^ xor_term
-                    if (p.out_fp32) {
+                    if (e_fp32) {
                         const uint32_t piece0 = (uint32_t)(half * cpw) >> 2;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -624,7 +637,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 u.z = pack2(v[q * 8 + 4], v[q * 8 + 5], p.is_f16);
                                 u.w = pack2(v[q * 8 + 6], v[q * 8 + 7], p.is_f16);
                                 *reinterpret_cast<uint4*>(sbuf + row_off + (((piece0 + q) << 4) ^ xor_term)) = u;
-                                if (p.split_out) {
+                                if (e_split) {
                                     const float2 h0 = unpack2(u.x, p.is_f16), h1 = unpack2(u.y, p.is_f16);
                                     const float2 h2 = unpack2(u.z, p.is_f16), h3 = unpack2(u.w, p.is_f16);
                                     uint4 l;
@@ -638,9 +651,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         }
                     }
                     if (etid == 0) LOCR_TRACE(2, 4);
-                    uint8_t* pbuf = pool_staging + (size_t)((p.split_out ? 0u : chunk_ctr) & 1u) * 32 * p.stage_rb;
-                    uint8_t* pbuf_lo = pool_staging + (size_t)32 * p.stage_rb;
-                    if (p.pool) {
+                    uint8_t* pbuf = pool_staging + (size_t)((e_split ? 0u : chunk_ctr) & 1u) * 32 * stage_rb;
+                    uint8_t* pbuf_lo = pool_staging + (size_t)32 * stage_rb;
+                    if (e_pool) {
                         ptx::named_bar_sync(1, 256);   // the whole 128-pixel chunk is staged
                         if (pool_active) {
                             float m[8];
@@ -654,7 +667,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                     const float2 v2 = unpack2(w4[q], p.is_f16);
                                     f[2 * q] = v2.x; f[2 * q + 1] = v2.y;
                                 }
-                                if (p.split_out) {   // value = hi + lo, exact in fp32
+                                if (e_split) {   // value = hi + lo, exact in fp32
                                     const uint4 ul = *reinterpret_cast<const uint4*>(sbuf_lo + pool_src[i]);
                                     const uint32_t l4[4] = {ul.x, ul.y, ul.z, ul.w};
 #pragma unroll
@@ -670,7 +683,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             hi.x = pack2(m[0], m[1], p.is_f16); hi.y = pack2(m[2], m[3], p.is_f16);
                             hi.z = pack2(m[4], m[5], p.is_f16); hi.w = pack2(m[6], m[7], p.is_f16);
                             *reinterpret_cast<uint4*>(pbuf + pool_dst) = hi;
-                            if (p.split_out) {
+                            if (e_split) {
                                 const float2 h0 = unpack2(hi.x, p.is_f16), h1 = unpack2(hi.y, p.is_f16);
                                 const float2 h2 = unpack2(hi.z, p.is_f16), h3 = unpack2(hi.w, p.is_f16);
                                 uint4 lo;
@@ -688,15 +701,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     ptx::named_bar_sync(1, 256);
                     if (etid == 0) LOCR_TRACE(2, 7);
                     if (etid == 0) {
-                        if (!p.skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
-                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * p.stage_cols, ow0, oh0, b0);
-                            if (p.split_out)
-                                ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * p.stage_cols, ow0, oh0, b0);
+                        if (!e_skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
+                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * stage_cols, ow0, oh0, b0);
+                            if (e_split)
+                                ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * stage_cols, ow0, oh0, b0);
                         }
-                        if (p.pool) {
-                            ptx::tma_store_4d(&tmap_p, pbuf, t.n0 + c * p.stage_cols, ow0 >> 1, oh0 >> 1, b0);
-                            if (p.split_out)
-                                ptx::tma_store_4d(&tmap_p, pbuf_lo, p.Cout + t.n0 + c * p.stage_cols, ow0 >> 1, oh0 >> 1, b0);
+                        if (e_pool) {
+                            ptx::tma_store_4d(&tmap_p, pbuf, t.n0 + c * stage_cols, ow0 >> 1, oh0 >> 1, b0);
+                            if (e_split)
+                                ptx::tma_store_4d(&tmap_p, pbuf_lo, p.Cout + t.n0 + c * stage_cols, ow0 >> 1, oh0 >> 1, b0);
                         }
                         ptx::tma_store_commit();
                     }
@@ -817,17 +830,17 @@ void set_err(char* err, int errlen, const char* msg) {
     }
 }
 
-template <int SWZ, int HALVES>
+template <int SWZ, int HALVES, int EPI>
 cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mp,
                        const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ, HALVES><<<grid, kThreads, smem, stream>>>(mx, mw, my, mp, p);
+    conv_tc_kernel<SWZ, HALVES, EPI><<<grid, kThreads, smem, stream>>>(mx, mw, my, mp, p);
     return cudaGetLastError();
 }
 
@@ -1128,14 +1141,25 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                 split_b, p.bw, p.bh, p.bb, n_tile, p.stages, p.num_kblocks, p.num_tiles, p.halo, p.pool, smem);
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
+    // plain 16-bit TMA-store epilogue: specialised instantiations (see conv_tc_kernel)
+    static int allow_epi = -1;
+    if (allow_epi < 0) { const char* ev = getenv("LOCR_CONV_EPI"); allow_epi = ev ? atoi(ev) : 1; }
+    int epi = 0;
+    if (allow_epi && swz == 128 && p.tma_store && c.tail_out == nullptr && c.residual == nullptr && !c.split_out &&
+        !c.out_fp32 && !pool && (p.stage_cols == 64 || p.stage_cols == 32))
+        epi = p.stage_cols / 2;
     if (halves == 2) {
-        if (swz == 128) e = launch_swz<128, 2>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 2>(mx, mw, my, mp, p, grid, smem, stream);
-        else e = launch_swz<32, 2>(mx, mw, my, mp, p, grid, smem, stream);
+        if (epi == 32) e = launch_swz<128, 2, 32>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (epi == 16) e = launch_swz<128, 2, 16>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 128) e = launch_swz<128, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        else e = launch_swz<32, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
     } else {
-        if (swz == 128) e = launch_swz<128, 1>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 1>(mx, mw, my, mp, p, grid, smem, stream);
-        else e = launch_swz<32, 1>(mx, mw, my, mp, p, grid, smem, stream);
+        if (epi == 32) e = launch_swz<128, 1, 32>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (epi == 16) e = launch_swz<128, 1, 16>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 128) e = launch_swz<128, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        else if (swz == 64) e = launch_swz<64, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        else e = launch_swz<32, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
     }
     if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
     return e;
