@@ -8,4 +8,4 @@ python tools/prof_kernels.py tc > gpurun_out/prof_tc_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'conv_tc|lstm_cluster' -o gpurun_out/prof_tc_${TAG} python tools/prof_kernels.py tc > gpurun_out/prof_tc_ncu.log 2>&1
 python tools/prof_kernels.py mem > gpurun_out/prof_mem_plain.log 2>&1 &&
 ncu --set full --clock-control none -k regex:'pp_|crop_resize|tps_sample|decode|maxpool|upsample|direct_conv|loc_head|preproc' -o gpurun_out/prof_mem_${TAG} python tools/prof_kernels.py mem > gpurun_out/prof_mem_ncu.log 2>&1
-ls -la gpurun_out/*.ncu-rep; tail -3 gpurun_out/prof_tc_plain.log gpurun_out/prof_mem_plain.log
+ls -la gpurun_out/*.ncu-rep; tail -n 3 gpurun_out/prof_tc_plain.log; tail -n 3 gpurun_out/prof_mem_plain.log
