@@ -94,3 +94,11 @@ def test_ocr_encoded_equals_decode_then_ocr():
     assert out_a["text"] == out_b["text"] and len(out_a["text"]) > 150
     assert np.array_equal(out_a["conf"], out_b["conf"])
     r.close()
+
+
+def test_imdecode_pillow_encoded_files(pipe):
+    from test_jpeg_oracle import pillow_cases
+    for name, data in pillow_cases():
+        if name == "cmyk":
+            continue
+        assert np.array_equal(pipe.imdecode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)), name

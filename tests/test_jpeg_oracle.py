@@ -122,3 +122,42 @@ def test_unsupported_files_fail_loudly():
         bridge.jpeg_info(rotated)
     with pytest.raises(jpeg_ref.JpegError):
         jpeg_ref.imdecode(rotated)
+
+
+def pillow_cases():
+    """Files from a second encoder front end (Pillow): other marker layouts (JFIF density, comments, multi-segment ICC
+    profiles), restart intervals in blocks / rows, custom quantisation presets, optimised tables."""
+    import io
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (97, 131, 3), dtype=np.uint8), (0, 0), 1.5)
+    pil = Image.fromarray(img[..., ::-1])
+    for kw in (dict(quality=90), dict(quality=50, optimize=True), dict(quality=95, subsampling=0),
+               dict(quality=80, subsampling=1), dict(quality=80, subsampling=2), dict(quality=70, restart_marker_blocks=5),
+               dict(quality=70, restart_marker_rows=1), dict(quality=85, dpi=(300, 300), comment=b"hello"),
+               dict(quality=3), dict(quality=100, subsampling=0), dict(quality=60, qtables="web_low"),
+               dict(quality=75, icc_profile=b"x" * 70000)):
+        for mode in ("RGB", "L"):
+            bio = io.BytesIO()
+            pil.convert(mode).save(bio, "JPEG", **kw)
+            yield "%s/%s" % (sorted(kw.items()), mode), bio.getvalue()
+    bio = io.BytesIO()
+    pil.convert("CMYK").save(bio, "JPEG")
+    yield "cmyk", bio.getvalue()
+
+
+def test_pillow_encoded_files():
+    from lightly_ocr_b200 import bridge
+    n = 0
+    for name, data in pillow_cases():
+        if name == "cmyk":
+            with pytest.raises(bridge.LocrError, match="component"):
+                bridge.jpeg_info(data)
+            continue
+        want = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(jpeg_ref.imdecode(data), want), name
+        got, _ = bridge.jpeg_coefficients(data)
+        ref, _ = jpeg_ref.decode_coefficients(jpeg_ref.parse(data))
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref)), name
+        n += 1
+    assert n == 24
