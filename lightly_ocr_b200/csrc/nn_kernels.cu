@@ -122,6 +122,87 @@ direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_
     }
 }
 
+// conv3x3 (Cin = 1, fp32 input) + BN + ReLU + MaxPool2d(2, 2) (TPS_STN.py:38-43), one thread = one POOLED pixel x 16 output
+// channels: the 4 x 4 input patch is loaded once, and every 16-byte weight load from shared memory feeds the four
+// positions of the pooling window (16 FMAs per LDS.128 instead of 4: the per-position form above is bound by the
+// shared-memory pipe).  Taps outside the image multiply a zero, which leaves the fp32 sums exactly as the skipping form
+// computes them.
+__global__ void __launch_bounds__(256)
+direct_conv3x3_pool4_kernel(const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w,
+                            const float* __restrict__ bias, int Cout, uint16_t* __restrict__ out, long out_pitch,
+                            int relu, int f16, int split) {
+    constexpr int CPT = 16;
+    extern __shared__ float sw[];  // [9][Cout] then bias[Cout]
+    const int nw = 9 * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias[i];
+    __syncthreads();
+    const uint32_t groups = (uint32_t)Cout / CPT;
+    const int OH = H / 2, OW = W / 2;
+    const uint32_t total = (uint32_t)B * OH * OW * groups;   // < 2^31, checked by the launcher
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        const uint32_t cg = gid % groups;
+        const uint32_t pix = gid / groups;
+        const int ox = (int)(pix % (uint32_t)OW);
+        const uint32_t rest = pix / (uint32_t)OW;
+        const int oy = (int)(rest % (uint32_t)OH);
+        const int b = (int)(rest / (uint32_t)OH);
+        float patch[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int yy = 2 * oy - 1 + r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int xx = 2 * ox - 1 + c;
+                patch[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(in + ((long)(b * H + yy) * W + xx)) : 0.f;
+            }
+        }
+        float acc[4][CPT];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[s4][j] = sw[nw + cg * CPT + j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* wt = sw + (ky * 3 + kx) * Cout + cg * CPT;
+#pragma unroll
+                for (int j = 0; j < CPT; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wt + j);
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const float v = patch[(s4 >> 1) + ky][(s4 & 1) + kx];
+                        acc[s4][j] = fmaf(v, w4.x, acc[s4][j]);
+                        acc[s4][j + 1] = fmaf(v, w4.y, acc[s4][j + 1]);
+                        acc[s4][j + 2] = fmaf(v, w4.z, acc[s4][j + 2]);
+                        acc[s4][j + 3] = fmaf(v, w4.w, acc[s4][j + 3]);
+                    }
+                }
+            }
+        }
+        uint16_t* op = out + (long)pix * out_pitch + cg * CPT;
+#pragma unroll
+        for (int q = 0; q < CPT / 8; ++q) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float m = fmaxf(fmaxf(acc[0][q * 8 + j], acc[1][q * 8 + j]), fmaxf(acc[2][q * 8 + j], acc[3][q * 8 + j]));
+                r[j] = relu ? fmaxf(m, 0.f) : m;
+            }
+            const uint4 hi = pack8(r, f16);
+            *reinterpret_cast<uint4*>(op + q * 8) = hi;
+            if (split) {  // split precision: lo = v - hi goes to channel Cout + n
+                float h[8];
+                unpack8(hi, h, f16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] -= h[j];
+                *reinterpret_cast<uint4*>(op + Cout + q * 8) = pack8(r, f16);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- CRAFT image -> NHWC16
 // normalizeMeanVariance on the zero-padded canvas (reference imgproc.py:19-25, :58-60) written as a 16-channel NHWC
 // tensor (channels 3..15 zero) so that the first convolution runs on the tensor cores like every other layer.
@@ -132,25 +213,26 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
     const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
     // output rows are padded to W + 3 pixels: column 0 and columns W + 1, W + 2 are zero (conv_tc.cuh: x_row_px)
     const uint32_t Wp = (uint32_t)W + 3;
-    const uint32_t total = (uint32_t)B * H * Wp;   // < 2^31, checked by the caller
-    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+    // two threads per pixel (16 bytes each), so that a warp's store is one contiguous 512-byte run
+    const uint32_t total = (uint32_t)B * H * Wp * 2u;   // < 2^32, checked by the caller
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const uint32_t pix = idx >> 1;
+        const bool upper = idx & 1u;                    // channels 8..15: always zero
         const int xp = (int)(pix % Wp);
         const uint32_t rest = pix / Wp;
         const int y = (int)(rest % (uint32_t)H);
         const int b = (int)(rest / (uint32_t)H);
         const int x = xp - 1;
-        uint4* o = reinterpret_cast<uint4*>(out + (long)pix * 16);
-        o[1] = make_uint4(0u, 0u, 0u, 0u);
-        if (x < 0 || x >= W) {
-            o[0] = make_uint4(0u, 0u, 0u, 0u);
-            continue;
-        }
-        const bool inside = (y < img_h) && (x < img_w);
-        const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (!upper && x >= 0 && x < W) {
+            const bool inside = (y < img_h) && (x < img_w);
+            const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
-        o[0] = pack8(v, f16);
+            for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
+            val = pack8(v, f16);
+        }
+        reinterpret_cast<uint4*>(out)[idx] = val;
     }
 }
 
@@ -632,7 +714,12 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
         direct_conv3x3_kernel<3, true, false><<<grid, 256, smem, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
                                                                       w, bias, Cout, (uint16_t*)out, out_pitch, relu,
                                                                       is_f16, split_out);
-    else if (pool)
+    else if (pool && Cin == 1 && Cout % 16 == 0 && H % 2 == 0 && W % 2 == 0 && !getenv("LOCR_DIRECT_POOL_OLD")) {
+        const long total4 = (long)B * (H / 2) * (W / 2) * (Cout / 16);
+        direct_conv3x3_pool4_kernel<<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias, Cout,
+                                                                             (uint16_t*)out, out_pitch, relu, is_f16,
+                                                                             split_out);
+    } else if (pool)
         direct_conv3x3_kernel<1, false, true><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
                                                                       (uint16_t*)out, out_pitch, relu, is_f16, split_out);
     else
@@ -642,7 +729,7 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, void* out, int is_f16, cudaStream_t s) {
-    const long total = (long)B * H * (W + 3);
+    const long total = (long)B * H * (W + 3) * 2;
     preproc_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
                                                                (uint16_t*)out, is_f16);
 }
