@@ -49,6 +49,7 @@ __device__ unsigned long long g_conv_trace[3][8192];
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 384;
 constexpr int kTileM = 128;
+constexpr int kEpiRes = 64, kEpiPool = 128, kEpiSkip = 256;
 
 struct ConvParams {
     int B, OH, OW, Cout;
@@ -130,9 +131,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
     }
 }
 
-// EPI = 0: generic epilogue (every option is a run-time switch).  EPI = 32 / 16: plain 16-bit TMA-store epilogue with
-// 64- / 32-column staging chunks (32 / 16 columns per warp) and no residual, pooling, split-precision, fp32 or fused-tail
-// option: the switches fold away at compile time, which matters for the layers whose tiles are epilogue-bound.
+// EPI = 0: generic epilogue (every option is a run-time switch).  Otherwise the 16-bit TMA-store epilogue with its options
+// fixed at compile time, which matters for the layers whose tiles are epilogue-bound: EPI & 63 = columns per warp (32 / 16:
+// 64- / 32-column staging chunks), kEpiRes = residual add, kEpiPool = fused 2x2 max-pool, kEpiSkip = pooled output only;
+// never split-precision, fp32, fused-tail or halo-pool (those stay on the generic path).
 template <int SWZ, int HALVES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -431,15 +433,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 if (acc == 0) acc_phase ^= 1u;
             }
         } else if (EPI != 0 || p.tma_store) {
-            const bool e_res = EPI == 0 && p.res != nullptr;
+            constexpr int kCpw = EPI & 63;
+            const bool e_res = EPI == 0 ? p.res != nullptr : (EPI & kEpiRes) != 0;
             const int e_fp32 = EPI == 0 ? p.out_fp32 : 0, e_split = EPI == 0 ? p.split_out : 0;
-            const int e_pool = EPI == 0 ? p.pool : 0, e_halo_pool = EPI == 0 ? p.halo_pool : 0;
-            const int e_skip_full = EPI == 0 ? p.skip_full : 0;
-            const int stage_cols = EPI ? 2 * EPI : p.stage_cols, stage_rb = EPI ? 4 * EPI : p.stage_rb;
+            const int e_pool = EPI == 0 ? p.pool : ((EPI & kEpiPool) ? 1 : 0), e_halo_pool = EPI == 0 ? p.halo_pool : 0;
+            const int e_skip_full = EPI == 0 ? p.skip_full : ((EPI & kEpiSkip) ? 1 : 0);
+            const int stage_cols = EPI ? 2 * kCpw : p.stage_cols, stage_rb = EPI ? 4 * kCpw : p.stage_rb;
             // 8 epilogue warps: warp (ew, half) owns TMEM lanes [32*ew, +32) and one half of every staging chunk's
             // columns, so each scheduler overlaps two warps' worth of TMEM loads / conversions / smem stores.
             const int etid = threadIdx.x - 128;
-            const int cpw = EPI ? EPI : (stage_cols >> 1);            // columns per warp per chunk: 32, 16 or 8
+            const int cpw = EPI ? kCpw : (stage_cols >> 1);            // columns per warp per chunk: 32, 16 or 8
             const uint32_t xor_term = ((((uint32_t)row * (uint32_t)stage_rb) >> 7) &
                                        (uint32_t)(stage_rb / 16 - 1)) << 4;
             const uint32_t row_off = (uint32_t)row * (uint32_t)stage_rb;
@@ -1141,25 +1144,38 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                 split_b, p.bw, p.bh, p.bb, n_tile, p.stages, p.num_kblocks, p.num_tiles, p.halo, p.pool, smem);
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     cudaError_t e;
-    // plain 16-bit TMA-store epilogue: specialised instantiations (see conv_tc_kernel)
+    // 16-bit TMA-store epilogues with compile-time options (see conv_tc_kernel); anything else takes the generic one
     static int allow_epi = -1;
     if (allow_epi < 0) { const char* ev = getenv("LOCR_CONV_EPI"); allow_epi = ev ? atoi(ev) : 1; }
     int epi = 0;
-    if (allow_epi && swz == 128 && p.tma_store && c.tail_out == nullptr && c.residual == nullptr && !c.split_out &&
-        !c.out_fp32 && !pool && (p.stage_cols == 64 || p.stage_cols == 32))
+    if (allow_epi && swz == 128 && p.tma_store && c.tail_out == nullptr && !c.split_out && !c.out_fp32 && !p.halo_pool &&
+        (p.stage_cols == 64 || p.stage_cols == 32)) {
         epi = p.stage_cols / 2;
-    if (halves == 2) {
-        if (epi == 32) e = launch_swz<128, 2, 32>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (epi == 16) e = launch_swz<128, 2, 16>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 128) e = launch_swz<128, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
-        else e = launch_swz<32, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
-    } else {
-        if (epi == 32) e = launch_swz<128, 1, 32>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (epi == 16) e = launch_swz<128, 1, 16>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 128) e = launch_swz<128, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
-        else if (swz == 64) e = launch_swz<64, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
-        else e = launch_swz<32, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        if (c.residual != nullptr) epi |= kEpiRes;
+        if (pool) epi |= kEpiPool | (p.skip_full ? kEpiSkip : 0);
+    }
+    bool done = false;
+    e = cudaSuccess;
+#define LOCR_EPI_CASE(HV, E)                                                                       \
+    if (!done && halves == HV && epi == (E)) {                                                     \
+        e = launch_swz<128, HV, (E)>(mx, mw, my, mp, p, grid, smem, stream);                       \
+        done = true;                                                                               \
+    }
+    LOCR_EPI_CASE(1, 32) LOCR_EPI_CASE(2, 32) LOCR_EPI_CASE(1, 16) LOCR_EPI_CASE(2, 16)
+    LOCR_EPI_CASE(1, 32 | kEpiRes) LOCR_EPI_CASE(2, 32 | kEpiRes)
+    LOCR_EPI_CASE(1, 32 | kEpiPool) LOCR_EPI_CASE(2, 32 | kEpiPool)
+    LOCR_EPI_CASE(1, 32 | kEpiPool | kEpiSkip) LOCR_EPI_CASE(2, 32 | kEpiPool | kEpiSkip)
+#undef LOCR_EPI_CASE
+    if (!done) {
+        if (halves == 2) {
+            if (swz == 128) e = launch_swz<128, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
+            else if (swz == 64) e = launch_swz<64, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
+            else e = launch_swz<32, 2, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        } else {
+            if (swz == 128) e = launch_swz<128, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+            else if (swz == 64) e = launch_swz<64, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+            else e = launch_swz<32, 1, 0>(mx, mw, my, mp, p, grid, smem, stream);
+        }
     }
     if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
     return e;
