@@ -432,6 +432,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
+        } else if (EPI == 32 && HALVES == 2 && p.n_chunks == 1 && p.tiles_n == 1 &&
+                   !(LOCR_CONV_EXPERIMENTS && (p.dbg & 256))) {
+            // ---- plain 16-bit TMA-store epilogue as TWO INDEPENDENT warpgroups.  A staging chunk costs a chain of
+            // latencies (buffer free -> barrier -> TMEM load -> convert -> st.shared -> proxy fence -> barrier -> TMA
+            // store) that eight warps marching in step cannot overlap; for the small-K layers that chain, not the MMAs,
+            // set the tile rate.  Here each warpgroup (4 warps = all 128 TMEM lanes) takes every other (half, chunk) unit
+            // of the tile with its own staging buffer, named barrier and store queue, so two chains are in flight.
+            // Used for the 64-channel layers with M = 256 tiles (one 128-pixel half per group: `slice1.0` 0.55 -> 0.49 ms);
+            // measured neutral or slightly worse for the 32-column and multi-chunk tiles, which keep the lock-step form.
+            constexpr int kCols = 2 * (EPI & 63);      // columns per staging chunk: 64 or 32
+            constexpr int kRb = 2 * kCols;             // bytes per staged row: 128 or 64
+            const int g = half;
+            const int gtid = threadIdx.x - 128 - g * 128;
+            uint8_t* sbuf = staging + (size_t)g * 128 * kRb;
+            const uint32_t xor_term = ((((uint32_t)row * (uint32_t)kRb) >> 7) & (uint32_t)(kRb / 16 - 1)) << 4;
+            const uint32_t row_off = (uint32_t)row * (uint32_t)kRb;
+            for (int i = threadIdx.x - 128; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[i]);
+            ptx::named_bar_sync(1, 256);
+            const int units = p.halves * p.n_chunks;
+            int last_u = -1;
+            for (int u = g; u < units; u += 2) last_u = u;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+                ptx::tc_fence_after();
+                if (last_u < 0) {          // single-unit tiles: this group only takes part in the TMEM hand-back
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                }
+                for (int u = g; u < units; u += 2) {
+                    const int hf = u / p.n_chunks, c = u - hf * p.n_chunks;
+                    const int oh0 = t.oh0 + (p.split_b == 0 ? hf * p.bh : 0), b0 = t.b0 + (p.split_b == 1 ? hf * p.bb : 0);
+                    const int ow0 = t.ow0 + (p.split_b == 2 ? hf * p.bw : 0);
+                    if (gtid == 0) ptx::tma_store_wait_read<0>();     // this group's previous store has left its buffer
+                    ptx::named_bar_sync(2 + g, 128);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                                           (uint32_t)((acc * p.halves + hf) * p.n_tile_alloc + c * kCols);
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32(taddr, r0);
+                    if (kCols == 64) ptx::tmem_ld_32x32(taddr + 32u, r1);
+                    ptx::tmem_ld_wait();
+                    if (u == last_u) {     // accumulators fully read by this group
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kCols / 8; ++q) {
+                        const float4 ba = *reinterpret_cast<const float4*>(&bias_s[c * kCols + q * 8]);
+                        const float4 bb4 = *reinterpret_cast<const float4*>(&bias_s[c * kCols + q * 8 + 4]);
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            v[j] = __uint_as_float(q < 4 ? r0[(q & 3) * 8 + j] : r1[(q & 3) * 8 + j]);
+                        v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
+                        v[4] += bb4.x; v[5] += bb4.y; v[6] += bb4.z; v[7] += bb4.w;
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        }
+                        uint4 o;
+                        o.x = pack2(v[0], v[1], p.is_f16); o.y = pack2(v[2], v[3], p.is_f16);
+                        o.z = pack2(v[4], v[5], p.is_f16); o.w = pack2(v[6], v[7], p.is_f16);
+                        *reinterpret_cast<uint4*>(sbuf + row_off + (((uint32_t)q << 4) ^ xor_term)) = o;
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(2 + g, 128);
+                    if (gtid == 0) {
+                        if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 8)))
+                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * kCols, ow0, oh0, b0);
+                        ptx::tma_store_commit();
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+            if (gtid == 0) ptx::tma_store_wait_all();
         } else if (EPI != 0 || p.tma_store) {
             constexpr int kCpw = EPI & 63;
             const bool e_res = EPI == 0 ? p.res != nullptr : (EPI & kEpiRes) != 0;
