@@ -38,11 +38,13 @@ CRNN_FLOPS_PER_CROP = 10.593e9
 
 
 def conv_traffic():
-    """DRAM bytes per conv_tc launch (mean over one 8-receipt pass) from the committed ncu capture, or None."""
+    """DRAM bytes per conv_tc launch (mean over one 8-receipt pass) from the newest committed ncu capture, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_conv_traffic.json")) as f:
+        import glob
+        path = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_traffic.json")))[-1]
+        with open(path) as f:
             t = json.load(f)
-        return float(t["bytes_per_launch"]), "profiles/r01c_conv_traffic.json: %s" % t["source"]
+        return float(t["bytes_per_launch"]), "profiles/%s: %s" % (os.path.basename(path), t["source"])
     except Exception:
         return None, None
 

@@ -611,18 +611,19 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
             Cc = P;
         }
         const std::string tail = fe + "conv" + std::to_string(l);
-        if (l <= 3) {
+        if (l == 1) {
+            // conv1 + BN + ReLU + MaxPool2d(2, 2) (resnet50v1.py:110-112): pooled in the conv epilogue, only the pooled tensor is written
+            c.pool(other, Cc, 1);
+            c.tc(tail, cur, B, Hc, Wc, Cc, nullptr, Cc, 1, 1, 1);
+            std::swap(cur, other);
+            Hc /= 2; Wc /= 2;
+        } else if (l <= 3) {
             c.tc(tail, cur, B, Hc, Wc, Cc, other, Cc, 1, 1, 1);
             std::swap(cur, other);
         }
-        if (l == 1 || l == 2) {
-            if (l == 1) {
-                { ProfScope ps_(h, "maxpool.res1", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 2, 0, 0, f16, s); }
-                Hc /= 2; Wc /= 2;
-            } else {
-                { ProfScope ps_(h, "maxpool.res2", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s); }
-                Hc = (Hc - 2) / 2 + 1; Wc = Wc + 2 - 2 + 1;
-            }
+        if (l == 2) {
+            { ProfScope ps_(h, "maxpool.res2", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s); }
+            Hc = (Hc - 2) / 2 + 1; Wc = Wc + 2 - 2 + 1;
             h->launches++;
             std::swap(cur, other);
         }

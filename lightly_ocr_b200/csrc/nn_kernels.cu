@@ -127,6 +127,8 @@ direct_conv3x3_kernel(const void* __restrict__ in, int B, int H, int W, int img_
 // positions of the pooling window (16 FMAs per LDS.128 instead of 4: the per-position form above is bound by the
 // shared-memory pipe).  Taps outside the image multiply a zero, which leaves the fp32 sums exactly as the skipping form
 // computes them.
+// POOL = false: the same thread writes its 2 x 2 block of conv outputs instead of their maximum (conv0_1 of the ResNet).
+template <bool POOL>
 __global__ void __launch_bounds__(256)
 direct_conv3x3_pool4_kernel(const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w,
                             const float* __restrict__ bias, int Cout, uint16_t* __restrict__ out, long out_pitch,
@@ -181,23 +183,29 @@ direct_conv3x3_pool4_kernel(const float* __restrict__ in, int B, int H, int W, c
                 }
             }
         }
-        uint16_t* op = out + (long)pix * out_pitch + cg * CPT;
 #pragma unroll
-        for (int q = 0; q < CPT / 8; ++q) {
-            float r[8];
+        for (int s4 = 0; s4 < (POOL ? 1 : 4); ++s4) {
+            const long opix = POOL ? (long)pix : ((long)(b * H + 2 * oy + (s4 >> 1)) * W + 2 * ox + (s4 & 1));
+            uint16_t* op = out + opix * out_pitch + cg * CPT;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float m = fmaxf(fmaxf(acc[0][q * 8 + j], acc[1][q * 8 + j]), fmaxf(acc[2][q * 8 + j], acc[3][q * 8 + j]));
-                r[j] = relu ? fmaxf(m, 0.f) : m;
-            }
-            const uint4 hi = pack8(r, f16);
-            *reinterpret_cast<uint4*>(op + q * 8) = hi;
-            if (split) {  // split precision: lo = v - hi goes to channel Cout + n
-                float h[8];
-                unpack8(hi, h, f16);
+            for (int q = 0; q < CPT / 8; ++q) {
+                float r[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] -= h[j];
-                *reinterpret_cast<uint4*>(op + Cout + q * 8) = pack8(r, f16);
+                for (int j = 0; j < 8; ++j) {
+                    const float m = POOL ? fmaxf(fmaxf(acc[0][q * 8 + j], acc[1][q * 8 + j]),
+                                                 fmaxf(acc[2][q * 8 + j], acc[3][q * 8 + j]))
+                                         : acc[s4][q * 8 + j];
+                    r[j] = relu ? fmaxf(m, 0.f) : m;
+                }
+                const uint4 hi = pack8(r, f16);
+                *reinterpret_cast<uint4*>(op + q * 8) = hi;
+                if (split) {  // split precision: lo = v - hi goes to channel Cout + n
+                    float h[8];
+                    unpack8(hi, h, f16);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] -= h[j];
+                    *reinterpret_cast<uint4*>(op + Cout + q * 8) = pack8(r, f16);
+                }
             }
         }
     }
@@ -716,9 +724,14 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
                                                                       is_f16, split_out);
     else if (pool && Cin == 1 && Cout % 16 == 0 && H % 2 == 0 && W % 2 == 0 && !getenv("LOCR_DIRECT_POOL_OLD")) {
         const long total4 = (long)B * (H / 2) * (W / 2) * (Cout / 16);
-        direct_conv3x3_pool4_kernel<<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias, Cout,
-                                                                             (uint16_t*)out, out_pitch, relu, is_f16,
-                                                                             split_out);
+        direct_conv3x3_pool4_kernel<true><<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias,
+                                                                                   Cout, (uint16_t*)out, out_pitch, relu,
+                                                                                   is_f16, split_out);
+    } else if (!pool && !u8_mode && Cin == 1 && Cout % 16 == 0 && H % 2 == 0 && W % 2 == 0 && !getenv("LOCR_DIRECT_POOL_OLD")) {
+        const long total4 = (long)B * (H / 2) * (W / 2) * (Cout / 16);
+        direct_conv3x3_pool4_kernel<false><<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias,
+                                                                                    Cout, (uint16_t*)out, out_pitch, relu,
+                                                                                    is_f16, split_out);
     } else if (pool)
         direct_conv3x3_kernel<1, false, true><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
                                                                       (uint16_t*)out, out_pitch, relu, is_f16, split_out);
