@@ -218,6 +218,20 @@ struct Ctx {
         }
         return p;
     }
+    // Same for a buffer whose per-item geometry never changes (only the item count does): the part that was zero-filled
+    // before keeps its zero pads, so only the newly covered tail is cleared.
+    void* zbuf_grow(const std::string& name, size_t bytes) {
+        void* p = buf(name, bytes);
+        if (p == nullptr) return p;
+        auto& z = h->zeroed[name];
+        if (z.first != p) { z.first = p; z.second = 0; }
+        if (bytes > z.second) {
+            if (cudaMemsetAsync((char*)p + z.second, 0, bytes - z.second, h->stream) != cudaSuccess && rc == LOCR_OK)
+                rc = h->fail(LOCR_ERR_CUDA, "memset failed for " + name);
+            z.second = bytes;
+        }
+        return p;
+    }
     void* buf(const std::string& name, size_t bytes) {
         void* p = engine_buffer(h, name, bytes);
         if (p == nullptr && rc == LOCR_OK) rc = h->fail(LOCR_ERR_CUDA, "device allocation failed for " + name);
@@ -235,6 +249,7 @@ void* engine_buffer(locr_handle* h, const std::string& name, size_t bytes) {
         cudaFree(e.first);
         e.first = nullptr;
     }
+    h->zeroed.erase(name);   // a fresh allocation (possibly at the old address) holds no zero pads yet
     const size_t want = bytes + bytes / 8 + 256;
     if (cudaMalloc(&e.first, want) != cudaSuccess) {
         e.first = nullptr;
@@ -410,7 +425,7 @@ int engine_finalize_crnn(locr_handle* h) {
     if ((rc = fold_conv(h, M, loc + "conv.8", loc + "conv.9", false, false, 0, true))) return rc;
     if ((rc = fold_conv(h, M, loc + "conv.12", loc + "conv.13", false, false, 0, true))) return rc;
     if ((rc = F(fe + "conv0_1", fe + "bn0_1", true))) return rc;
-    if ((rc = F(fe + "conv0_2", fe + "bn0_2"))) return rc;
+    if ((rc = fold_conv(h, M, fe + "conv0_2", fe + "bn0_2", false, false, 0, false, true))) return rc;   // window view
     const int nblocks[5] = {0, 1, 2, 5, 3};
     for (int l = 1; l <= 4; ++l) {
         for (int i = 0; i < nblocks[l]; ++i) {
@@ -584,9 +599,14 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
 
     // ---- ResNet feature extractor (resnet50v1.py:101-135)
     const ConvW& r0 = h->conv[fe + "conv0_1"];
-    { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, sA, 32, 1, f16, s); }
+    // conv0_1 writes a row-padded tensor (103 pixels per row, pads zero) so that conv0_2 takes the 4-pixel window view
+    // (6 k-blocks of 128-byte rows instead of 9 of 64 bytes; conv_tc.cuh x_row_px)
+    void* r0out = c.zbuf_grow("crnn.res0", (size_t)B * 32 * 103 * 32 * 2);
+    if (c.rc != LOCR_OK || r0out == nullptr) return c.rc != LOCR_OK ? c.rc : h->fail(LOCR_ERR_CUDA, "allocation failed");
+    { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, r0out, 32, 1, f16, s, 0, 0, 103); }
     c.pool(sB, 64, 1);
-    c.tc(fe + "conv0_2", sA, B, 32, 100, 32, nullptr, 64, 1, 1, 1);
+    c.rows(103, 0);
+    c.tc(fe + "conv0_2", r0out, B, 32, 100, 32, nullptr, 64, 1, 1, 0);
     h->launches += 1;
     // x lives in `cur`; BasicBlock (resnet50v1.py:33-48): relu(bn2(conv2(relu(bn1(conv1 x)))) + residual)
     void* cur = sB;

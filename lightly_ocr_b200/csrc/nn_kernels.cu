@@ -132,7 +132,7 @@ template <bool POOL>
 __global__ void __launch_bounds__(256)
 direct_conv3x3_pool4_kernel(const float* __restrict__ in, int B, int H, int W, const float* __restrict__ w,
                             const float* __restrict__ bias, int Cout, uint16_t* __restrict__ out, long out_pitch,
-                            int relu, int f16, int split) {
+                            int relu, int f16, int split, int out_row_px) {
     constexpr int CPT = 16;
     extern __shared__ float sw[];  // [9][Cout] then bias[Cout]
     const int nw = 9 * Cout;
@@ -185,7 +185,10 @@ direct_conv3x3_pool4_kernel(const float* __restrict__ in, int B, int H, int W, c
         }
 #pragma unroll
         for (int s4 = 0; s4 < (POOL ? 1 : 4); ++s4) {
-            const long opix = POOL ? (long)pix : ((long)(b * H + 2 * oy + (s4 >> 1)) * W + 2 * ox + (s4 & 1));
+            // out_row_px > 0: row-padded output (one zero pixel left, two right of every row: conv_tc.cuh x_row_px)
+            const long opix = POOL ? (long)pix
+                                   : (out_row_px > 0 ? (long)(b * H + 2 * oy + (s4 >> 1)) * out_row_px + 2 * ox + (s4 & 1) + 1
+                                                     : (long)(b * H + 2 * oy + (s4 >> 1)) * W + 2 * ox + (s4 & 1));
             uint16_t* op = out + opix * out_pitch + cg * CPT;
 #pragma unroll
             for (int q = 0; q < CPT / 8; ++q) {
@@ -714,7 +717,7 @@ inline int grid_for(long total, int block) {
 
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out, int pool) {
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out, int pool, int out_row_px) {
     const long total = (long)B * (pool ? H / 2 : H) * (pool ? W / 2 : W) * (Cout / 32);
     const int grid = grid_for(total, 256);
     const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
@@ -726,12 +729,12 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
         const long total4 = (long)B * (H / 2) * (W / 2) * (Cout / 16);
         direct_conv3x3_pool4_kernel<true><<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias,
                                                                                    Cout, (uint16_t*)out, out_pitch, relu,
-                                                                                   is_f16, split_out);
+                                                                                   is_f16, split_out, 0);
     } else if (!pool && !u8_mode && Cin == 1 && Cout % 16 == 0 && H % 2 == 0 && W % 2 == 0 && !getenv("LOCR_DIRECT_POOL_OLD")) {
         const long total4 = (long)B * (H / 2) * (W / 2) * (Cout / 16);
         direct_conv3x3_pool4_kernel<false><<<grid_for(total4, 256), 256, smem, s>>>((const float*)in, B, H, W, w, bias,
                                                                                     Cout, (uint16_t*)out, out_pitch, relu,
-                                                                                    is_f16, split_out);
+                                                                                    is_f16, split_out, out_row_px);
     } else if (pool)
         direct_conv3x3_kernel<1, false, true><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
                                                                       (uint16_t*)out, out_pitch, relu, is_f16, split_out);

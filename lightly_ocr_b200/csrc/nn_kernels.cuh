@@ -18,8 +18,11 @@ namespace locr {
 //   f32 mode : `in` is fp32 [B][H][W] (Cin = 1).
 void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int img_h, int img_w, long row_stride,
                            long img_stride, const float* w, const float* bias, int Cin, int Cout, void* out,
-                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out = 0, int pool = 0);
+                           long out_pitch, int relu, int is_f16, cudaStream_t s, int split_out = 0, int pool = 0,
+                           int out_row_px = 0);
 //   pool     : f32 mode only; writes MaxPool2d(2, 2) of the activated output instead, [B][H/2][W/2][Cout]
+//   out_row_px : f32 mode without pool, even H and W only; > 0 writes a row-padded tensor (pixel x lands at x + 1 of a
+//              row of out_row_px = W + 3 pixels; the pad pixels are the caller's, see conv_tc.cuh x_row_px)
 
 // CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
 // channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.  Output rows are padded to W + 3
