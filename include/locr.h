@@ -107,10 +107,11 @@ LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* 
 
 /* cv2.imread(path) / cv2.imdecode(buf, IMREAD_COLOR) for baseline JPEG files (pipeline.py:68), bit-exact
  * with OpenCV's libjpeg defaults (ISLOW inverse DCT, fancy up-sampling, 16-bit fixed-point YCbCr -> BGR).  The Huffman
- * entropy decoding runs on host threads, everything else on the GPU.  Covered: 8-bit baseline / extended sequential
- * Huffman files with 1 or 3 components in one interleaved scan, any integral sampling ratios, restart intervals.
- * Progressive, arithmetic-coded, CMYK files and EXIF orientations other than 1 return LOCR_ERR_INVALID (the caller
- * falls back to its own reader and hands the pixels to locr_detect). */
+ * entropy decoding runs on host threads, everything else on the GPU.  Covered: 8-bit Huffman-coded DCT files - baseline,
+ * extended sequential (one or several scans) and progressive (spectral selection + successive approximation) - with 1
+ * or 3 components, any integral sampling ratios, restart intervals, EXIF orientations 1-8 (applied like OpenCV's
+ * ExifTransform; sizes are those of the rotated image).  Arithmetic-coded, lossless, 12-bit, CMYK and truncated files
+ * return LOCR_ERR_INVALID (the caller falls back to its own reader and hands the pixels to locr_detect). */
 LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components);
 /* One file -> packed uint8 [height][width][3] BGR in the caller's host buffer (capacity in bytes). */
 LOCR_API int locr_imdecode(locr_handle* h, const uint8_t* jpeg, int64_t nbytes, uint8_t* bgr, int64_t capacity,

@@ -367,7 +367,7 @@ class Pipeline(Engine):
     def imdecode(self, data):
         """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a baseline JPEG file, decoded on the GPU
         (Huffman on the host, the rest in CUDA): uint8 [H][W][3] BGR.  Raises LocrError for files outside the covered
-        subset (progressive, CMYK, EXIF-rotated ...)."""
+        subset (arithmetic-coded, CMYK, truncated ...)."""
         data = bytes(data)
         h, w, _ = jpeg_info(data)
         out = np.empty((h, w, 3), np.uint8)

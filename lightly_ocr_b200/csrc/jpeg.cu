@@ -1,11 +1,13 @@
 // cv2.imread / cv2.imdecode(IMREAD_COLOR) for baseline JPEG files — the step in front of the detect-then-recognize path
 // (reference ocr/pipeline.py:68).  OpenCV hands JPEG files to libjpeg(-turbo) with its defaults; the
 // stages are restated from the published algorithms and are integer-exact:
-//   host   : marker parsing, Huffman entropy decoding of the interleaved baseline scan (ITU-T T.81 annex F), one host
-//            thread per image -> quantised coefficients, int16 [component][block row][block col][64] in pinned memory
+//   host   : marker parsing, Huffman entropy decoding (ITU-T T.81 annex F: sequential scans; annex G: progressive scans
+//            with spectral selection, successive approximation and EOB runs), one host thread per image -> quantised
+//            coefficients, int16 [component][block row][block col][64] in pinned memory
 //   device : jpeg_idct_kernel   dequantisation + jidctint.c "ISLOW" inverse DCT (CONST_BITS 13, PASS1_BITS 2)
 //            jpeg_color_kernel  jdsample.c up-sampling (triangle filters for 2:1 ratios, replication otherwise) fused
 //                               with jdcolor.c YCbCr -> RGB (16-bit fixed point), written as packed BGR
+// EXIF orientations 2-8 are applied while the pixels are written, like cv2.imread does after decoding.
 // The entropy decoder is inherently serial per restart interval, which is why it stays on host cores; everything that
 // is data-parallel runs on the GPU and the decoded image never visits the host.
 #include "jpeg.cuh"
@@ -49,9 +51,14 @@ struct Header {
     bool qt_present[4] = {false, false, false, false};
     HuffTab dc[4], ac[4];
     int restart_interval = 0;
-    const uint8_t* scan = nullptr;
+    const uint8_t* data = nullptr;   // the whole file
+    size_t size = 0;
+    const uint8_t* scan = nullptr;   // entropy-coded data of the first scan
     size_t scan_len = 0;
     int orientation = 1;
+    bool progressive = false;    // SOF2
+    bool fast = false;           // one interleaved sequential scan in frame order: decode_scan(); else decode_multiscan()
+    size_t sos_pos = 0;          // offset of the first SOS marker (multi-scan files are walked again from here)
     int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
     size_t coef_elems = 0, plane_bytes = 0;
 };
@@ -106,6 +113,8 @@ int exif_orientation(const uint8_t* t, size_t n) {
 bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
     auto bad = [&](const char* m) { *err = std::string("JPEG: ") + m; return false; };
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return bad("not a JPEG file (no SOI marker)");
+    hd->data = d;
+    hd->size = n;
     size_t pos = 2;
     struct Frame { int id, h, v, tq; } frame[3];
     int nframe = 0;
@@ -136,8 +145,9 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
                 i += pq ? 128 : 64;
                 hd->qt_present[tq] = true;
             }
-        } else if (m == 0xC0 || m == 0xC1) {
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (sl < 6 || s[0] != 8) return bad("only 8-bit samples are supported");
+            hd->progressive = m == 0xC2;
             hd->H = (s[1] << 8) | s[2];
             hd->W = (s[3] << 8) | s[4];
             nframe = s[5];
@@ -146,8 +156,8 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
             for (int k = 0; k < nframe; ++k)
                 frame[k] = {s[6 + 3 * k], s[7 + 3 * k] >> 4, s[7 + 3 * k] & 15, s[8 + 3 * k]};
             have_frame = true;
-        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-            return bad("unsupported JPEG process (progressive / lossless / arithmetic): only baseline sequential Huffman");
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return bad("unsupported JPEG process (lossless / hierarchical / arithmetic-coded): only Huffman-coded DCT files");
         } else if (m == 0xC4) {
             size_t i = 0;
             while (i < sl) {
@@ -168,27 +178,33 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
             if (nframe == 3 && s[11] == 0) return bad("Adobe RGB (untransformed) files are not supported");
         } else if (m == 0xDA) {
             if (!have_frame) return bad("SOS before SOF");
-            if (sl < 1 || s[0] != nframe || sl < 1 + 2 * (size_t)nframe)
-                return bad("non-interleaved scans are not supported");
+            const int ns = sl >= 1 ? s[0] : 0;
+            if (ns < 1 || ns > nframe || sl < 4 + 2 * (size_t)ns) return bad("bad SOS segment");
             hd->ncomp = nframe;
             for (int k = 0; k < nframe; ++k) {
-                const int cid = s[1 + 2 * k], tabs = s[2 + 2 * k];
-                int f = -1;
-                for (int j = 0; j < nframe; ++j)
-                    if (frame[j].id == cid) f = j;
-                if (f < 0) return bad("scan component not in frame");
                 Comp& c = hd->comp[k];
-                c.id = cid; c.h = frame[f].h; c.v = frame[f].v; c.tq = frame[f].tq; c.td = tabs >> 4; c.ta = tabs & 15;
-                if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4 || c.tq > 3 || c.td > 3 || c.ta > 3) return bad("bad component");
-                if (!hd->qt_present[c.tq] || !hd->dc[c.td].present || !hd->ac[c.ta].present) return bad("missing table");
+                c.id = frame[k].id; c.h = frame[k].h; c.v = frame[k].v; c.tq = frame[k].tq; c.td = c.ta = 0;
+                if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4 || c.tq > 3) return bad("bad component");
+                if (!hd->qt_present[c.tq]) return bad("missing quantisation table");
             }
+            // the common file: ONE interleaved sequential scan with the components in frame order
+            hd->fast = !hd->progressive && ns == nframe;
+            for (int k = 0; k < ns && hd->fast; ++k) {
+                const int cid = s[1 + 2 * k], tabs = s[2 + 2 * k];
+                Comp& c = hd->comp[k];
+                if (cid != c.id) { hd->fast = false; break; }
+                c.td = tabs >> 4; c.ta = tabs & 15;
+                if (c.td > 3 || c.ta > 3) return bad("bad component");
+                if (!hd->dc[c.td].present || !hd->ac[c.ta].present) return bad("missing table");
+            }
+            hd->sos_pos = pos - len - 2;
             hd->scan = d + pos;
             hd->scan_len = n - pos;
             break;
         }
     }
     if (hd->H <= 0 || hd->W <= 0) return bad("empty image");
-    if (hd->orientation != 1) return bad("EXIF orientation other than 1 (cv2.imread would rotate the image) is not supported");
+    if (hd->orientation < 1 || hd->orientation > 8) hd->orientation = 1;   // OpenCV leaves other values alone
     hd->hmax = hd->vmax = 1;
     for (int k = 0; k < hd->ncomp; ++k) {
         if (hd->comp[k].h > hd->hmax) hd->hmax = hd->comp[k].h;
@@ -329,6 +345,214 @@ bool decode_scan(const Header& hd, int16_t* coef, std::string* err) {
     return true;
 }
 
+// One block of a progressive or non-interleaved scan (T.81 annex G; the refinement pass follows jdphuff.c's
+// decode_mcu_AC_refine flow).  ss / se = spectral selection, ah / al = successive approximation.
+inline bool decode_block_general(BitReader& br, int16_t* blk, const HuffTab* dct, const HuffTab* act, int ss, int se,
+                                 int ah, int al, bool progressive, int* pred, int* eobrun) {
+    br.fill();
+    if (ss == 0) {
+        if (ah == 0) {
+            const int s = decode_symbol(br, *dct);
+            if (s < 0 || s > 15) return false;
+            if (s) {
+                const int v = (int)br.peek(s);
+                br.skip(s);
+                *pred += v >= (1 << (s - 1)) ? v : v - (1 << s) + 1;
+            }
+            blk[0] = (int16_t)(*pred * (1 << al));
+        } else {
+            if (br.peek(1)) blk[0] = (int16_t)(blk[0] | (1 << al));
+            br.skip(1);
+        }
+        if (se == 0) return true;
+    }
+    int k = ss > 1 ? ss : 1;
+    if (ah == 0) {
+        if (*eobrun > 0) { --*eobrun; return true; }
+        while (k <= se) {
+            if (br.n < 32) br.fill();
+            const int rs = decode_symbol(br, *act);
+            if (rs < 0) return false;
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+                if (r == 15) { k += 16; continue; }
+                if (progressive) {
+                    *eobrun = (1 << r) - 1;
+                    if (r) { *eobrun += (int)br.peek(r); br.skip(r); }
+                }
+                break;
+            }
+            k += r;
+            if (k > 63) return false;
+            const int v = (int)br.peek(s);
+            br.skip(s);
+            blk[kZigzag[k]] = (int16_t)((v >= (1 << (s - 1)) ? v : v - (1 << s) + 1) * (1 << al));
+            ++k;
+        }
+        return true;
+    }
+    const int p1 = 1 << al, m1 = -(1 << al);
+    if (*eobrun == 0) {
+        while (k <= se) {
+            if (br.n < 32) br.fill();
+            const int rs = decode_symbol(br, *act);
+            if (rs < 0) return false;
+            int r = rs >> 4;
+            const int s = rs & 15;
+            int val = 0;
+            if (s) {
+                val = br.peek(1) ? p1 : m1;
+                br.skip(1);
+            } else if (r != 15) {
+                *eobrun = 1 << r;
+                if (r) { *eobrun += (int)br.peek(r); br.skip(r); }
+                break;
+            }
+            while (k <= se) {
+                int16_t* c = blk + kZigzag[k];
+                if (*c != 0) {
+                    if (br.n < 8) br.fill();
+                    if (br.peek(1) && (*c & p1) == 0) *c = (int16_t)(*c + (*c >= 0 ? p1 : m1));
+                    br.skip(1);
+                } else if (--r < 0) {
+                    break;
+                }
+                ++k;
+            }
+            if (val && k <= 63) blk[kZigzag[k]] = (int16_t)val;
+            ++k;
+        }
+    }
+    if (*eobrun > 0) {
+        while (k <= se) {
+            int16_t* c = blk + kZigzag[k];
+            if (*c != 0) {
+                if (br.n < 8) br.fill();
+                if (br.peek(1) && (*c & p1) == 0) *c = (int16_t)(*c + (*c >= 0 ? p1 : m1));
+                br.skip(1);
+            }
+            ++k;
+        }
+        --*eobrun;
+    }
+    return true;
+}
+
+// Progressive files and sequential files with more than one scan: walks the marker segments from the first SOS on
+// (Huffman tables and the restart interval may change between scans) and decodes every scan into the coefficient planes.
+bool decode_multiscan(const Header& hd, int16_t* coef, std::string* err) {
+    auto bad = [&](const char* m) { *err = std::string("JPEG: ") + m; return false; };
+    std::vector<HuffTab> dc(hd.dc, hd.dc + 4), ac(hd.ac, hd.ac + 4);
+    int ri = hd.restart_interval;
+    memset(coef, 0, hd.coef_elems * 2);
+    const uint8_t* d = hd.data;
+    const size_t n = hd.size;
+    size_t pos = hd.sos_pos;
+    int scans = 0;
+    while (pos + 4 <= n) {
+        if (d[pos] != 0xFF) return bad("marker expected between scans");
+        while (pos + 1 < n && d[pos + 1] == 0xFF) ++pos;
+        if (pos + 2 > n) break;
+        const int m = d[pos + 1];
+        pos += 2;
+        if (m == 0xD9) break;
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (pos + 2 > n) return bad("truncated file");
+        const size_t len = ((size_t)d[pos] << 8) | d[pos + 1];
+        if (len < 2 || pos + len > n) return bad("truncated segment");
+        const uint8_t* s = d + pos + 2;
+        const size_t sl = len - 2;
+        pos += len;
+        if (m == 0xC4) {
+            size_t i = 0;
+            while (i < sl) {
+                if (i + 17 > sl) return bad("bad DHT segment");
+                const int tc = s[i] >> 4, th = s[i] & 15;
+                int cnt = 0;
+                for (int k = 0; k < 16; ++k) cnt += s[i + 1 + k];
+                if (tc > 1 || th > 3 || cnt > 256 || i + 17 + cnt > sl) return bad("bad DHT segment");
+                build_table(s + i + 1, s + i + 17, cnt, tc ? &ac[th] : &dc[th]);
+                i += 17 + (size_t)cnt;
+            }
+        } else if (m == 0xDD) {
+            if (sl < 2) return bad("bad DRI segment");
+            ri = (s[0] << 8) | s[1];
+        } else if (m == 0xDB) {
+            return bad("quantisation tables redefined between scans are not supported");
+        } else if (m == 0xDA) {
+            const int ns = sl >= 1 ? s[0] : 0;
+            if (ns < 1 || ns > hd.ncomp || sl < 4 + 2 * (size_t)ns) return bad("bad SOS segment");
+            int ci[3], td[3], ta[3];
+            for (int k = 0; k < ns; ++k) {
+                ci[k] = -1;
+                for (int j = 0; j < hd.ncomp; ++j)
+                    if (hd.comp[j].id == s[1 + 2 * k]) ci[k] = j;
+                td[k] = s[2 + 2 * k] >> 4;
+                ta[k] = s[2 + 2 * k] & 15;
+                if (ci[k] < 0 || td[k] > 3 || ta[k] > 3) return bad("bad scan component");
+            }
+            const int ss = s[1 + 2 * ns], se = s[2 + 2 * ns], ah = s[3 + 2 * ns] >> 4, al = s[3 + 2 * ns] & 15;
+            if (ss > se || se > 63 || al > 13 || ah > 13) return bad("bad scan parameters");
+            if (!hd.progressive && (ss != 0 || se != 63 || ah || al)) return bad("bad sequential scan header");
+            if (hd.progressive && ss == 0 && se != 0) return bad("bad progressive scan header");
+            if (ss > 0 && ns != 1) return bad("AC scans must hold one component");
+            for (int k = 0; k < ns; ++k) {
+                if (ss == 0 && ah == 0 && !dc[td[k]].present) return bad("missing DC table");
+                if (se > 0 && !ac[ta[k]].present) return bad("missing AC table");
+            }
+            BitReader br;
+            br.p = d + pos;
+            br.end = d + n;
+            int pred[3] = {0, 0, 0};
+            int eobrun = 0;
+            // units of the scan: whole MCUs when interleaved, else the blocks of the component's true extent
+            const Comp& c0 = hd.comp[ci[0]];
+            const int ux = ns > 1 ? hd.mcux : (c0.dw + 7) / 8;
+            const int uy = ns > 1 ? hd.mcuy : (c0.dh + 7) / 8;
+            int until_restart = ri;
+            for (int u = 0; u < ux * uy; ++u) {
+                if (ri && until_restart == 0) {
+                    br.acc = 0; br.n = 0; br.pad = 0;
+                    const uint8_t* q = br.p;
+                    while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+                    if (q + 1 >= br.end) return bad("restart marker missing");
+                    br.p = q + 2;
+                    br.marker = false;
+                    pred[0] = pred[1] = pred[2] = 0;
+                    eobrun = 0;
+                    until_restart = ri;
+                }
+                --until_restart;
+                const int uy_i = u / ux, ux_i = u - uy_i * ux;
+                for (int k = 0; k < ns; ++k) {
+                    const Comp& c = hd.comp[ci[k]];
+                    const int nh = ns > 1 ? c.h : 1, nv = ns > 1 ? c.v : 1;
+                    for (int by = 0; by < nv; ++by)
+                        for (int bx = 0; bx < nh; ++bx) {
+                            int16_t* blk = coef + c.coef_off +
+                                           ((size_t)(uy_i * nv + by) * c.blocks_h + (ux_i * nh + bx)) * 64;
+                            if (!decode_block_general(br, blk, &dc[td[k]], &ac[ta[k]], ss, se, ah, al, hd.progressive,
+                                                      &pred[ci[k]], &eobrun))
+                                return bad("corrupt entropy-coded data");
+                            if (br.exhausted()) return bad("premature end of the entropy-coded data");
+                        }
+                }
+            }
+            // next marker: the first 0xFF that is followed by neither a stuffed zero, a restart marker nor a fill byte
+            const uint8_t* q = br.p;
+            while (q + 1 < d + n && !(q[0] == 0xFF && q[1] != 0x00 && q[1] != 0xFF && !(q[1] >= 0xD0 && q[1] <= 0xD7))) ++q;
+            pos = (size_t)(q - d);
+            ++scans;
+        }
+    }
+    if (scans == 0) return bad("no scan");
+    return true;
+}
+
+bool decode_image(const Header& hd, int16_t* coef, std::string* err) {
+    return hd.fast ? decode_scan(hd, coef, err) : decode_multiscan(hd, coef, err);
+}
+
 // ---------------------------------------------------------------------------------------------- device kernels
 
 struct IdctParams {
@@ -420,7 +644,8 @@ struct ColorParams {
     const uint8_t* plane[3];
     int pitch[3], dw[3], dh[3], hs[3], vs[3], mode[3];
     int ncomp, H, W;
-    uint8_t* out;   // packed [H][W][3] BGR
+    int orientation;   // EXIF orientation 1..8 (OpenCV's ExifTransform applied while writing)
+    uint8_t* out;      // packed BGR, [H][W][3] for orientations 1-4, [W][H][3] for 5-8
 };
 
 // jdsample.c: h2v1_fancy_upsample / h2v2_fancy_upsample / h1v2_fancy_upsample / int_upsample, evaluated per output sample
@@ -468,7 +693,20 @@ __global__ void jpeg_color_kernel(const ColorParams p) {
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= p.W || y >= p.H) return;
     const int Y = upsampled(p.plane[0], p.pitch[0], p.dw[0], p.dh[0], p.mode[0], p.hs[0], p.vs[0], y, x);
-    uint8_t* o = p.out + ((size_t)y * p.W + x) * 3;
+    // cv2.imread applies the EXIF orientation (loadsave.cpp ExifTransform: flips for 2-4, a transpose followed by a flip
+    // for 5-8): source pixel (y, x) lands at (yd, xd) of the rotated image
+    int yd = y, xd = x, wd = p.W;
+    switch (p.orientation) {
+        case 2: xd = p.W - 1 - x; break;
+        case 3: yd = p.H - 1 - y; xd = p.W - 1 - x; break;
+        case 4: yd = p.H - 1 - y; break;
+        case 5: yd = x; xd = y; wd = p.H; break;
+        case 6: yd = x; xd = p.H - 1 - y; wd = p.H; break;
+        case 7: yd = p.W - 1 - x; xd = p.H - 1 - y; wd = p.H; break;
+        case 8: yd = p.W - 1 - x; xd = y; wd = p.H; break;
+        default: break;
+    }
+    uint8_t* o = p.out + ((size_t)yd * wd + xd) * 3;
     if (p.ncomp == 1) {
         o[0] = o[1] = o[2] = (uint8_t)Y;
         return;
@@ -498,8 +736,9 @@ struct PinnedBuf {
 int jpeg_probe(const uint8_t* data, size_t nbytes, int* height, int* width, int* components, std::string* err) {
     std::vector<Header> hd(1);
     if (!parse(data, nbytes, &hd[0], err)) return LOCR_ERR_INVALID;
-    *height = hd[0].H;
-    *width = hd[0].W;
+    const bool swap = hd[0].orientation >= 5;     // size of the image as cv2.imread returns it
+    *height = swap ? hd[0].W : hd[0].H;
+    *width = swap ? hd[0].H : hd[0].W;
     *components = hd[0].ncomp;
     return LOCR_OK;
 }
@@ -518,7 +757,7 @@ int jpeg_host_coefficients(const uint8_t* data, size_t nbytes, int16_t* out, siz
     }
     if (out == nullptr) return LOCR_OK;
     if (capacity < H.coef_elems) { *err = "JPEG: coefficient buffer too small"; return LOCR_ERR_CAPACITY; }
-    if (!decode_scan(H, out, err)) return LOCR_ERR_INVALID;
+    if (!decode_image(H, out, err)) return LOCR_ERR_INVALID;
     return LOCR_OK;
 }
 
@@ -551,7 +790,7 @@ int jpeg_decode_to_device(locr_handle* h, const uint8_t* const* blobs, const int
             for (;;) {
                 const int i = next.fetch_add(1);
                 if (i >= n) break;
-                if (!decode_scan(hd[i], hc + coef_off[i], &errs[i])) ok[i] = 0;
+                if (!decode_image(hd[i], hc + coef_off[i], &errs[i])) ok[i] = 0;
             }
         };
         if (nthreads <= 1) {
@@ -601,6 +840,7 @@ int jpeg_decode_to_device(locr_handle* h, const uint8_t* const* blobs, const int
         }
         cp.H = H.H;
         cp.W = H.W;
+        cp.orientation = H.orientation;
         cp.out = d_out[i];
         {
             ProfScope ps_(h, "jpeg_idct", 0, false);

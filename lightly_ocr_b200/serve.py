@@ -121,9 +121,9 @@ class serveModel:
 
     @staticmethod
     def _read(r):
-        """pipeline.py:68 `cv2.imread(path)`.  Baseline JPEG uploads stay encoded (r.blob): liblocr decodes them on the
-        GPU, bit-identical to OpenCV (include/locr.h locr_detect_encoded).  Everything else - PNG, progressive or
-        EXIF-rotated JPEG ... - is read by OpenCV itself."""
+        """pipeline.py:68 `cv2.imread(path)`.  JPEG uploads (baseline, sequential or progressive Huffman files) stay encoded
+        (r.blob): liblocr decodes them on the GPU, bit-identical to OpenCV incl. the EXIF rotation (include/locr.h
+        locr_detect_encoded).  Everything else - PNG, arithmetic-coded or CMYK JPEG ... - is read by OpenCV itself."""
         with open(r.path, "rb") as f:
             data = f.read()
         if data[:2] == b"\xff\xd8":

@@ -113,7 +113,8 @@ def _exif_orientation(tiff):
         for k in range(n):
             e = tiff[off + 2 + 12 * k:off + 14 + 12 * k]
             if rd(e[0:2]) == 0x0112:
-                return rd(e[8:10])
+                v = rd(e[8:10])
+                return v if 1 <= v <= 8 else 1
     except Exception:
         pass
     return 1
@@ -234,6 +235,257 @@ def decode_coefficients(info):
     return planes, (hmax, vmax, mcux, mcuy)
 
 
+def parse_scans(data):
+    """Every marker segment of a Huffman-coded 8-bit file, progressive (SOF2) or sequential, any number of scans.
+    Returns the frame description plus `scans`: a list of dicts (comps [(component index, td, ta)], ss, se, ah, al,
+    dc / ac tables and restart interval in force, entropy-coded bytes)."""
+    data = bytes(data)
+    if len(data) < 4 or data[0] != 0xFF or data[1] != 0xD8:
+        raise JpegError("not a JPEG file (no SOI)")
+    pos = 2
+    out = {"qt": {}, "orientation": 1, "scans": [], "progressive": False}
+    dc, ac, ri, frame = {}, {}, 0, None
+    while pos + 4 <= len(data):
+        if data[pos] != 0xFF:
+            raise JpegError("marker expected at byte %d" % pos)
+        while data[pos + 1] == 0xFF:
+            pos += 1
+        m = data[pos + 1]
+        pos += 2
+        if m == 0xD9:
+            break
+        if m == 0x01 or 0xD0 <= m <= 0xD7:
+            continue
+        n = (data[pos] << 8) | data[pos + 1]
+        seg = data[pos + 2:pos + n]
+        if len(seg) != n - 2:
+            raise JpegError("truncated segment")
+        pos += n
+        if m == 0xDB:
+            i = 0
+            while i < len(seg):
+                pq, tq = seg[i] >> 4, seg[i] & 15
+                i += 1
+                vals = [(seg[i + 2 * k] << 8) | seg[i + 2 * k + 1] for k in range(64)] if pq else list(seg[i:i + 64])
+                i += 128 if pq else 64
+                q = np.zeros(64, np.int32)
+                q[ZIGZAG] = vals
+                out["qt"][tq] = q
+        elif m in (0xC0, 0xC1, 0xC2):
+            if seg[0] != 8:
+                raise JpegError("only 8-bit samples are supported")
+            out["progressive"] = m == 0xC2
+            out["height"] = (seg[1] << 8) | seg[2]
+            out["width"] = (seg[3] << 8) | seg[4]
+            frame = [(seg[6 + 3 * k], seg[7 + 3 * k] >> 4, seg[7 + 3 * k] & 15, seg[8 + 3 * k]) for k in range(seg[5])]
+            if len(frame) == 1:
+                frame = [(frame[0][0], 1, 1, frame[0][3])]
+            out["frame"] = frame
+        elif m in (0xC3, 0xC5, 0xC6, 0xC7, 0xC9, 0xCA, 0xCB, 0xCD, 0xCE, 0xCF):
+            raise JpegError("unsupported JPEG process (SOF%d)" % (m - 0xC0))
+        elif m == 0xC4:
+            i = 0
+            while i < len(seg):
+                tc, th = seg[i] >> 4, seg[i] & 15
+                bits = list(seg[i + 1:i + 17])
+                cnt = sum(bits)
+                (ac if tc else dc)[th] = (bits, list(seg[i + 17:i + 17 + cnt]))
+                i += 17 + cnt
+        elif m == 0xDD:
+            ri = (seg[0] << 8) | seg[1]
+        elif m == 0xE1 and seg[:6] == b"Exif\x00\x00":
+            out["orientation"] = _exif_orientation(seg[6:])
+        elif m == 0xDA:
+            if frame is None:
+                raise JpegError("SOS before SOF")
+            ns = seg[0]
+            comps = []
+            for k in range(ns):
+                idx = [j for j, c in enumerate(frame) if c[0] == seg[1 + 2 * k]]
+                if not idx:
+                    raise JpegError("scan component not in frame")
+                comps.append((idx[0], seg[2 + 2 * k] >> 4, seg[2 + 2 * k] & 15))
+            ss, se, a = seg[1 + 2 * ns], seg[2 + 2 * ns], seg[3 + 2 * ns]
+            end = pos
+            while end + 1 < len(data):     # the entropy-coded segment runs up to the next real marker
+                if data[end] == 0xFF and data[end + 1] != 0x00 and not (0xD0 <= data[end + 1] <= 0xD7) and data[end + 1] != 0xFF:
+                    break
+                end += 1
+            else:
+                end = len(data)
+            out["scans"].append(dict(comps=comps, ss=ss, se=se, ah=a >> 4, al=a & 15, dc=dict(dc), ac=dict(ac), ri=ri,
+                                     data=data[pos:end]))
+            pos = end
+    if frame is None or not out["scans"]:
+        raise JpegError("no image data")
+    return out
+
+
+class _Bits:
+    """Bit reader over one restart segment (byte stuffing already removed); zero bits after the end."""
+
+    def __init__(self, seg):
+        self.acc = int.from_bytes(seg + b"\x00" * 8, "big")
+        self.n = (len(seg) + 8) * 8
+        self.pos = 0
+        self.limit = len(seg) * 8
+
+    def bits(self, k):
+        if k == 0:
+            return 0
+        v = (self.acc >> (self.n - self.pos - k)) & ((1 << k) - 1)
+        self.pos += k
+        return v
+
+    def symbol(self, table):
+        length, sym = table
+        peek = (self.acc >> (self.n - self.pos - 16)) & 0xFFFF
+        ln = int(length[peek])
+        if ln == 0:
+            raise JpegError("bad Huffman code")
+        self.pos += ln
+        return int(sym[peek])
+
+
+def _extend(v, s):
+    return v if s == 0 or v >= (1 << (s - 1)) else v - (1 << s) + 1
+
+
+def _split_restarts(scan):
+    segs, cur, i = [], bytearray(), 0
+    while i < len(scan):
+        b = scan[i]
+        if b != 0xFF:
+            cur.append(b)
+            i += 1
+            continue
+        nb = scan[i + 1] if i + 1 < len(scan) else 0xD9
+        if nb == 0x00:
+            cur.append(0xFF)
+            i += 2
+        elif 0xD0 <= nb <= 0xD7:
+            segs.append(bytes(cur))
+            cur = bytearray()
+            i += 2
+        elif nb == 0xFF:
+            i += 1
+        else:
+            break
+    segs.append(bytes(cur))
+    return segs
+
+
+def decode_scans(info):
+    """Entropy decoding of all scans (T.81 annex F sequential, annex G progressive with spectral selection and successive
+    approximation; restated from the standard's flow charts / jdphuff.c).  Same return value as decode_coefficients."""
+    frame = info["frame"]
+    hmax = max(c[1] for c in frame)
+    vmax = max(c[2] for c in frame)
+    H, W = info["height"], info["width"]
+    mcux = (W + 8 * hmax - 1) // (8 * hmax)
+    mcuy = (H + 8 * vmax - 1) // (8 * vmax)
+    planes = [np.zeros((mcuy * c[2], mcux * c[1], 64), np.int32) for c in frame]
+    for sc in info["scans"]:
+        dct = {k: _huff_lookup(*v) for k, v in sc["dc"].items()}
+        act = {k: _huff_lookup(*v) for k, v in sc["ac"].items()}
+        ss, se, ah, al = sc["ss"], sc["se"], sc["ah"], sc["al"]
+        if not info["progressive"] and (ss != 0 or se != 63 or ah or al):
+            raise JpegError("bad sequential scan header")
+        if info["progressive"] and ss == 0 and se != 0:
+            raise JpegError("bad progressive scan header")
+        if ss > 0 and len(sc["comps"]) != 1:
+            raise JpegError("AC scans must have one component")
+        # the units of the scan: whole MCUs for interleaved scans, single blocks of the component's true extent otherwise
+        if len(sc["comps"]) > 1:
+            units = [[(ci, my * frame[ci][2] + by, mx * frame[ci][1] + bx, td, ta)
+                      for (ci, td, ta) in sc["comps"] for by in range(frame[ci][2]) for bx in range(frame[ci][1])]
+                     for my in range(mcuy) for mx in range(mcux)]
+        else:
+            ci, td, ta = sc["comps"][0]
+            bw = ((W * frame[ci][1] + hmax - 1) // hmax + 7) // 8
+            bh = ((H * frame[ci][2] + vmax - 1) // vmax + 7) // 8
+            units = [[(ci, by, bx, td, ta)] for by in range(bh) for bx in range(bw)]
+        segs = _split_restarts(sc["data"])
+        ri = sc["ri"] if sc["ri"] else len(units)
+        u = 0
+        for seg in segs:
+            if u >= len(units):
+                break
+            br = _Bits(seg)
+            pred = [0] * len(frame)
+            eobrun = 0
+            for unit in units[u:u + ri]:
+                for (ci, by, bx, td, ta) in unit:
+                    blk = planes[ci][by, bx]
+                    if ss == 0:
+                        if ah == 0:                                   # DC first scan (or the DC of a sequential scan)
+                            s = br.symbol(dct[td])
+                            pred[ci] += _extend(br.bits(s), s)
+                            blk[0] = pred[ci] * (1 << al)
+                        elif br.bits(1):                              # DC refinement
+                            blk[0] |= 1 << al
+                        if se == 0:
+                            continue
+                    k0 = max(ss, 1)
+                    if ah == 0:                                       # AC first scan / sequential AC
+                        if eobrun > 0:
+                            eobrun -= 1
+                            continue
+                        k = k0
+                        while k <= se:
+                            rs = br.symbol(act[ta])
+                            r, s = rs >> 4, rs & 15
+                            if s == 0:
+                                if r == 15:
+                                    k += 16
+                                    continue
+                                if info["progressive"]:
+                                    eobrun = (1 << r) + br.bits(r) - 1
+                                break
+                            k += r
+                            if k > 63:
+                                raise JpegError("coefficient index out of range")
+                            blk[ZIGZAG[k]] = _extend(br.bits(s), s) * (1 << al)
+                            k += 1
+                    else:                                             # AC refinement (jdphuff.c decode_mcu_AC_refine)
+                        p1, m1 = 1 << al, -(1 << al)
+                        k = k0
+                        if eobrun == 0:
+                            while k <= se:
+                                rs = br.symbol(act[ta])
+                                r, s = rs >> 4, rs & 15
+                                val = 0
+                                if s:
+                                    val = p1 if br.bits(1) else m1
+                                elif r != 15:
+                                    eobrun = (1 << r) + br.bits(r)
+                                    break
+                                while k <= se:
+                                    z = ZIGZAG[k]
+                                    if blk[z] != 0:
+                                        if br.bits(1) and (blk[z] & p1) == 0:
+                                            blk[z] += p1 if blk[z] >= 0 else m1
+                                    else:
+                                        r -= 1
+                                        if r < 0:
+                                            break
+                                    k += 1
+                                if val and k <= 63:
+                                    blk[ZIGZAG[k]] = val
+                                k += 1
+                        if eobrun > 0:
+                            while k <= se:
+                                z = ZIGZAG[k]
+                                if blk[z] != 0 and br.bits(1) and (blk[z] & p1) == 0:
+                                    blk[z] += p1 if blk[z] >= 0 else m1
+                                k += 1
+                            eobrun -= 1
+                    if br.pos > br.limit:
+                        raise JpegError("premature end of the entropy-coded data")
+            u += ri
+    return [p.astype(np.int16) for p in planes], (hmax, vmax, mcux, mcuy)
+
+
 # jidctint.c: CONST_BITS = 13, PASS1_BITS = 2
 _F = dict(f0298=2446, f0390=3196, f0541=4433, f0765=6270, f0899=7373, f1175=9633, f1501=12299, f1847=15137, f1961=16069,
           f2053=16819, f2562=20995, f3072=25172)
@@ -345,13 +597,18 @@ def ycc_to_bgr(y, cb, cr):
 
 
 def imdecode(data):
-    """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a baseline JPEG: uint8 [H][W][3] BGR."""
-    info = parse(data)
-    if info["orientation"] != 1:
-        raise JpegError("EXIF orientation %d: rotation on load is not supported" % info["orientation"])
-    planes, (hmax, vmax, mcux, mcuy) = decode_coefficients(info)
+    """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a Huffman-coded 8-bit JPEG (baseline, extended
+    sequential or progressive): uint8 [H][W][3] BGR, rotated by the EXIF orientation like OpenCV does."""
+    multi = parse_scans(data)
+    if not multi["progressive"] and len(multi["scans"]) == 1 and len(multi["scans"][0]["comps"]) == len(multi["frame"]):
+        info = parse(data)                                   # the common baseline file: one interleaved scan
+        planes, (hmax, vmax, mcux, mcuy) = decode_coefficients(info)
+        comps = info["comps"]
+    else:
+        info = multi
+        planes, (hmax, vmax, mcux, mcuy) = decode_scans(info)
+        comps = [c + (0, 0) for c in info["frame"]]
     H, W = info["height"], info["width"]
-    comps = info["comps"]
     full = []
     for (cid, ch, cv, tq, td, ta), coef in zip(comps, planes):
         pl = _plane(idct_islow(coef, info["qt"][tq]))
@@ -376,7 +633,43 @@ def imdecode(data):
             raise JpegError("unsupported sampling factors")
         full.append(pl[:H, :W])
     if len(full) == 1:
-        return np.repeat(full[0][..., None], 3, -1)
-    if len(full) != 3:
+        img = np.repeat(full[0][..., None], 3, -1)
+    elif len(full) == 3:
+        img = ycc_to_bgr(*full)
+    else:
         raise JpegError("unsupported number of components")
-    return ycc_to_bgr(*full)
+    return exif_transform(img, info["orientation"])
+
+
+def exif_transform(img, orientation):
+    """OpenCV's ExifTransform (modules/imgcodecs/src/loadsave.cpp): cv2.imread / imdecode rotate the decoded image by the
+    EXIF orientation tag (IFD0 tag 0x0112) unless IMREAD_IGNORE_ORIENTATION is given; other values leave it alone."""
+    if orientation == 2:
+        img = img[:, ::-1]
+    elif orientation == 3:
+        img = img[::-1, ::-1]
+    elif orientation == 4:
+        img = img[::-1]
+    elif orientation == 5:
+        img = img.transpose(1, 0, 2)
+    elif orientation == 6:
+        img = img.transpose(1, 0, 2)[:, ::-1]
+    elif orientation == 7:
+        img = img.transpose(1, 0, 2)[::-1, ::-1]
+    elif orientation == 8:
+        img = img.transpose(1, 0, 2)[::-1]
+    return np.ascontiguousarray(img)
+
+
+def with_exif_orientation(data, orientation, little_endian=False):
+    """Test helper: the same JPEG file with an APP1 Exif segment carrying the given orientation inserted after SOI."""
+    if little_endian:
+        tiff = b"II\x2a\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00" + \
+            int(orientation).to_bytes(2, "little") + b"\x00\x00" + b"\x00\x00\x00\x00"
+    else:
+        tiff = b"MM\x00\x2a\x00\x00\x00\x08" + b"\x00\x01" + b"\x01\x12\x00\x03\x00\x00\x00\x01" + \
+            int(orientation).to_bytes(2, "big") + b"\x00\x00" + b"\x00\x00\x00\x00"
+    exif = b"Exif\x00\x00" + tiff
+    seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
+    data = bytes(data)
+    return data[:2] + seg + data[2:]

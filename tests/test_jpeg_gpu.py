@@ -61,9 +61,9 @@ def test_imread_and_errors(pipe, tmp_path):
     path = str(tmp_path / "a.jpg")
     cv2.imwrite(path, img)
     assert np.array_equal(pipe.imread(path), cv2.imread(path))
-    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
-    with pytest.raises(bridge.LocrError, match="progressive"):
-        pipe.imdecode(prog.tobytes())
+    ok, png = cv2.imencode(".png", img)
+    with pytest.raises(bridge.LocrError, match="not a JPEG"):
+        pipe.imdecode(png.tobytes())
     ok, good = cv2.imencode(".jpg", img)
     data = good.tobytes()
     with pytest.raises(bridge.LocrError):
@@ -102,3 +102,26 @@ def test_imdecode_pillow_encoded_files(pipe):
         if name == "cmyk":
             continue
         assert np.array_equal(pipe.imdecode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)), name
+
+
+def test_imdecode_exif_orientations(pipe):
+    from oracle import jpeg_ref
+    rng = np.random.default_rng(2)
+    for shape, sf in (((37, 53, 3), "420"), ((64, 48, 3), "444"), ((21, 80), "gray")):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        params = [cv2.IMWRITE_JPEG_QUALITY, 90] + ([] if sf == "gray" else [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SF[sf]])
+        ok, buf = cv2.imencode(".jpg", img, params)
+        for o in range(1, 9):
+            d = jpeg_ref.with_exif_orientation(buf.tobytes(), o, little_endian=(o % 2 == 0))
+            want = cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR)
+            got = pipe.imdecode(d)
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, o)
+
+
+def test_imdecode_progressive_files(pipe):
+    from test_jpeg_oracle import progressive_cases
+    for name, data in progressive_cases():
+        assert np.array_equal(pipe.imdecode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)), name
+    from lightly_ocr_b200.synth import receipts
+    ok, buf = cv2.imencode(".jpg", receipts.receipt(2), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 90])
+    assert np.array_equal(pipe.imdecode(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR))

@@ -101,11 +101,13 @@ def test_library_entropy_decoder_full_receipt():
 def test_unsupported_files_fail_loudly():
     from lightly_ocr_b200 import bridge
     img = np.random.default_rng(0).integers(0, 256, (32, 48, 3), dtype=np.uint8)
-    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    ok, good = cv2.imencode(".jpg", img)
+    arith = bytearray(good.tobytes())
+    arith[arith.index(b"\xff\xc0") + 1] = 0xC9               # SOF9: arithmetic-coded sequential DCT
     with pytest.raises(jpeg_ref.JpegError):
-        jpeg_ref.imdecode(prog.tobytes())
-    with pytest.raises(bridge.LocrError, match="progressive"):
-        bridge.jpeg_info(prog.tobytes())
+        jpeg_ref.imdecode(bytes(arith))
+    with pytest.raises(bridge.LocrError, match="arithmetic"):
+        bridge.jpeg_info(bytes(arith))
     ok, png = cv2.imencode(".png", img)
     with pytest.raises(bridge.LocrError, match="not a JPEG"):
         bridge.jpeg_info(png.tobytes())
@@ -113,16 +115,19 @@ def test_unsupported_files_fail_loudly():
     data = good.tobytes()
     with pytest.raises(bridge.LocrError):
         bridge.jpeg_coefficients(data[:len(data) // 3] + b"\xff\xd9")   # truncated inside a marker segment or the scan
-    # EXIF orientation 6 (cv2.imread would rotate): refused rather than returned unrotated
-    exif = b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01\x00\x06\x00\x00\x00\x00\x00\x00"
-    seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
-    rotated = data[:2] + seg + data[2:]
-    assert cv2.imdecode(np.frombuffer(rotated, np.uint8), cv2.IMREAD_COLOR).shape == (48, 32, 3)
-    with pytest.raises(bridge.LocrError, match="orientation"):
-        bridge.jpeg_info(rotated)
-    with pytest.raises(jpeg_ref.JpegError):
-        jpeg_ref.imdecode(rotated)
 
+
+def test_exif_orientation_like_cv2():
+    """cv2.imread rotates by the EXIF orientation tag; the oracle does the same and the library reports the rotated size."""
+    from lightly_ocr_b200 import bridge
+    img = cv2.GaussianBlur(np.random.default_rng(0).integers(0, 256, (37, 53, 3), dtype=np.uint8), (0, 0), 1.2)
+    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+    for little in (False, True):
+        for o in range(0, 10):
+            d = jpeg_ref.with_exif_orientation(buf.tobytes(), o, little)
+            want = cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR)
+            assert np.array_equal(jpeg_ref.imdecode(d), want), (little, o)
+            assert bridge.jpeg_info(d)[:2] == want.shape[:2], (little, o)
 
 def pillow_cases():
     """Files from a second encoder front end (Pillow): other marker layouts (JFIF density, comments, multi-segment ICC
@@ -161,3 +166,52 @@ def test_pillow_encoded_files():
         assert all(np.array_equal(a, b) for a, b in zip(got, ref)), name
         n += 1
     assert n == 24
+
+
+def progressive_cases():
+    rng = np.random.default_rng(5)
+    imgs = [cv2.GaussianBlur(rng.integers(0, 256, (67, 93, 3), dtype=np.uint8), (0, 0), 1.0),
+            rng.integers(0, 256, (33, 49, 3), dtype=np.uint8), rng.integers(0, 256, (8, 8, 3), dtype=np.uint8),
+            rng.integers(0, 256, (17, 5, 3), dtype=np.uint8)]
+    for img in imgs:
+        for sn, sf in SF.items():
+            for q in (30, 90):
+                for extra in ([], [cv2.IMWRITE_JPEG_RST_INTERVAL, 3], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]):
+                    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, q,
+                                                         cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf] + extra)
+                    yield "%s/%s/q%d/%s" % (img.shape, sn, q, extra), buf.tobytes()
+        ok, buf = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+        yield "%s/gray" % (img.shape,), buf.tobytes()
+    import io
+    from PIL import Image
+    pil = Image.fromarray(imgs[0][..., ::-1])
+    for kw in (dict(progressive=True, quality=85), dict(progressive=True, quality=60, subsampling=0),
+               dict(progressive=True, optimize=True, quality=95, subsampling=1)):
+        for mode in ("RGB", "L"):
+            bio = io.BytesIO()
+            pil.convert(mode).save(bio, "JPEG", **kw)
+            yield "pillow/%s/%s" % (sorted(kw.items()), mode), bio.getvalue()
+
+
+def test_progressive_files():
+    """Progressive (SOF2) files - spectral selection, successive approximation, EOB runs, refinement scans: the oracle
+    equals cv2.imdecode and the library's entropy decoder equals the oracle's coefficients."""
+    from lightly_ocr_b200 import bridge
+    n = 0
+    for name, data in progressive_cases():
+        want = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(jpeg_ref.imdecode(data), want), name
+        ref, _ = jpeg_ref.decode_scans(jpeg_ref.parse_scans(data))
+        got, _ = bridge.jpeg_coefficients(data)
+        assert len(got) == len(ref) and all(np.array_equal(a, b) for a, b in zip(got, ref)), name
+        n += 1
+    assert n == 130
+
+
+def test_multiscan_decoder_equals_single_scan_decoder_on_baseline_files():
+    """The general scan decoder of the oracle, run on baseline files, gives the coefficients of the baseline decoder."""
+    for name, buf in cases():
+        data = buf.tobytes()
+        a, _ = jpeg_ref.decode_coefficients(jpeg_ref.parse(data))
+        b, _ = jpeg_ref.decode_scans(jpeg_ref.parse_scans(data))
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), name

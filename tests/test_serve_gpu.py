@@ -89,8 +89,9 @@ def test_batched_serving_equals_one_at_a_time(tmp_path):
         p = str(d / ("photo%d.jpg" % i))
         cv2.imwrite(p, receipts.receipt(60 + i), [cv2.IMWRITE_JPEG_QUALITY, 90])
         jpgs.append(p)
-    pp = str(d / "progressive.jpg")
-    cv2.imwrite(pp, receipts.receipt(63)[:640, :480], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])     # not covered: OpenCV reads it
+    pp = str(d / "actually_png.jpg")
+    with open(pp, "wb") as f:                 # PNG content under a .jpg name: not for the JPEG reader, OpenCV reads it
+        f.write(cv2.imencode(".png", receipts.receipt(63)[:640, :480])[1].tobytes())
     jpgs.append(pp)
     for p in jpgs:
         res = {}
