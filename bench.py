@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jpeg", action="store_true",
+                    help="extra leg: the same receipts handed over as JPEG files (q90, 4:2:0) through locr_detect_encoded; "
+                         "adds an `e2e_jpeg` object to the JSON line (BASELINE's metric itself excludes the image decode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -248,6 +251,32 @@ def main():
     barrier()
     e2e_s = shard.max_over_ranks(max(e2e_ms / 1e3, e2e_wall), dev)
     launches_e2e = launches() - launches0
+
+    # ---------------- optional: encoded files in (Huffman decoding on host threads, the rest of the JPEG reader on the GPU)
+    e2e_jpeg = None
+    if args.jpeg:
+        import cv2
+        blobs = [[cv2.imencode(".jpg", np.asarray(im), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in b] for b in batches]
+
+        def jpeg_step(k):
+            bl = blobs[k % len(blobs)]
+            return sum(len(o[1]["text"]) for o in lanes(lambda i, r: r.ocr_encoded(bl[i * per_lane:(i + 1) * per_lane])))
+
+        for w in range(max(args.warmup, 3)):
+            jpeg_step(w)
+        barrier()
+        t0 = time.perf_counter()
+        crops_jpeg = sum(jpeg_step(k) for k in range(args.steps))
+        barrier()
+        jpeg_s = shard.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_jpeg = {"value": world * RECEIPTS_PER_STEP * args.steps / jpeg_s, "unit": UNIT,
+                    "crops_per_sec": world * crops_jpeg / jpeg_s,
+                    "file_bytes_per_step": int(sum(len(x) for b in blobs for x in b) / len(blobs)),
+                    "h2d_bytes_per_step": int(sum((im.shape[0] + 15) // 16 * ((im.shape[1] + 15) // 16) * 6 * 128
+                                                  for im in batches[0])),   # quantised coefficients, 4:2:0
+
+                    "input": "JPEG q90 4:2:0 files of the same receipts; entropy decoding on host threads (one per "
+                             "image), coefficients -> pixels on the GPU (lightly_ocr_b200/csrc/jpeg.cu); wall-clock"}
 
     # ---------------- value: the same path with the step's receipts already resident in HBM
     clocks = ClockSampler(local_rank)
@@ -324,6 +353,8 @@ def main():
                          "algorithmic_flops": conv_flops},
             "clocks": clk,
         }
+        if e2e_jpeg is not None:
+            line["e2e_jpeg"] = e2e_jpeg
         if not args.no_cpu_baseline and world == 1:     # rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             secs, ncrops, _ = cpu_oracle_sample(cores, full=True)
