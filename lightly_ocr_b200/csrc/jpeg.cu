@@ -32,6 +32,9 @@ struct HuffTab {
     bool present = false;
     uint8_t vals[256];
     uint16_t look[1 << kLook];   // (code length << 8) | symbol, 0 = longer than kLook bits
+    // AC fast path: when a code AND its magnitude bits fit into the look-ahead window, the decoded coefficient itself:
+    // (value << 16) | (zero run << 8) | (bits consumed), 0 = take the general path
+    int32_t fast[1 << kLook];
     int32_t maxcode[18];
     int32_t valoffset[17];
 };
@@ -88,6 +91,16 @@ void build_table(const uint8_t* bits /* [16] */, const uint8_t* vals, int count,
         code <<= 1;
     }
     t->maxcode[17] = 0x7fffffff;
+    for (int i = 0; i < (1 << kLook); ++i) {
+        t->fast[i] = 0;
+        const uint16_t e = t->look[i];
+        if (!e) continue;
+        const int len = e >> 8, run = (e & 0xFF) >> 4, mag = e & 15;
+        if (mag == 0 || len + mag > kLook) continue;
+        const int v = (i >> (kLook - len - mag)) & ((1 << mag) - 1);
+        const int val = v >= (1 << (mag - 1)) ? v : v - (1 << mag) + 1;
+        t->fast[i] = (int32_t)(((uint32_t)(uint16_t)(int16_t)val << 16) | (uint32_t)(run << 8) | (uint32_t)(len + mag));
+    }
 }
 
 int exif_orientation(const uint8_t* t, size_t n) {
@@ -239,6 +252,15 @@ struct BitReader {
     int pad = 0;         // zero bits appended behind the data (a marker or the end of the file was reached)
     bool marker = false;
     inline void fill() {
+        // fast path: four bytes at a time while none of them is 0xFF (no stuffing, no marker) - the common case
+        while (n <= 32 && !marker && p + 4 <= end) {
+            const uint32_t v = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+            const uint32_t inv = ~v;
+            if ((inv - 0x01010101u) & ~inv & 0x80808080u) break;    // some byte of v is 0xFF
+            acc = (acc << 32) | v;
+            n += 32;
+            p += 4;
+        }
         while (n <= 56) {
             uint32_t b = 0;
             if (!marker && p < end) {
@@ -322,6 +344,15 @@ bool decode_scan(const Header& hd, int16_t* coef, std::string* err) {
                     blk[0] = (int16_t)pred[ci];
                     for (int k = 1; k < 64;) {
                         if (br.n < 32) br.fill();
+                        const int32_t f = act.fast[br.peek(kLook)];
+                        if (f) {                       // code + magnitude inside the look-ahead window
+                            k += (f >> 8) & 15;
+                            if (k > 63) { *err = "JPEG: corrupt entropy-coded data"; return false; }
+                            blk[kZigzag[k]] = (int16_t)(f >> 16);
+                            br.skip(f & 255);
+                            ++k;
+                            continue;
+                        }
                         const int rs = decode_symbol(br, act);
                         if (rs < 0) { *err = "JPEG: corrupt entropy-coded data"; return false; }
                         const int r = rs >> 4;
