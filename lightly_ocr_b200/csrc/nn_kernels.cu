@@ -248,6 +248,15 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
 }
 
 // ------------------------------------------------------------------------------------------- max pool
+__device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b, int f16) {
+    if (f16) {
+        const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&m);
+    }
+    const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
+}
+
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C, uint16_t* __restrict__ out,
                long out_pitch, int OH, int OW, int kh, int kw, int sh, int sw_, int ph, int pw, int f16, int split) {
@@ -261,6 +270,24 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
         const uint32_t rest = pix / (uint32_t)OW;
         const int oy = (int)(rest % (uint32_t)OH);
         const int b = (int)(rest / (uint32_t)OH);
+        if (!split) {
+            // plain tensors: the maximum of 16-bit values is exact in their own format, four packed max per tap
+            const uint32_t ninf = f16 ? 0xFC00FC00u : 0xFF80FF80u;
+            uint4 mp = make_uint4(ninf, ninf, ninf, ninf);
+            for (int ky = 0; ky < kh; ++ky) {
+                const int iy = oy * sh + ky - ph;
+                if (iy < 0 || iy >= H) continue;
+                for (int kx = 0; kx < kw; ++kx) {
+                    const int ix = ox * sw_ + kx - pw;
+                    if (ix < 0 || ix >= W) continue;
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((long)(b * H + iy) * W + ix) * in_pitch + cg * 8));
+                    mp.x = max2_packed(mp.x, u.x, f16); mp.y = max2_packed(mp.y, u.y, f16);
+                    mp.z = max2_packed(mp.z, u.z, f16); mp.w = max2_packed(mp.w, u.w, f16);
+                }
+            }
+            *reinterpret_cast<uint4*>(out + (long)pix * out_pitch + cg * 8) = mp;
+            continue;
+        }
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = -INFINITY;

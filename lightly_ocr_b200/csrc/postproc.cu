@@ -270,24 +270,43 @@ __global__ void __launch_bounds__(1024) pp_assign(const int* __restrict__ parent
 __global__ void pp_stats(const float2* __restrict__ score, const int* __restrict__ parent,
                          const int* __restrict__ rootid, int B, int H, int W, int* area, int* minx, int* miny,
                          int* maxx, int* maxy, int* maxtext, int32_t* __restrict__ labels_out) {
+    // Neighbouring pixels mostly belong to the same component: the lanes of a warp that share a component combine their
+    // contribution with warp reductions and ONE lane issues the six atomics (sum / min / max commute, so the tables come
+    // out exactly as with one atomic per pixel).
     const long npix = (long)B * H * W;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
-        const int r = parent[i];
-        int id = 0;
-        if (r >= 0) {
-            id = rootid[r];
-            if (id < kCap) {
-                const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long)W * H));
-                const int c = b * kCap + id;
-                atomicAdd(&area[c], 1);
-                atomicMin(&minx[c], x);
-                atomicMax(&maxx[c], x);
-                atomicMin(&miny[c], y);
-                atomicMax(&maxy[c], y);
-                atomicMax(&maxtext[c], float_orderable(__ldg(&score[i]).x));
+    const int lane = threadIdx.x & 31;
+    for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < npix; base += (long)gridDim.x * blockDim.x) {
+        const long i = base + lane;
+        int id = 0, c = -1, x = 0, y = 0, t = (int)0x80000000;
+        if (i < npix) {
+            const int r = parent[i];
+            if (r >= 0) {
+                id = rootid[r];
+                if (id < kCap) {
+                    x = (int)(i % W);
+                    y = (int)((i / W) % H);
+                    c = (int)(i / ((long)W * H)) * kCap + id;
+                    t = float_orderable(__ldg(&score[i]).x);
+                }
+            }
+            if (labels_out != nullptr) labels_out[i] = id;
+        }
+        const unsigned fg = __ballot_sync(0xffffffffu, c >= 0);
+        if (c >= 0) {
+            const unsigned peers = __match_any_sync(fg, c);
+            const int cnt = __popc(peers);
+            const int mnx = __reduce_min_sync(peers, x), mxx = __reduce_max_sync(peers, x);
+            const int mny = __reduce_min_sync(peers, y), mxy = __reduce_max_sync(peers, y);
+            const int mt = __reduce_max_sync(peers, t);
+            if (lane == __ffs(peers) - 1) {
+                atomicAdd(&area[c], cnt);
+                atomicMin(&minx[c], mnx);
+                atomicMax(&maxx[c], mxx);
+                atomicMin(&miny[c], mny);
+                atomicMax(&maxy[c], mxy);
+                atomicMax(&maxtext[c], mt);
             }
         }
-        if (labels_out != nullptr) labels_out[i] = id;
     }
 }
 
