@@ -66,7 +66,16 @@ struct Header {
     size_t coef_elems = 0, plane_bytes = 0;
 };
 
-void build_table(const uint8_t* bits /* [16] */, const uint8_t* vals, int count, HuffTab* t) {
+// Returns false for a table whose code lengths over-subscribe the code space (a corrupt DHT segment).
+bool build_table(const uint8_t* bits /* [16] */, const uint8_t* vals, int count, HuffTab* t) {
+    {
+        int32_t code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            code += bits[l - 1];
+            if (code > (1 << l)) return false;
+            code <<= 1;
+        }
+    }
     t->present = true;
     memset(t->vals, 0, sizeof(t->vals));
     memcpy(t->vals, vals, (size_t)count);
@@ -101,6 +110,7 @@ void build_table(const uint8_t* bits /* [16] */, const uint8_t* vals, int count,
         const int val = v >= (1 << (mag - 1)) ? v : v - (1 << mag) + 1;
         t->fast[i] = (int32_t)(((uint32_t)(uint16_t)(int16_t)val << 16) | (uint32_t)(run << 8) | (uint32_t)(len + mag));
     }
+    return true;
 }
 
 int exif_orientation(const uint8_t* t, size_t n) {
@@ -179,7 +189,7 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
                 int cnt = 0;
                 for (int k = 0; k < 16; ++k) cnt += s[i + 1 + k];
                 if (tc > 1 || th > 3 || cnt > 256 || i + 17 + cnt > sl) return bad("bad DHT segment");
-                build_table(s + i + 1, s + i + 17, cnt, tc ? &hd->ac[th] : &hd->dc[th]);
+                if (!build_table(s + i + 1, s + i + 17, cnt, tc ? &hd->ac[th] : &hd->dc[th])) return bad("bad Huffman table");
                 i += 17 + (size_t)cnt;
             }
         } else if (m == 0xDD) {
@@ -502,7 +512,7 @@ bool decode_multiscan(const Header& hd, int16_t* coef, std::string* err) {
                 int cnt = 0;
                 for (int k = 0; k < 16; ++k) cnt += s[i + 1 + k];
                 if (tc > 1 || th > 3 || cnt > 256 || i + 17 + cnt > sl) return bad("bad DHT segment");
-                build_table(s + i + 1, s + i + 17, cnt, tc ? &ac[th] : &dc[th]);
+                if (!build_table(s + i + 1, s + i + 17, cnt, tc ? &ac[th] : &dc[th])) return bad("bad Huffman table");
                 i += 17 + (size_t)cnt;
             }
         } else if (m == 0xDD) {

@@ -215,3 +215,30 @@ def test_multiscan_decoder_equals_single_scan_decoder_on_baseline_files():
         a, _ = jpeg_ref.decode_coefficients(jpeg_ref.parse(data))
         b, _ = jpeg_ref.decode_scans(jpeg_ref.parse_scans(data))
         assert all(np.array_equal(x, y) for x, y in zip(a, b)), name
+
+
+def test_corrupt_huffman_table_is_refused():
+    """A DHT segment whose code lengths over-subscribe the code space (found by the ASan fuzz harness, tools/fuzz_jpeg.cu)
+    must be refused, not turned into look-up tables."""
+    from lightly_ocr_b200 import bridge
+    img = np.random.default_rng(0).integers(0, 256, (16, 16, 3), dtype=np.uint8)
+    data = bytearray(cv2.imencode(".jpg", img)[1].tobytes())
+    p = data.index(b"\xff\xc4")
+    assert data[p + 5] == 0 and data[p + 7] >= 3     # standard luminance DC table: no 1-bit code, five 3-bit codes
+    data[p + 5] = 3            # three codes of length 1 (the code space has two) ...
+    data[p + 7] -= 3           # ... with the symbol count of the segment unchanged
+    with pytest.raises(bridge.LocrError, match="Huffman table"):
+        bridge.jpeg_info(bytes(data))
+    # random corruption never crashes the host decoder: every outcome is a decoded image or a LocrError
+    rng = np.random.default_rng(1)
+    good = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()
+    for _ in range(2000):
+        d = bytearray(good)
+        for _ in range(int(rng.integers(1, 5))):
+            d[int(rng.integers(2, len(d)))] = int(rng.integers(0, 256))
+        try:
+            h, w, _ = bridge.jpeg_info(bytes(d))
+            if h * w <= 1 << 20:
+                bridge.jpeg_coefficients(bytes(d))
+        except bridge.LocrError:
+            pass
