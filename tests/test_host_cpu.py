@@ -128,6 +128,12 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
                     eos.append(1)
             return per_image, dict(text=text, conf=np.array(conf, np.float32), has_eos=np.array(eos, np.int32))
 
+        def ocr_encoded(self, blobs):
+            # the GPU JPEG route: stand-in decodes with OpenCV and reports the route taken
+            self.encoded_calls = getattr(self, "encoded_calls", 0) + 1
+            per_image, out = self.ocr([cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in blobs])
+            return per_image, out, [(0, 0)] * len(blobs)
+
         def close(self):
             pass
 
@@ -157,4 +163,16 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
     with pytest.raises(ValueError):
         m.predict(str(d / "missing.png"))
     assert m.predict(paths[0]) == [["h100k0"]]
+    # JPEG uploads stay encoded and take the GPU-decode route (runner.ocr_encoded); other formats go through OpenCV
+    jp = str(d / "u.jpg")
+    cv2.imwrite(jp, np.full((300, 50, 3), 255, np.uint8))
+    assert m.encoded_batches == 0
+    assert m.predict(jp) == [["h300k0"], ["h300k2"]]
+    assert m.encoded_batches == 1 and m.runner.encoded_calls == 1
+    assert m.predict(paths[2]) == [["h300k0"], ["h300k2"]] and m.encoded_batches == 1
+    bad = str(d / "broken.jpg")
+    with open(bad, "wb") as f:
+        f.write(open(jp, "rb").read()[:40])          # truncated header: neither reader accepts it
+    with pytest.raises(ValueError):
+        m.predict(bad)
     m.close()
