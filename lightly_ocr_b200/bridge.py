@@ -435,7 +435,7 @@ class OcrRunner(Pipeline):
         self._cap = 0
 
     def _buffers(self, n):
-        cap = 1024 * n
+        cap = 4096 * n          # the detector keeps up to 4096 boxes per image (pipeline.cu)
         if cap > self._cap:
             self._rects = np.empty((cap, 4), np.int32)
             self._counts = np.zeros(max(n, 1), np.int32)
@@ -490,6 +490,16 @@ class OcrRunner(Pipeline):
         rects, counts = self._buffers(n)
         _check(self.L.locr_detect_resident(self.h, self._cap, _fptr(rects), None, _fptr(counts), None), self.h)
         return self._sort_and_recognize(n, rects, counts, want_logits)
+
+    def detect_resident(self, n):
+        """Detection only (CRAFT forward + boxes) on the n images left resident in HBM: rects per image."""
+        rects, counts = self._buffers(n)
+        _check(self.L.locr_detect_resident(self.h, self._cap, _fptr(rects), None, _fptr(counts), None), self.h)
+        out, base = [], 0
+        for i in range(n):
+            out.append(rects[base:base + int(counts[i])].copy())
+            base += int(counts[i])
+        return out
 
     def timer_start(self):
         _check(self.L.locr_timer_start(self.h), self.h)

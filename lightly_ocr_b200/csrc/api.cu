@@ -72,8 +72,10 @@ LOCR_API int locr_finalize(locr_handle* h, int model) {
 LOCR_API int64_t locr_launch_count(const locr_handle* h) { return h ? h->launches : 0; }
 
 LOCR_API const char* locr_last_error(const locr_handle* h) {
-    if (h != nullptr && !h->err.empty()) return h->err.c_str();
-    return tls_error().c_str();
+    // Every failure path (with or without a handle) records its text for the calling thread; the handle's copy only
+    // serves a caller that asks from another thread than the one that made the failing call.
+    if (!tls_error().empty()) return tls_error().c_str();
+    return h != nullptr ? h->err.c_str() : "";
 }
 
 LOCR_API int locr_timer_start(locr_handle* h) {
@@ -153,6 +155,7 @@ LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, 
     LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
     const int H = (img_h + 31) / 32 * 32, W = (img_w + 31) / 32 * 32;
     const size_t nbytes = (size_t)B * img_h * img_w * 3;
+    h->resident.clear();   // the image buffer is about to be overwritten (and possibly moved)
     uint8_t* d = (uint8_t*)engine_buffer(h, "images", nbytes);
     if (!d) return h->fail(LOCR_ERR_CUDA, "allocation failed");
     LOCR_CUDA_OK(cudaMemcpyAsync(d, bgr, nbytes, cudaMemcpyHostToDevice, h->stream));

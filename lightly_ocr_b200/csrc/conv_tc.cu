@@ -104,14 +104,14 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     return t;
 }
 
+// Round-to-nearest conversion of two fp32 values to a packed 16-bit pair (a in the low half).  Saturating
+// (F2FP.SATFINITE, same cost as the plain conversion): an activation beyond the fp16 range becomes +-65504 instead of
+// an infinity that would turn into NaN in the next layer.
 __device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
-    if (is_f16) {
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
-    } else {
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
+    uint32_t r;
+    if (is_f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 // element-wise max of two packed 16-bit pairs
 __device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b, int is_f16) {

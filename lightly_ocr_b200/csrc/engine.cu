@@ -260,6 +260,17 @@ void* engine_buffer(locr_handle* h, const std::string& name, size_t bytes) {
     return e.first;
 }
 
+void engine_release(locr_handle* h, const std::string& name) {
+    auto it = h->buffers.find(name);
+    if (it == h->buffers.end()) return;
+    if (it->second.first != nullptr) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(it->second.first);
+    }
+    h->buffers.erase(it);
+    h->zeroed.erase(name);
+}
+
 // ------------------------------------------------------------------------------------------------ CRAFT
 static const char* kCraftBn[][2] = {
     {"basenet.slice1.3", "basenet.slice1.4"},   {"basenet.slice1.7", "basenet.slice1.8"},

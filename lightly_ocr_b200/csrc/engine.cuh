@@ -112,5 +112,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
 
 // Named activation buffer (device), at least `bytes` large; contents are undefined after growth.
 void* engine_buffer(locr_handle* h, const std::string& name, size_t bytes);
+// Frees a named buffer (it is re-created on next use).
+void engine_release(locr_handle* h, const std::string& name);
 
 }  // namespace locr

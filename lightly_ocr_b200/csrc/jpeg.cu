@@ -12,6 +12,8 @@
 // is data-parallel runs on the GPU and the decoded image never visits the host.
 #include "jpeg.cuh"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -132,6 +134,16 @@ int exif_orientation(const uint8_t* t, size_t n) {
     return 1;
 }
 
+size_t max_image_pixels() {
+    static size_t v = 0;
+    if (v == 0) {
+        const char* e = getenv("LOCR_MAX_IMAGE_PIXELS");
+        v = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        if (v == 0) v = (size_t)1 << 30;     // cv2.imread refuses larger images (CV_IO_MAX_IMAGE_PIXELS)
+    }
+    return v;
+}
+
 // Marker segments up to the first SOS.  Returns false with a reason on anything this decoder does not cover.
 bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
     auto bad = [&](const char* m) { *err = std::string("JPEG: ") + m; return false; };
@@ -142,6 +154,8 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
     struct Frame { int id, h, v, tq; } frame[3];
     int nframe = 0;
     bool have_frame = false;
+    bool saw_jfif = false;
+    int adobe_transform = -1;      // APP14 comes BEFORE the frame header: remembered here, judged at the first scan
     for (;;) {
         if (pos + 4 > n) return bad("truncated file");
         if (d[pos] != 0xFF) return bad("marker expected");
@@ -197,10 +211,19 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
             hd->restart_interval = (s[0] << 8) | s[1];
         } else if (m == 0xE1 && sl > 6 && memcmp(s, "Exif\0\0", 6) == 0) {
             hd->orientation = exif_orientation(s + 6, sl - 6);
+        } else if (m == 0xE0 && sl >= 5 && memcmp(s, "JFIF\0", 5) == 0) {
+            saw_jfif = true;
         } else if (m == 0xEE && sl >= 12 && memcmp(s, "Adobe", 5) == 0) {
-            if (nframe == 3 && s[11] == 0) return bad("Adobe RGB (untransformed) files are not supported");
+            adobe_transform = s[11];
         } else if (m == 0xDA) {
             if (!have_frame) return bad("SOS before SOF");
+            if (nframe == 3 && !saw_jfif) {
+                // libjpeg's colour-space guess (jdapimin.c default_decompress_parms): JFIF implies YCbCr; otherwise an
+                // Adobe marker with transform 0, or component ids 'R','G','B' without any marker, mean untransformed RGB
+                const bool rgb_ids = frame[0].id == 'R' && frame[1].id == 'G' && frame[2].id == 'B';
+                if (adobe_transform == 0 || (adobe_transform < 0 && rgb_ids))
+                    return bad("untransformed RGB files (Adobe transform 0 / component ids R,G,B) are not supported");
+            }
             const int ns = sl >= 1 ? s[0] : 0;
             if (ns < 1 || ns > nframe || sl < 4 + 2 * (size_t)ns) return bad("bad SOS segment");
             hd->ncomp = nframe;
@@ -227,6 +250,8 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
         }
     }
     if (hd->H <= 0 || hd->W <= 0) return bad("empty image");
+    if ((size_t)hd->H * (size_t)hd->W > max_image_pixels())
+        return bad("image larger than the pixel limit (OpenCV's CV_IO_MAX_IMAGE_PIXELS, 2^30; LOCR_MAX_IMAGE_PIXELS)");
     if (hd->orientation < 1 || hd->orientation > 8) hd->orientation = 1;   // OpenCV leaves other values alone
     hd->hmax = hd->vmax = 1;
     for (int k = 0; k < hd->ncomp; ++k) {
@@ -251,6 +276,10 @@ bool parse(const uint8_t* d, size_t n, Header* hd, std::string* err) {
     }
     hd->coef_elems = co;
     hd->plane_bytes = po;
+    // Every coded block costs at least one bit in every scan that visits it, so a file whose entropy-coded part holds
+    // fewer bits than it declares blocks is truncated: refuse it HERE, before any buffer is sized from the header
+    // (a 200-byte file may declare 65535 x 65535 pixels).
+    if ((size_t)hd->scan_len * 8 < co / 64) return bad("premature end of the entropy-coded data");
     return true;
 }
 
@@ -763,6 +792,7 @@ struct PinnedBuf {
     void* p = nullptr;
     size_t cap = 0;
     ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     void* get(size_t n) {
         if (n <= cap) return p;
         if (p) cudaFreeHost(p);
@@ -897,6 +927,13 @@ int jpeg_decode_to_device(locr_handle* h, const uint8_t* const* blobs, const int
     LOCR_CUDA_OK(cudaGetLastError());
     // the pinned coefficient buffer is reused by the next call of this thread: wait until the copy has left it
     LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    // the scratch buffers only ever grow: hand the memory of an unusually large request back instead of keeping
+    // gigabytes pinned in a serving process
+    if (coef_total * 2 > ((size_t)1 << 30)) {
+        host_coef.release();
+        engine_release(h, "jpeg.coef");
+        engine_release(h, "jpeg.planes");
+    }
     return LOCR_OK;
 }
 

@@ -12,9 +12,12 @@ __device__ __forceinline__ float act2f(uint16_t u, int f16) {
     if (f16) return __half2float(__ushort_as_half(u));
     return __bfloat162float(__ushort_as_bfloat16(u));
 }
+// saturating (F2FP.SATFINITE): beyond the fp16 range a value becomes +-65504, never an infinity
 __device__ __forceinline__ uint16_t f2act(float v, int f16) {
-    if (f16) return __half_as_ushort(__float2half_rn(v));
-    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    uint16_t r;
+    if (f16) asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    else asm("cvt.rn.satfinite.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return r;
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int f16) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};

@@ -222,6 +222,7 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
         img_off[i] = total_bytes;
         total_bytes += (size_t)heights[i] * widths[i] * 3;
     }
+    h->resident.clear();   // stale after this point: the buffer may move and is overwritten
     uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
     if (!d_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
     // Images that already live in pinned (page-locked) host memory with packed rows are copied straight from the
@@ -275,6 +276,7 @@ static int decode_resident(locr_handle* h, const uint8_t* const* jpeg, const int
         img_off[i] = total_bytes;
         total_bytes += (size_t)hh[i] * ww[i] * 3;
     }
+    h->resident.clear();   // stale after this point: the buffer may move and is overwritten
     uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
     if (!d_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
     std::vector<uint8_t*> outs(n);
@@ -437,6 +439,7 @@ LOCR_API int locr_debug_postproc(locr_handle* h, const float* score, int B, int 
 LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw) {
     if (h == nullptr || src == nullptr || dst == nullptr) return fail(LOCR_ERR_INVALID, "bad argument");
     LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    h->resident.clear();   // the image buffer is about to be overwritten (and possibly moved)
     uint8_t* d_s = (uint8_t*)engine_buffer(h, "images", (size_t)sh * sw * 3);
     uint8_t* d_d = (uint8_t*)engine_buffer(h, "resized", (size_t)dh * dw * 3);
     if (!d_s || !d_d) return h->fail(LOCR_ERR_CUDA, "allocation failed");

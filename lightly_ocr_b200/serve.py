@@ -52,6 +52,7 @@ class serveModel:
         self.device_id = device_id
         self.batches = []               # sizes of the batches served so far (observability / tests)
         self.encoded_batches = 0        # batches that went through the GPU JPEG decoder without touching host pixels
+        self.retried_batches = 0        # batches whose call failed and whose members were then served one at a time
         self.loadModel()
         self._q = queue.Queue()
         self._stop = False
@@ -133,7 +134,7 @@ class serveModel:
                 return
             except bridge.LocrError:
                 pass
-        r.image = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        r.image = cv2.imread(r.path)       # not imdecode: only the file reader salvages a truncated JPEG scan
         if r.image is None:
             raise ValueError("cv2.imread could not read %r" % (r.path,))
 
@@ -149,23 +150,47 @@ class serveModel:
         if not good:
             return
         self.batches.append(len(good))
+        self._serve_group(good)
+
+    def _run(self, group):
+        """One detect + recognise pass over the requests of `group`: (sorted rects per image, recognition outputs)."""
+        if all(r.blob is not None for r in group) and hasattr(self.runner, "ocr_encoded"):
+            self.encoded_batches += 1
+            per_image, out, _ = self.runner.ocr_encoded([r.blob for r in group])
+            return per_image, out
+        for r in group:                                # mixed batch: the JPEG members are decoded on the GPU as well
+            if r.image is None:
+                r.image = (self.runner.imdecode(r.blob) if hasattr(self.runner, "imdecode") else
+                           cv2.imdecode(np.frombuffer(r.blob, np.uint8), cv2.IMREAD_COLOR))
+        return self.runner.ocr([r.image for r in group])
+
+    def _serve_group(self, group):
+        """Failures stay with the request that caused them: when a batched call fails (a JPEG whose scan is truncated,
+        an image the detector refuses, more boxes than the result buffer holds ...) its members are retried one at a
+        time, and a single JPEG that liblocr refuses is handed to OpenCV like any other format - cv2.imread returns a
+        partly grey image for a truncated scan and the reference carries on with it (pipeline.py:68)."""
         try:
-            if all(r.blob is not None for r in good) and hasattr(self.runner, "ocr_encoded"):
-                self.encoded_batches += 1
-                per_image, out, _ = self.runner.ocr_encoded([r.blob for r in good])
-            else:
-                for r in good:                         # mixed batch: the JPEG members are decoded on the GPU as well
-                    if r.image is None:
-                        r.image = (self.runner.imdecode(r.blob) if hasattr(self.runner, "imdecode") else
-                                   cv2.imdecode(np.frombuffer(r.blob, np.uint8), cv2.IMREAD_COLOR))
-                per_image, out = self.runner.ocr([r.image for r in good])
-        except Exception as e:                         # noqa: BLE001 - the whole batch failed (e.g. CUDA error)
-            for r in good:
-                r.error = e
-                r.done.set()
+            per_image, out = self._run(group)
+        except Exception as e:                         # noqa: BLE001
+            if len(group) > 1:
+                self.retried_batches += 1
+                for r in group:
+                    self._serve_group([r])
+                return
+            r = group[0]
+            if r.blob is not None and isinstance(e, bridge.LocrError):
+                img = cv2.imread(r.path)
+                r.blob = None
+                if img is not None:
+                    r.image = img
+                    self._serve_group([r])
+                    return
+                e = ValueError("cv2.imread could not read %r" % (r.path,))
+            r.error = e
+            r.done.set()
             return
         k = 0
-        for r, rects in zip(good, per_image):
+        for r, rects in zip(group, per_image):
             lo, k = k, k + len(rects)
             try:
                 r.result = self._filter(out, lo, k)

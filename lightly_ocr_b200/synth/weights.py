@@ -156,28 +156,41 @@ def craft_calibrated(seed=0, ink=True):
 def crnn_calibrated(seed=1, head="CTC", trained=True):
     """Raw recipe + committed calibration (calib_crnn_<head>.npz): BN statistics and the prediction head.
 
-    CTC, trained=True (default): the sequence read-out (SequenceModeling.*, Prediction.*; 2.9 M of the 48.9 M
-    parameters) additionally comes from calib_crnn_ctc_trained.npz - a short CTC training run with stock PyTorch on
-    synthetic receipts on top of the frozen seed-generated front end (tools/train_synth_crnn.py), stored as
-    fp16-representable values - so that the checkpoint decodes confident, input-dependent strings like a trained
-    recogniser instead of the near-tie arg-maxes of random weights."""
+    trained=True (default): the sequence read-out and the early convolutions additionally come from
+    calib_crnn_ctc_trained.npz - a short CTC training run with stock PyTorch on synthetic receipts on top of the
+    frozen seed-generated front end (tools/train_synth_crnn.py) with the CUDA path's 16-bit storage emulated in the
+    forward pass, stored as fp16-representable values - so that the checkpoint decodes confident, input-dependent
+    strings like a trained recogniser instead of the near-tie arg-maxes of random weights.
+    trained="fp32": the same recipe trained the plain way (fp32 forward pass, no rounding emulation, no injected
+    noise, tensors stored unrounded; calib_crnn_*_fp32.npz) - a recogniser that has never seen this repository's
+    rounding.
+    trained=False: the purely seed-generated checkpoint."""
     assert seed == 1
     sd = crnn_state_dict(seed, head=head)
     sd.update(_overrides("calib_crnn_%s.npz" % head.lower()))
     os_ = __import__("os")
-    path = os_.path.join(_HERE, "calib_crnn_ctc_trained.npz")
-    path_a = os_.path.join(_HERE, "calib_crnn_attention_trained.npz")
+    tag = "fp32" if trained == "fp32" else "trained"
+    path = os_.path.join(_HERE, "calib_crnn_ctc_%s.npz" % tag)
+    path_a = os_.path.join(_HERE, "calib_crnn_attention_%s.npz" % tag)
+    if trained == "fp32" and not (os_.path.exists(path) and (head == "CTC" or os_.path.exists(path_a))):
+        raise FileNotFoundError("fp32-trained synthetic checkpoint not generated yet (tools/train_synth_crnn.py)")
     if trained and os_.path.exists(path) and (head == "CTC" or os_.path.exists(path_a)):
-        for k, v in _overrides("calib_crnn_ctc_trained.npz").items():
+        for k, v in _overrides("calib_crnn_ctc_%s.npz" % tag).items():
             if head != "CTC" and k.startswith("Prediction."):
                 continue                      # the Attention model shares the trained front end and BiLSTMs only
             assert tuple(v.shape) == tuple(sd[k].shape), k
             sd[k] = v.float()
         if head != "CTC":
-            for k, v in _overrides("calib_crnn_attention_trained.npz").items():
+            for k, v in _overrides("calib_crnn_attention_%s.npz" % tag).items():
                 assert tuple(v.shape) == tuple(sd[k].shape), k
                 sd[k] = v.float()
     return sd
+
+
+def has_fp32_checkpoint(head="CTC"):
+    os_ = __import__("os")
+    names = ["calib_crnn_ctc_fp32.npz"] + ([] if head == "CTC" else ["calib_crnn_attention_fp32.npz"])
+    return all(os_.path.exists(os_.path.join(_HERE, n)) for n in names)
 
 
 def _pca_head(feats, ncls, gain):

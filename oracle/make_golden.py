@@ -2,13 +2,7 @@
 
 /root/reference is read-only and absent on the GPU box, so the live reference is imported here once, fed the
 synthetic checkpoints of oracle/weights.py, and its outputs are committed as small fixtures.  The reference sources
-are copied to a scratch directory under /tmp (never into the repository) because ocr/net.py derives its checkpoint
-directory from its own location (net.py:19) and needs a writable save_models/.
-
-Shims, none of them touching reference files:
-  * torchvision.models.vgg.model_urls   (removed from torchvision >= 0.13; vgg_bn.py:6,37 only rewrites a URL)
-  * stub modules lmdb, skimage, skimage.io  (imported by tools/dataset.py:7, tools/imgproc.py:3; unused on the path)
-  * the scratch copy's config.yml gets `prediction` / `num_classes` set per head
+are staged in a scratch directory under /tmp by oracle/ref_env.py (shims and staging are documented there).
 
 Usage:  python -m oracle.make_golden
 """
@@ -16,53 +10,18 @@ import contextlib
 import io
 import json
 import os
-import shutil
 import sys
-import types
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REF = "/root/reference/ocr"
-
-
-def load_reference(head, scratch):
-    """Import the reference's net / pipeline modules from a scratch copy configured for `head`."""
-    import yaml
-    dst = os.path.join(scratch, "ocr_" + head)
-    if os.path.exists(dst):
-        shutil.rmtree(dst)
-    shutil.copytree(REF, dst)
-    os.makedirs(os.path.join(dst, "test"), exist_ok=True)
-    cfg_path = os.path.join(dst, "config.yml")
-    cfg = yaml.safe_load(open(cfg_path))
-    cfg["prediction"] = head
-    cfg["num_classes"] = 37 if head == "CTC" else 38
-    yaml.safe_dump(cfg, open(cfg_path, "w"))
-    import torchvision.models.vgg as tv_vgg
-    if not hasattr(tv_vgg, "model_urls"):
-        tv_vgg.model_urls = {"vgg16_bn": "https://download.pytorch.org/models/vgg16_bn-6c64b313.pth"}
-    for name in ("lmdb", "skimage", "skimage.io"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["skimage"].io = sys.modules["skimage.io"]
-    for m in [k for k in sys.modules if k.split(".")[0] in ("net", "model", "modules", "tools", "pipeline")]:
-        del sys.modules[m]
-    sys.path.insert(0, dst)
-    cwd = os.getcwd()
-    os.chdir(dst)  # MODEL_PATH is relative to the cwd (os.path.relpath, net.py:19)
-    return dst, cwd
-
-
-def unload_reference(dst, cwd):
-    os.chdir(cwd)
-    sys.path.remove(dst)
 
 
 def main():
     sys.path.insert(0, ROOT)
-    from oracle import ocr_ref, receipts, weights
+    from oracle import ocr_ref, receipts, ref_env, weights
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLDEN, exist_ok=True)
     scratch = "/tmp/locr_ref_scratch"
@@ -75,13 +34,10 @@ def main():
     craft_calibrated = weights.craft_calibrated
 
     for head in ("CTC", "Attention"):
-        dst, cwd = load_reference(head, scratch)
-        try:
-            craft_sd = craft_calibrated(0, ink=True)
-            crnn_sd = weights.crnn_calibrated(1, head=head)
-            os.makedirs("save_models", exist_ok=True)
-            torch.save(craft_sd, os.path.join("save_models", "CRAFT.pth"))
-            torch.save(crnn_sd, os.path.join("save_models", "CRNN.pth"))
+        craft_sd = craft_calibrated(0, ink=True)
+        crnn_sd = weights.crnn_calibrated(1, head=head)
+        dst = ref_env.stage(head, craft_sd, crnn_sd, scratch)
+        with ref_env.imported(dst):
             import net as ref_net
             import pipeline as ref_pipeline
             import tools as ref_tools
@@ -173,8 +129,6 @@ def main():
             out["e2e_conf"] = np.array(confs, np.float32)
             np.savez_compressed(os.path.join(GOLDEN, "ref_%s.npz" % head.lower()), **out)
             print(head, {k: getattr(v, "shape", None) for k, v in out.items()})
-        finally:
-            unload_reference(dst, cwd)
 
 
 if __name__ == "__main__":

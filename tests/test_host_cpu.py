@@ -129,8 +129,12 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
             return per_image, dict(text=text, conf=np.array(conf, np.float32), has_eos=np.array(eos, np.int32))
 
         def ocr_encoded(self, blobs):
-            # the GPU JPEG route: stand-in decodes with OpenCV and reports the route taken
+            # the GPU JPEG route: stand-in decodes with OpenCV and reports the route taken; like liblocr it refuses
+            # a file whose entropy-coded data ends early (here: no EOI marker)
             self.encoded_calls = getattr(self, "encoded_calls", 0) + 1
+            from lightly_ocr_b200 import bridge as _b
+            if any(not b.rstrip(b"\0").endswith(b"\xff\xd9") for b in blobs):
+                raise _b.LocrError("liblocr error -2: JPEG: premature end of the entropy-coded data")
             per_image, out = self.ocr([cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in blobs])
             return per_image, out, [(0, 0)] * len(blobs)
 
@@ -175,4 +179,29 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
         f.write(open(jp, "rb").read()[:40])          # truncated header: neither reader accepts it
     with pytest.raises(ValueError):
         m.predict(bad)
+    # a JPEG with a valid header whose SCAN is truncated, batched with good uploads: the batched GPU call fails, the
+    # members are retried one at a time, the good ones are served, and the broken one falls back to OpenCV, which
+    # returns a partly grey image exactly like the reference's cv2.imread (the request succeeds)
+    big = str(d / "big.jpg")
+    rng = np.random.default_rng(0)
+    cv2.imwrite(big, rng.integers(0, 256, (300, 64, 3), dtype=np.uint8))
+    cut = str(d / "cut.jpg")
+    blob = open(big, "rb").read()
+    with open(cut, "wb") as f:
+        f.write(blob[:len(blob) * 2 // 3])
+    from lightly_ocr_b200 import bridge
+    assert bridge.jpeg_info(open(cut, "rb").read())[:2] == (300, 64)         # the header alone looks fine
+    m.max_wait = 0.5
+    before = m.retried_batches
+    trio = [jp, cut, big]
+    got3 = [None] * 3
+    th = [threading.Thread(target=lambda i=i: got3.__setitem__(i, serve.api_response(m, trio[i]))) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=30)
+    assert all(g is not None and g[1] == 200 for g in got3)
+    assert got3[0][0]["results"] == {0: ["h300k0"], 1: ["h300k2"]} and got3[2][0]["results"] == got3[0][0]["results"]
+    assert got3[1][0]["results"] == got3[0][0]["results"]                   # OpenCV's partly grey 300-row image
+    assert m.retried_batches == before + 1
     m.close()

@@ -117,6 +117,64 @@ def test_unsupported_files_fail_loudly():
         bridge.jpeg_coefficients(data[:len(data) // 3] + b"\xff\xd9")   # truncated inside a marker segment or the scan
 
 
+def _strip_app0(data):
+    """The file without its JFIF APP0 segment."""
+    i = data.index(b"\xff\xe0")
+    n = (data[i + 2] << 8) | data[i + 3]
+    return data[:i] + data[i + 2 + n:]
+
+
+def test_colour_space_guess_follows_libjpeg():
+    """libjpeg's default_decompress_parms: JFIF implies YCbCr; without JFIF an Adobe APP14 marker with transform 0, or
+    component ids 'R','G','B', mean untransformed RGB - which this reader refuses (the caller falls back to OpenCV)
+    instead of pushing RGB samples through the YCbCr conversion.  APP14 precedes the frame header."""
+    from lightly_ocr_b200 import bridge
+    img = np.random.default_rng(1).integers(0, 256, (24, 40, 3), dtype=np.uint8)
+    ok, good = cv2.imencode(".jpg", img)
+    data = good.tobytes()
+    assert bridge.jpeg_info(data) == (24, 40, 3)
+
+    def adobe(transform):
+        return b"\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00" + bytes([transform])
+
+    bare = _strip_app0(data)
+    assert bridge.jpeg_info(bare) == (24, 40, 3)                                     # ids 1,2,3, no marker: YCbCr
+    with pytest.raises(bridge.LocrError, match="RGB"):
+        bridge.jpeg_info(bare[:2] + adobe(0) + bare[2:])
+    assert bridge.jpeg_info(bare[:2] + adobe(1) + bare[2:]) == (24, 40, 3)           # Adobe YCbCr
+    assert bridge.jpeg_info(data[:2] + adobe(0) + data[2:]) == (24, 40, 3)           # JFIF wins over Adobe
+    # what OpenCV (libjpeg) makes of the same files: identical pixels whenever this reader accepts the file
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    for blob in (bare, bare[:2] + adobe(1) + bare[2:], data[:2] + adobe(0) + data[2:]):
+        assert np.array_equal(cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_COLOR), ref)
+        assert np.array_equal(jpeg_ref.imdecode(blob), ref)
+    rgb0 = cv2.imdecode(np.frombuffer(bare[:2] + adobe(0) + bare[2:], np.uint8), cv2.IMREAD_COLOR)
+    assert not np.array_equal(rgb0, ref)                                             # libjpeg really treats it as RGB
+    sof = bare.index(b"\xff\xc0")
+    ids = bytearray(bare)
+    ids[sof + 10], ids[sof + 13], ids[sof + 16] = ord("R"), ord("G"), ord("B")
+    sos = bytes(ids).index(b"\xff\xda")
+    ids[sos + 5], ids[sos + 7], ids[sos + 9] = ord("R"), ord("G"), ord("B")
+    with pytest.raises(bridge.LocrError, match="RGB"):
+        bridge.jpeg_info(bytes(ids))
+
+
+def test_header_cannot_demand_unbounded_memory():
+    """A tiny file may declare 65535 x 65535 pixels: it is refused from the header alone (pixel limit of cv2.imread,
+    and fewer entropy-coded bits than declared blocks), before any buffer is sized from it."""
+    from lightly_ocr_b200 import bridge
+    img = np.random.default_rng(2).integers(0, 256, (16, 16, 3), dtype=np.uint8)
+    ok, good = cv2.imencode(".jpg", img)
+    data = bytearray(good.tobytes())
+    sof = bytes(data).index(b"\xff\xc0")
+    data[sof + 5:sof + 9] = b"\xff\xff\xff\xff"
+    with pytest.raises(bridge.LocrError, match="pixel limit"):
+        bridge.jpeg_info(bytes(data))
+    data[sof + 5:sof + 9] = b"\x40\x00\x40\x00"            # 16384 x 16384: under the limit, but the scan is 200 bytes
+    with pytest.raises(bridge.LocrError, match="premature end"):
+        bridge.jpeg_info(bytes(data))
+
+
 def test_exif_orientation_like_cv2():
     """cv2.imread rotates by the EXIF orientation tag; the oracle does the same and the library reports the rotated size."""
     from lightly_ocr_b200 import bridge

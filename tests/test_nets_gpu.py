@@ -64,6 +64,34 @@ def test_craft_score_maps(oracle_mods, act):
     eng.close()
 
 
+def test_craft_score_maps_full_canvas(oracle_mods):
+    """BASELINE-size parity (reference ocr/net.py:100-107): a batch of eight 1280x960 receipts in one CRAFT pass, so the
+    M = 256 tiles, the haloed-patch path at full width and the multi-wave persistent grids all run; the score maps of
+    two of them are compared with the fp32 oracle (gate: 1e-2 max-abs), and the threshold flips are reported."""
+    ocr_ref, receipts, weights = oracle_mods
+    from lightly_ocr_b200 import bridge
+    sd = weights.craft_calibrated(0, ink=True)
+    eng = bridge.Engine(act_dtype=ACT["f16"])
+    eng.load_state_dict(bridge.MODEL_CRAFT, sd)
+    batch = np.stack([receipts.receipt(i) for i in range(8)])
+    got = eng.craft_scores(batch)
+    assert got.shape == (8, 640, 480, 2) and np.isfinite(got).all()
+    for i in (0, 5):
+        with torch.no_grad():
+            x, _, _ = ocr_ref.craft_preproc(batch[i])
+            ref = ocr_ref.craft_forward(sd, x)[0].numpy()
+        err = np.abs(got[i] - ref).max()
+        flips = int(((got[i] > 0.4) != (ref > 0.4)).sum() + ((got[i][..., 0] > 0.7) != (ref[..., 0] > 0.7)).sum())
+        print("receipt %d at 1280x960 (batch of 8): score max-abs err %.4g, range [%.3f, %.3f], threshold flips %d / %d"
+              % (i, err, ref.min(), ref.max(), flips, ref.size))
+        assert err < 1e-2
+        assert flips <= ref.size // 10000
+    # one canvas alone (B = 1: other tile shapes / fewer waves) gives the same maps as in the batch
+    alone = eng.craft_scores(batch[5:6])
+    assert np.array_equal(alone[0], got[5])
+    eng.close()
+
+
 @pytest.mark.parametrize("head", ["CTC", "Attention"])
 @pytest.mark.parametrize("act", ["f16", "bf16"])
 def test_crnn_logits_and_decode(oracle_mods, act, head):

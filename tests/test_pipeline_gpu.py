@@ -83,8 +83,14 @@ def test_dropin_ctc_end_to_end(tmp_path, eager):
     want = [v[0] for v in ref_res.values()]
     n = min(len(got), len(want))
     match = sum(g == w for g, w in zip(got, want)) / max(n, 1)
-    print("eager=%s boxes %d vs %d, sorted rects identical %s, string exact-match %.3f" %
-          (eager, len(got), len(want), same_rects, match))
+    # rects of the CUDA path vs the fp32 oracle's own detection (its own score maps): identical unless a score-map
+    # pixel sits within rounding distance of a threshold; every differing rect must be explained by such a flip
+    flips = int(((t > 0.4) != (info["text"] > 0.4)).sum() + ((l > 0.4) != (info["link"] > 0.4)).sum())
+    mine = {tuple(int(v) for v in r) for r in rects[0]}
+    theirs = {tuple(int(v) for v in r) for r in info["rects"]}
+    print("eager=%s boxes %d vs %d, sorted rects identical %s (threshold flips %d, rects differing %d), string "
+          "exact-match %.3f" % (eager, len(got), len(want), same_rects, flips, len(mine ^ theirs), match))
+    assert same_rects or 0 < len(mine ^ theirs) <= 2 * flips
     assert abs(len(got) - len(want)) <= 2
     if eager == "1":
         # the same receipt through the LIVE reference pipeline (pipeline.getText, recorded by oracle/make_golden.py)

@@ -10,6 +10,10 @@ still come from the seed.  The trained tensors are rounded to fp16-representable
 It is not product code: the product path loads whatever state dict the caller provides.
 
 Usage (GPU box): python tools/train_synth_crnn.py [n_receipts] [steps] -> gpurun_out/calib_crnn_ctc_trained.npz
+
+LOCR_TRAIN_MODE=fp32 trains a SECOND checkpoint the plain way - fp32 forward pass, no emulation of the CUDA path's
+16-bit storage, no injected noise, tensors saved unrounded - as `calib_crnn_{ctc,attention}_fp32.npz`: a recogniser that
+has never seen this repository's rounding, for the parity gates that must not depend on such conditioning.
 """
 import os
 import sys
@@ -29,6 +33,8 @@ ALPHABET = receipts.ALPHABET
 N_RECEIPTS = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
 SEED0 = 5000                                                 # training receipts: seeds 5000.. (tests use 0..255)
+PLAIN = os.environ.get("LOCR_TRAIN_MODE", "q16") == "fp32"   # plain fp32 training (no rounding emulation, no noise)
+TAG = "fp32" if PLAIN else "trained"
 
 
 def label_for(rect, words):
@@ -64,7 +70,7 @@ def collect(runner, n_receipts):
         if not srt:
             continue
         runner.recognize_boxes(idx, srt)
-        rect.append(runner.debug_read("rectified").astype(np.float16))
+        rect.append(runner.debug_read("rectified").astype(np.float32 if PLAIN else np.float16))
         labels.extend(lab)
     print("collected %d crops from %d receipts in %.1f s" % (len(labels), n_receipts, time.time() - t0), flush=True)
     return np.concatenate(rect), labels
@@ -191,7 +197,7 @@ def attn_tokens(ids):
 def train_attention():
     """Second stage: the attention decoder on top of the (already trained, frozen) front end + BiLSTMs."""
     torch.manual_seed(1)
-    base_sd = weights.crnn_calibrated(1, "CTC", trained=True)
+    base_sd = weights.crnn_calibrated(1, "CTC", trained="fp32" if PLAIN else True)
     runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
     runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
     runner.load_state_dict(bridge.MODEL_CRNN, base_sd)
@@ -201,7 +207,7 @@ def train_attention():
     dev = torch.device("cuda", 0)
     X = torch.from_numpy(rect).to(dev)
     front = Crnn(base_sd, False).to(dev)
-    tr = weights._overrides("calib_crnn_ctc_trained.npz")
+    tr = weights._overrides("calib_crnn_ctc_%s.npz" % TAG)
     rnn_sd = {0: {}, 1: {}}
     for k, v in tr.items():
         if k.startswith("SequenceModeling."):
@@ -217,8 +223,9 @@ def train_attention():
     ctx = []
     with torch.no_grad():
         for i in range(0, n, 512):
-            ctx.append(front(X[i:i + 512].float().unsqueeze(1), "q16+ctx").half())
-    Hc = torch.cat(ctx)                                           # [n, 26, 256] as the CUDA path stores them
+            c = front(X[i:i + 512].float().unsqueeze(1), "fp32+ctx" if PLAIN else "q16+ctx")
+            ctx.append(c if PLAIN else c.half())
+    Hc = torch.cat(ctx)                                           # [n, 26, 256] (q16: as the CUDA path stores them)
     del front, X
     tgt = torch.ones(n, 26, dtype=torch.long)                      # [s] everywhere after the text
     for i, s in enumerate(labels):
@@ -236,7 +243,8 @@ def train_attention():
     for step in range(STEPS):
         b = trn[torch.randint(0, len(trn), (bs,), device=dev)]
         Hb = Hc[b].float()
-        Hb = Hb + 0.01 * rms * torch.randn_like(Hb)
+        if not PLAIN:
+            Hb = Hb + 0.01 * rms * torch.randn_like(Hb)
         # teacher forcing with 20 % of the inputs replaced by the model's own previous guess (exposure to its errors)
         logits = dec(Hb, teacher=tgt[b])
         loss = F.cross_entropy(logits.reshape(-1, 38), tgt[b].reshape(-1))
@@ -263,13 +271,15 @@ def train_attention():
     m = {"i2h.weight": dec.i2h.weight, "h2h.weight": dec.h2h.weight, "h2h.bias": dec.h2h.bias,
          "score.weight": dec.score.weight, "rnn.weight_ih": dec.rnn.weight_ih, "rnn.weight_hh": dec.rnn.weight_hh,
          "rnn.bias_ih": dec.rnn.bias_ih, "rnn.bias_hh": dec.rnn.bias_hh}
+    keep = (lambda v: v.detach().cpu().float().numpy()) if PLAIN else (lambda v: v.detach().cpu().half().numpy())
     for k, v in m.items():
-        sd["Prediction.attention_cell." + k] = v.detach().cpu().half().numpy()      # fp16-representable
-    sd["Prediction.generator.weight"] = dec.generator.weight.detach().cpu().half().numpy()
-    sd["Prediction.generator.bias"] = dec.generator.bias.detach().cpu().half().numpy()
+        sd["Prediction.attention_cell." + k] = keep(v)                               # q16: fp16-representable
+    sd["Prediction.generator.weight"] = keep(dec.generator.weight)
+    sd["Prediction.generator.bias"] = keep(dec.generator.bias)
     os.makedirs("gpurun_out", exist_ok=True)
-    np.savez_compressed("gpurun_out/calib_crnn_attention_trained.npz", **sd)
-    print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize("gpurun_out/calib_crnn_attention_trained.npz") / 1e6))
+    out_path = "gpurun_out/calib_crnn_attention_%s.npz" % TAG
+    np.savez_compressed(out_path, **sd)
+    print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize(out_path) / 1e6))
 
 
 def decode(ids):
@@ -328,7 +338,7 @@ def main():
         model.train()
         b = trn[torch.randint(0, len(trn), (bs,), device=dev)]
         x = X[b].float().unsqueeze(1)
-        lp = model(x).log_softmax(2).permute(1, 0, 2)
+        lp = model(x, "fp32" if PLAIN else "q16").log_softmax(2).permute(1, 0, 2)
         loss = ctc(lp, tgt[b], torch.full((bs,), 26, dtype=torch.long, device=dev), tl[b])
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -337,7 +347,7 @@ def main():
         sched.step()
         if step % 250 == 0 or step == STEPS - 1:
             model.eval()
-            got = decode(predict(val, "q16").argmax(2).cpu().numpy())
+            got = decode(predict(val, "fp32" if PLAIN else "q16").argmax(2).cpu().numpy())
             acc = np.mean([g == labels[i] for g, i in zip(got, val.cpu().numpy())])
             print("step %5d loss %.4f val word acc %.4f (%.0f s)" % (step, float(loss.detach()), acc, time.time() - t0),
                   flush=True)
@@ -362,17 +372,20 @@ def main():
         q = model.P[name]
         if q.requires_grad:
             v = q.detach().cpu()
-            sd[k] = (v.half() if v.dim() == 4 else v).numpy()     # conv weights fp16-representable, BN affine fp32
+            # q16: conv weights fp16-representable, BN affine fp32; plain: everything exactly as trained
+            sd[k] = (v.half() if (v.dim() == 4 and not PLAIN) else v).numpy()
+    keep = (lambda v: v.detach().cpu().float().numpy()) if PLAIN else (lambda v: v.detach().cpu().half().numpy())
     for li, (rnn, lin) in enumerate(((model.rnn0, model.lin0), (model.rnn1, model.lin1))):
         for k, v in rnn.state_dict().items():
-            sd["SequenceModeling.%d.rnn.%s" % (li, k)] = v.detach().cpu().half().numpy()
-        sd["SequenceModeling.%d.linear.weight" % li] = lin.weight.detach().cpu().half().numpy()
-        sd["SequenceModeling.%d.linear.bias" % li] = lin.bias.detach().cpu().half().numpy()
-    sd["Prediction.weight"] = model.pred.weight.detach().cpu().half().numpy()
-    sd["Prediction.bias"] = model.pred.bias.detach().cpu().half().numpy()
+            sd["SequenceModeling.%d.rnn.%s" % (li, k)] = keep(v)
+        sd["SequenceModeling.%d.linear.weight" % li] = keep(lin.weight)
+        sd["SequenceModeling.%d.linear.bias" % li] = keep(lin.bias)
+    sd["Prediction.weight"] = keep(model.pred.weight)
+    sd["Prediction.bias"] = keep(model.pred.bias)
     os.makedirs("gpurun_out", exist_ok=True)
-    np.savez_compressed("gpurun_out/calib_crnn_ctc_trained.npz", **sd)
-    print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize("gpurun_out/calib_crnn_ctc_trained.npz") / 1e6))
+    out_path = "gpurun_out/calib_crnn_ctc_%s.npz" % TAG
+    np.savez_compressed(out_path, **sd)
+    print("saved %d tensors, %.1f MB" % (len(sd), os.path.getsize(out_path) / 1e6))
 
 
 if __name__ == "__main__":
