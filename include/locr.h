@@ -113,6 +113,16 @@ LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* 
  * ExifTransform; sizes are those of the rotated image).  Arithmetic-coded, lossless, 12-bit, CMYK and truncated files
  * return LOCR_ERR_INVALID (the caller falls back to its own reader and hands the pixels to locr_detect). */
 LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components);
+/* PNG files (the reference server accepts .png uploads, ocr/server.py:11; cv2.imread at pipeline.py:68 hands them to
+ * libpng): locr_imdecode / locr_detect_encoded take JPEG and PNG files alike, told apart by their signature.  Byte-exact
+ * with cv2.imdecode(IMREAD_COLOR): every colour type and bit depth (gray / RGB / palette / alpha, 1-16 bit), both
+ * interlace methods; 16-bit samples -> high byte, alpha and tRNS dropped, gamma chunks ignored, as OpenCV asks of
+ * libpng.  zlib inflate runs on host threads, scanline un-filtering and sample conversion on the GPU.  Animated,
+ * truncated or CRC-damaged files return LOCR_ERR_INVALID (the caller falls back to its own reader).
+ * locr_image_info: header query for either format; *format (optional) receives LOCR_FORMAT_*. */
+enum { LOCR_FORMAT_JPEG = 0, LOCR_FORMAT_PNG = 1 };
+LOCR_API int locr_image_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components,
+                             int* format);
 /* One file -> packed uint8 [height][width][3] BGR in the caller's host buffer (capacity in bytes). */
 LOCR_API int locr_imdecode(locr_handle* h, const uint8_t* jpeg, int64_t nbytes, uint8_t* bgr, int64_t capacity,
                            int* height, int* width);
@@ -182,6 +192,9 @@ LOCR_API int locr_debug_resize(locr_handle* h, const uint8_t* src, int sh, int s
  * [component][block row][block col][64] quantised coefficients in natural order (NULL: geometry only), info[19] = H, W,
  * components, hmax, vmax, MCUs per row, MCU rows, then (h, v, blocks per row, block rows) per component. */
 LOCR_API int locr_test_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* out, int64_t capacity, int* info);
+/* Host half of the PNG reader alone (chunk walk, CRC, zlib inflate; no GPU): the filtered scanlines, pass after pass.
+ * out may be NULL to query *need (bytes) only. */
+LOCR_API int locr_test_png_scanlines(const uint8_t* data, int64_t nbytes, uint8_t* out, int64_t capacity, int64_t* need);
 
 /* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);

@@ -48,6 +48,11 @@ def lib():
         _lib.locr_jpeg_info.restype = C.c_int
         _lib.locr_jpeg_info.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(C.c_int)]
+        _lib.locr_image_info.restype = C.c_int
+        _lib.locr_image_info.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.locr_test_png_scanlines.restype = C.c_int
+        _lib.locr_test_png_scanlines.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     return _lib
 
 
@@ -67,6 +72,29 @@ def jpeg_info(data):
     h, w, c = C.c_int(), C.c_int(), C.c_int()
     _check(lib().locr_jpeg_info(data, len(data), C.byref(h), C.byref(w), C.byref(c)))
     return h.value, w.value, c.value
+
+
+FORMAT_JPEG, FORMAT_PNG = 0, 1
+
+
+def image_info(data):
+    """(height, width, components, format) of a JPEG or PNG file from its header (host only); raises LocrError for
+    files outside the subset the GPU ingest covers."""
+    data = bytes(data)
+    h, w, c, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().locr_image_info(data, len(data), C.byref(h), C.byref(w), C.byref(c), C.byref(f)))
+    return h.value, w.value, c.value, f.value
+
+
+def png_scanlines(data):
+    """Host half of the PNG reader (chunk walk, CRC, zlib inflate; no GPU): the filtered scanlines as uint8 [n]."""
+    data = bytes(data)
+    need = C.c_int64()
+    L = lib()
+    _check(L.locr_test_png_scanlines(data, len(data), None, 0, C.byref(need)))
+    out = np.zeros(need.value, np.uint8)
+    _check(L.locr_test_png_scanlines(data, len(data), _fptr(out), out.size, C.byref(need)))
+    return out
 
 
 def jpeg_coefficients(data):
@@ -365,18 +393,18 @@ class Pipeline(Engine):
         return o
 
     def imdecode(self, data):
-        """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a baseline JPEG file, decoded on the GPU
-        (Huffman on the host, the rest in CUDA): uint8 [H][W][3] BGR.  Raises LocrError for files outside the covered
-        subset (arithmetic-coded, CMYK, truncated ...)."""
+        """cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR) for a JPEG or PNG file, decoded on the GPU
+        (entropy decoding / inflate on the host, the rest in CUDA): uint8 [H][W][3] BGR.  Raises LocrError for files
+        outside the covered subset (arithmetic-coded or CMYK JPEG, animated PNG, truncated files ...)."""
         data = bytes(data)
-        h, w, _ = jpeg_info(data)
+        h, w, _, _ = image_info(data)
         out = np.empty((h, w, 3), np.uint8)
         hh, ww = C.c_int(), C.c_int()
         _check(self.L.locr_imdecode(self.h, data, len(data), _fptr(out), out.nbytes, C.byref(hh), C.byref(ww)), self.h)
         return out
 
     def imread(self, path):
-        """cv2.imread(path) for baseline JPEG files (reference ocr/pipeline.py:68)."""
+        """cv2.imread(path) for JPEG and PNG files (reference ocr/pipeline.py:68)."""
         with open(path, "rb") as f:
             return self.imdecode(f.read())
 

@@ -7,6 +7,7 @@
 #include "engine.cuh"
 #include "imgops.cuh"
 #include "jpeg.cuh"
+#include "png.cuh"
 #include "postproc.cuh"
 
 using namespace locr;
@@ -252,7 +253,7 @@ LOCR_API int locr_detect(locr_handle* h, const uint8_t* const* bgr, const int* h
     return detect_resident(h, max_boxes_total, rects, boxes, box_counts, score_maps);
 }
 
-/* cv2.imread / cv2.imdecode(IMREAD_COLOR) of one baseline JPEG file (pipeline.py:68): header only. */
+/* cv2.imread / cv2.imdecode(IMREAD_COLOR) of one JPEG file (pipeline.py:68): header only. */
 LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components) {
     if (data == nullptr || nbytes <= 0 || height == nullptr || width == nullptr || components == nullptr)
         return fail(LOCR_ERR_INVALID, "locr_jpeg_info: bad argument");
@@ -261,17 +262,33 @@ LOCR_API int locr_jpeg_info(const uint8_t* data, int64_t nbytes, int* height, in
     return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
 }
 
-/* Decodes n JPEG files on the GPU and leaves the BGR images resident (packed) like locr_detect does. */
-static int decode_resident(locr_handle* h, const uint8_t* const* jpeg, const int64_t* nbytes, int n, int* heights,
+/* The same for any format the GPU ingest covers (JPEG or PNG, told apart by the file signature). */
+LOCR_API int locr_image_info(const uint8_t* data, int64_t nbytes, int* height, int* width, int* components,
+                             int* format) {
+    if (data == nullptr || nbytes <= 0 || height == nullptr || width == nullptr || components == nullptr)
+        return fail(LOCR_ERR_INVALID, "locr_image_info: bad argument");
+    std::string err;
+    const bool png = png_is_png(data, (size_t)nbytes);
+    const int rc = png ? png_probe(data, (size_t)nbytes, height, width, components, &err)
+                       : jpeg_probe(data, (size_t)nbytes, height, width, components, &err);
+    if (rc == LOCR_OK && format) *format = png ? LOCR_FORMAT_PNG : LOCR_FORMAT_JPEG;
+    return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
+}
+
+/* Decodes n encoded files (JPEG or PNG) on the GPU and leaves the BGR images resident (packed) like locr_detect does. */
+static int decode_resident(locr_handle* h, const uint8_t* const* blob, const int64_t* nbytes, int n, int* heights,
                            int* widths) {
     std::vector<size_t> img_off(n);
     std::vector<int> hh(n), ww(n);
+    std::vector<char> is_png(n);
     size_t total_bytes = 0;
     for (int i = 0; i < n; ++i) {
         int comps = 0;
         std::string err;
-        if (jpeg[i] == nullptr || nbytes[i] <= 0) return h->fail(LOCR_ERR_INVALID, "JPEG: empty input");
-        const int rc = jpeg_probe(jpeg[i], (size_t)nbytes[i], &hh[i], &ww[i], &comps, &err);
+        if (blob[i] == nullptr || nbytes[i] <= 0) return h->fail(LOCR_ERR_INVALID, "imdecode: empty input");
+        is_png[i] = png_is_png(blob[i], (size_t)nbytes[i]) ? 1 : 0;
+        const int rc = is_png[i] ? png_probe(blob[i], (size_t)nbytes[i], &hh[i], &ww[i], &comps, &err)
+                                 : jpeg_probe(blob[i], (size_t)nbytes[i], &hh[i], &ww[i], &comps, &err);
         if (rc != LOCR_OK) return h->fail(rc, err);
         img_off[i] = total_bytes;
         total_bytes += (size_t)hh[i] * ww[i] * 3;
@@ -279,11 +296,21 @@ static int decode_resident(locr_handle* h, const uint8_t* const* jpeg, const int
     h->resident.clear();   // stale after this point: the buffer may move and is overwritten
     uint8_t* d_img = (uint8_t*)engine_buffer(h, "images", total_bytes);
     if (!d_img) return h->fail(LOCR_ERR_CUDA, "image buffer allocation failed");
-    std::vector<uint8_t*> outs(n);
-    for (int i = 0; i < n; ++i) outs[i] = d_img + img_off[i];
-    const int rc = jpeg_decode_to_device(h, jpeg, nbytes, n, outs.data());
-    if (rc != LOCR_OK) return rc;
-    h->resident.clear();
+    for (int kind = 0; kind < 2; ++kind) {
+        std::vector<const uint8_t*> bl;
+        std::vector<int64_t> nb;
+        std::vector<uint8_t*> outs;
+        for (int i = 0; i < n; ++i)
+            if (is_png[i] == kind) {
+                bl.push_back(blob[i]);
+                nb.push_back(nbytes[i]);
+                outs.push_back(d_img + img_off[i]);
+            }
+        if (bl.empty()) continue;
+        const int rc = kind ? png_decode_to_device(h, bl.data(), nb.data(), (int)bl.size(), outs.data())
+                            : jpeg_decode_to_device(h, bl.data(), nb.data(), (int)bl.size(), outs.data());
+        if (rc != LOCR_OK) return rc;
+    }
     for (int i = 0; i < n; ++i) {
         h->resident.push_back({d_img + img_off[i], hh[i], ww[i]});
         if (heights) heights[i] = hh[i];

@@ -5,6 +5,7 @@
 
 #include "conv_tc.cuh"
 #include "jpeg.cuh"
+#include "png.cuh"
 #include "nn_kernels.cuh"
 #include "util.cuh"
 
@@ -182,6 +183,16 @@ LOCR_API int locr_test_jpeg_coefficients(const uint8_t* data, int64_t nbytes, in
     if (data == nullptr || nbytes <= 0 || info == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
     std::string err;
     const int rc = jpeg_host_coefficients(data, (size_t)nbytes, out, (size_t)(capacity < 0 ? 0 : capacity), info, &err);
+    return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
+}
+
+/* Host half of the PNG reader alone (no GPU): see png.cuh png_host_scanlines. */
+LOCR_API int locr_test_png_scanlines(const uint8_t* data, int64_t nbytes, uint8_t* out, int64_t capacity, int64_t* need) {
+    if (data == nullptr || nbytes <= 0) return fail(LOCR_ERR_INVALID, "null argument");
+    std::string err;
+    size_t nd = 0;
+    const int rc = png_host_scanlines(data, (size_t)nbytes, out, (size_t)(capacity < 0 ? 0 : capacity), &nd, &err);
+    if (need) *need = (int64_t)nd;
     return rc == LOCR_OK ? LOCR_OK : fail(rc, err);
 }
 

@@ -122,14 +122,15 @@ class serveModel:
 
     @staticmethod
     def _read(r):
-        """pipeline.py:68 `cv2.imread(path)`.  JPEG uploads (baseline, sequential or progressive Huffman files) stay encoded
-        (r.blob): liblocr decodes them on the GPU, bit-identical to OpenCV incl. the EXIF rotation (include/locr.h
-        locr_detect_encoded).  Everything else - PNG, arithmetic-coded or CMYK JPEG ... - is read by OpenCV itself."""
+        """pipeline.py:68 `cv2.imread(path)`.  JPEG uploads (baseline, sequential or progressive Huffman files) and PNG
+        uploads stay encoded (r.blob): liblocr decodes them on the GPU, bit-identical to OpenCV incl. the EXIF rotation
+        (include/locr.h locr_detect_encoded).  Files outside that subset - arithmetic-coded or CMYK JPEG, animated
+        PNG, damaged files ... - and other formats are read by OpenCV itself, exactly like the reference does."""
         with open(r.path, "rb") as f:
             data = f.read()
-        if data[:2] == b"\xff\xd8":
+        if data[:2] == b"\xff\xd8" or data[:8] == b"\x89PNG\r\n\x1a\n":
             try:
-                bridge.jpeg_info(data)
+                bridge.image_info(data)
                 r.blob = data
                 return
             except bridge.LocrError:

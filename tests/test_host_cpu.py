@@ -133,7 +133,7 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
             # a file whose entropy-coded data ends early (here: no EOI marker)
             self.encoded_calls = getattr(self, "encoded_calls", 0) + 1
             from lightly_ocr_b200 import bridge as _b
-            if any(not b.rstrip(b"\0").endswith(b"\xff\xd9") for b in blobs):
+            if any(b[:2] == b"\xff\xd8" and not b.rstrip(b"\0").endswith(b"\xff\xd9") for b in blobs):
                 raise _b.LocrError("liblocr error -2: JPEG: premature end of the entropy-coded data")
             per_image, out = self.ocr([cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in blobs])
             return per_image, out, [(0, 0)] * len(blobs)
@@ -150,7 +150,7 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
     m = serve.serveModel(config_file="config.yml", thresh=0.7, docker=True, max_batch=4, max_wait_ms=200)
     paths = []
     for i, h in enumerate((100, 200, 300, 400, 500, 600)):
-        p = str(d / ("u%d.png" % i))
+        p = str(d / ("u%d.bmp" % i))                     # a format outside the GPU ingest: read by OpenCV on the host
         cv2.imwrite(p, np.full((h, 50, 3), 255, np.uint8))
         paths.append(p)
     got = [None] * len(paths)
@@ -167,13 +167,16 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
     with pytest.raises(ValueError):
         m.predict(str(d / "missing.png"))
     assert m.predict(paths[0]) == [["h100k0"]]
-    # JPEG uploads stay encoded and take the GPU-decode route (runner.ocr_encoded); other formats go through OpenCV
+    # JPEG and PNG uploads stay encoded and take the GPU-decode route (runner.ocr_encoded); other formats go through OpenCV
     jp = str(d / "u.jpg")
     cv2.imwrite(jp, np.full((300, 50, 3), 255, np.uint8))
     assert m.encoded_batches == 0
     assert m.predict(jp) == [["h300k0"], ["h300k2"]]
     assert m.encoded_batches == 1 and m.runner.encoded_calls == 1
     assert m.predict(paths[2]) == [["h300k0"], ["h300k2"]] and m.encoded_batches == 1
+    pg = str(d / "u.png")
+    cv2.imwrite(pg, np.full((200, 50, 3), 255, np.uint8))
+    assert m.predict(pg) == [["h200k0"]] and m.encoded_batches == 2
     bad = str(d / "broken.jpg")
     with open(bad, "wb") as f:
         f.write(open(jp, "rb").read()[:40])          # truncated header: neither reader accepts it
