@@ -488,6 +488,10 @@ def main():
     ap.add_argument("--head", default=None, choices=["CTC", "Attention"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (one image at a time through net.py)")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
+                    help="arithmetic of the recogniser for the main legs (include/locr.h LOCR_PREC_*); the other mode is "
+                         "timed as an extra e2e leg (`other_precision`) unless --no-other-precision")
+    ap.add_argument("--no-other-precision", action="store_true")
     ap.add_argument("--jpeg", action="store_true",
                     help="extra leg: the same receipts handed over as JPEG files (q90, 4:2:0) through locr_detect_encoded; "
                          "adds an `e2e_jpeg` object to the JSON line (BASELINE's metric itself excludes the image decode)")
@@ -521,12 +525,17 @@ def main():
 
     from concurrent.futures import ThreadPoolExecutor
     craft_sd, crnn_sd = weights.craft_calibrated(0, ink=True), weights.crnn_calibrated(1, head)
-    runners = []
-    for _ in range(LANES):
-        r = bridge.OcrRunner(device_id=local_rank, act_dtype=bridge.ACT_F16, head=head)
-        r.load_state_dict(bridge.MODEL_CRAFT, craft_sd)
-        r.load_state_dict(bridge.MODEL_CRNN, crnn_sd)
-        runners.append(r)
+    def make_runners(precision):
+        out = []
+        for _ in range(LANES):
+            r = bridge.OcrRunner(device_id=local_rank, act_dtype=bridge.ACT_F16, head=head,
+                                 precision=bridge.PREC_EXACT if precision == "exact" else bridge.PREC_FAST)
+            r.load_state_dict(bridge.MODEL_CRAFT, craft_sd)
+            r.load_state_dict(bridge.MODEL_CRNN, crnn_sd)
+            out.append(r)
+        return out
+
+    runners = make_runners(args.precision)
     pool = make_receipts(rank, POOL)
     batches = [pool[i:i + PER_PASS] for i in range(0, POOL, PER_PASS)]
     ex = ThreadPoolExecutor(max_workers=LANES)
@@ -658,6 +667,35 @@ def main():
         total_crops, crops_e2e = int(t[0].item()), int(t[1].item())
     for r in runners:
         r.close()
+    # ---------------- the other arithmetic of the recogniser through the same e2e leg (host buffers in, results out)
+    other = None
+    if not args.no_other_precision:
+        other_name = "exact" if args.precision == "fast" else "fast"
+        runners = make_runners(other_name)
+        n_pass = max(args.steps // 2, 2) * PASSES
+        for w in range(3):
+            e2e_pass(w)
+        barrier()
+        for r in runners:
+            r.timer_start()
+        t0 = time.perf_counter()
+        oc = 0
+        for k in range(n_pass):
+            oc += e2e_pass(k)[0]
+        o_ms = max(r.timer_stop() for r in runners)
+        o_wall = time.perf_counter() - t0
+        barrier()
+        o_rows = per_rank(o_ms / 1e3, o_wall)
+        o_s = max(max(a, b) for a, b in o_rows)
+        if world > 1:
+            t = torch.tensor([oc], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            oc = int(t[0].item())
+        other = {"precision": other_name, "value": world * PER_PASS * n_pass / o_s, "unit": UNIT,
+                 "crops_per_sec": oc / o_s, "passes": n_pass,
+                 "leg": "e2e (host buffers in, host results out), same receipts and lanes as `e2e`"}
+        for r in runners:
+            r.close()
     runners = []
 
     if rank == 0:
@@ -669,6 +707,7 @@ def main():
             "metric": metric_name(head), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "precision": args.precision,
             "config": {"workload": "end-to-end CRAFT+CRNN(%s) over synthetic 1280x960 receipts, %d receipts per "
                                    "step per GPU in %d passes of %d (BASELINE config %d; ~%d crops per receipt)"
                                    % (head, RECEIPTS_PER_STEP, PASSES, PER_PASS, 4 if head == "CTC" else 5,
@@ -699,6 +738,8 @@ def main():
                                                     / elapsed / 1e12 / world / peak_tf) if peak_tf else None},
             "clocks": clk,
         }
+        if other is not None:
+            line["other_precision"] = other
         if e2e_jpeg is not None:
             line["e2e_jpeg"] = e2e_jpeg
         if world == 1 and not args.no_dropin:

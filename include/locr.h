@@ -38,6 +38,13 @@ typedef enum {
 enum { LOCR_MODEL_CRAFT = 0, LOCR_MODEL_CRNN = 1 };
 enum { LOCR_HEAD_CTC = 0, LOCR_HEAD_ATTN = 1 };
 enum { LOCR_ACT_F16 = 0, LOCR_ACT_BF16 = 1 };
+/* Arithmetic of the recogniser (CRNN):
+ *   LOCR_PREC_FAST  : 16-bit operands, fp32 accumulate - one tensor-core pass per layer (north-star precision policy);
+ *   LOCR_PREC_EXACT : split precision - every activation and folded weight of the ResNet, the BiLSTM projections and
+ *                     the prediction head is carried as a hi + lo pair of 16-bit numbers (~22 significant bits, three
+ *                     tensor-core passes per product), which reproduces the reference's fp32 logits to ~1e-2 of their
+ *                     trained scale at about twice the recognition time.  Detection (CRAFT) is unaffected. */
+enum { LOCR_PREC_FAST = 0, LOCR_PREC_EXACT = 1 };
 
 /* Mirrors the knobs of CRAFT.__init__ (ocr/net.py:45-50) and the config.yml keys read by CRNN (ocr/config.yml:27-45). */
 typedef struct {
@@ -50,6 +57,7 @@ typedef struct {
     float text_threshold; /* 0.7   (net.py:47) */
     float link_threshold; /* 0.4   (net.py:48) */
     float low_text;       /* 0.4   (net.py:49) */
+    int crnn_precision;   /* LOCR_PREC_* */
 } locr_config;
 
 LOCR_API const char* locr_version(void);

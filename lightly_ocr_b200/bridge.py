@@ -175,12 +175,13 @@ def test_lstm(xproj, whh, act_dtype=0, iters=0):
 class Config(C.Structure):
     _fields_ = [("device_id", C.c_int), ("act_dtype", C.c_int), ("head", C.c_int), ("num_classes", C.c_int),
                 ("canvas_size", C.c_int), ("mag_ratio", C.c_float), ("text_threshold", C.c_float),
-                ("link_threshold", C.c_float), ("low_text", C.c_float)]
+                ("link_threshold", C.c_float), ("low_text", C.c_float), ("crnn_precision", C.c_int)]
 
 
 MODEL_CRAFT, MODEL_CRNN = 0, 1
 HEAD_CTC, HEAD_ATTN = 0, 1
 ACT_F16, ACT_BF16 = 0, 1
+PREC_FAST, PREC_EXACT = 0, 1      # include/locr.h LOCR_PREC_*: arithmetic of the recogniser
 TEXT_STRIDE = 128
 
 
@@ -211,13 +212,16 @@ class Engine:
     """One liblocr handle = one GPU.  Weights go in as a {name: array-like fp32} mapping with reference key names."""
 
     def __init__(self, device_id=0, act_dtype=ACT_BF16, head="CTC", num_classes=None, canvas_size=1280,
-                 mag_ratio=1.5, text_threshold=0.7, link_threshold=0.4, low_text=0.4):
+                 mag_ratio=1.5, text_threshold=0.7, link_threshold=0.4, low_text=0.4, precision=None):
         self.L = lib()
         _bind_engine(self.L)
         self.head = HEAD_CTC if head == "CTC" else HEAD_ATTN
         self.num_classes = num_classes or (37 if self.head == HEAD_CTC else 38)
+        if precision is None:
+            precision = PREC_EXACT if os.environ.get("LOCR_CRNN_PREC", "fast") == "exact" else PREC_FAST
+        self.precision = precision
         cfg = Config(device_id, act_dtype, self.head, self.num_classes, canvas_size, mag_ratio, text_threshold,
-                     link_threshold, low_text)
+                     link_threshold, low_text, precision)
         self.h = C.c_void_p()
         _check(self.L.locr_create(C.byref(cfg), C.byref(self.h)))
 

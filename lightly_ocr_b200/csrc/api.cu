@@ -26,6 +26,7 @@ LOCR_API int locr_create(const locr_config* cfg, locr_handle** out) {
     if (h->cfg.link_threshold <= 0.f) h->cfg.link_threshold = 0.4f;
     if (h->cfg.low_text <= 0.f) h->cfg.low_text = 0.4f;
     if (h->cfg.num_classes <= 0) h->cfg.num_classes = h->cfg.head == LOCR_HEAD_CTC ? 37 : 38;
+    if (h->cfg.crnn_precision != LOCR_PREC_EXACT) h->cfg.crnn_precision = LOCR_PREC_FAST;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
         return fail(LOCR_ERR_CUDA, "locr_create: stream creation failed");
@@ -219,10 +220,18 @@ LOCR_API int locr_debug_read(locr_handle* h, const char* name, float* out, int64
     const int64_t inner = d.shape.back();
     const int64_t rows = n / inner;
     const size_t esz = d.kind == 0 ? 2 : (d.kind == 3 ? 1 : 4);
-    std::vector<uint8_t> raw((size_t)rows * inner * esz);
+    std::vector<uint8_t> raw((size_t)rows * inner * esz), raw_lo;
     LOCR_CUDA_OK(cudaMemcpy2D(raw.data(), inner * esz, d.p, d.pitch * esz, inner * esz, rows, cudaMemcpyDeviceToHost));
+    if (d.kind == 0 && d.lo_off > 0) {
+        raw_lo.resize(raw.size());
+        LOCR_CUDA_OK(cudaMemcpy2D(raw_lo.data(), inner * esz, (const uint16_t*)d.p + d.lo_off, d.pitch * esz, inner * esz,
+                                  rows, cudaMemcpyDeviceToHost));
+    }
     for (int64_t i = 0; i < n; ++i) {
-        if (d.kind == 0) out[i] = act_to_f32(reinterpret_cast<uint16_t*>(raw.data())[i], h->cfg.act_dtype);
+        if (d.kind == 0 && d.lo_off > 0)
+            out[i] = act_to_f32(reinterpret_cast<uint16_t*>(raw.data())[i], h->cfg.act_dtype) +
+                     act_to_f32(reinterpret_cast<uint16_t*>(raw_lo.data())[i], h->cfg.act_dtype);
+        else if (d.kind == 0) out[i] = act_to_f32(reinterpret_cast<uint16_t*>(raw.data())[i], h->cfg.act_dtype);
         else if (d.kind == 1) out[i] = reinterpret_cast<float*>(raw.data())[i];
         else if (d.kind == 2) out[i] = (float)reinterpret_cast<int32_t*>(raw.data())[i];
         else out[i] = (float)raw[i];

@@ -67,6 +67,7 @@ struct ConvParams {
     int out_fp32;
     const void* res;
     long res_pitch;
+    long res_lo_off;    // split-precision residual: offset (elements) of its lo halves, 0 = plain residual
     const float* bias;
     int relu, is_f16;
     // TMA-store epilogue: accumulators -> registers -> swizzled staging tile in smem -> one bulk tensor store
@@ -688,6 +689,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 v[q * 8 + 2] += f1.x; v[q * 8 + 3] += f1.y;
                                 v[q * 8 + 4] += f2.x; v[q * 8 + 5] += f2.y;
                                 v[q * 8 + 6] += f3.x; v[q * 8 + 7] += f3.y;
+                                if (EPI == 0 && p.res_lo_off > 0) {   // split-precision residual: value = hi + lo
+                                    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo_off + q * 8));
+                                    const float2 l0 = unpack2(ul.x, p.is_f16), l1 = unpack2(ul.y, p.is_f16);
+                                    const float2 l2 = unpack2(ul.z, p.is_f16), l3 = unpack2(ul.w, p.is_f16);
+                                    v[q * 8 + 0] += l0.x; v[q * 8 + 1] += l0.y;
+                                    v[q * 8 + 2] += l1.x; v[q * 8 + 3] += l1.y;
+                                    v[q * 8 + 4] += l2.x; v[q * 8 + 5] += l2.y;
+                                    v[q * 8 + 6] += l3.x; v[q * 8 + 7] += l3.y;
+                                }
                             }
                         }
                     }
@@ -1111,7 +1121,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         return cudaErrorInvalidValue;
     }
     p.y = c.y; p.y_pitch = c.y_pitch; p.out_fp32 = c.out_fp32;
-    p.res = c.residual; p.res_pitch = c.res_pitch;
+    p.res = c.residual; p.res_pitch = c.res_pitch; p.res_lo_off = c.res_lo_off;
     p.bias = c.bias; p.relu = c.relu; p.is_f16 = (c.dtype == ACT_F16) ? 1 : 0;
     {
         static int dbg = -1;
@@ -1227,6 +1237,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     if (allow_epi < 0) { const char* ev = getenv("LOCR_CONV_EPI"); allow_epi = ev ? atoi(ev) : 1; }
     int epi = 0;
     if (allow_epi && swz == 128 && p.tma_store && c.tail_out == nullptr && !c.split_out && !c.out_fp32 && !p.halo_pool &&
+        c.res_lo_off == 0 &&
         (p.stage_cols == 64 || p.stage_cols == 32)) {
         epi = p.stage_cols / 2;
         if (c.residual != nullptr) epi |= kEpiRes;

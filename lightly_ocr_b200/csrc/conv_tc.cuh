@@ -26,6 +26,7 @@ struct ConvCall {
     const float* bias = nullptr;   // [Cout_pad] fp32
     const void* residual = nullptr;  // NHWC at output resolution, 16-bit, pitch res_pitch
     long res_pitch = 0;
+    long res_lo_off = 0;  // > 0: the residual is a split-precision tensor, its lo halves live res_lo_off channels further
     int relu = 0;
     int dtype = ACT_BF16;
     int n_tile = 0;  // 0 = choose automatically

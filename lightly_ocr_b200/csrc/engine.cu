@@ -24,8 +24,10 @@ T* dev_upload(locr_handle* h, const std::vector<T>& v) {
 }
 
 // Conv (+ optional BatchNorm, eval mode, eps 1e-5) -> weights with the BN scale folded in and a single fp32 bias.
+// split: 0 = plain; 3 = split-precision input AND weights (K per tap [x_hi | x_lo | x_hi] against [w_hi | w_hi | w_lo]);
+//        2 = split-precision weights only, plain 16-bit input (K per tap [x | x] against [w_hi | w_lo])
 int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct,
-              bool fold_image_std = false, int cin_pad = 0, bool split3 = false, bool window = false) {
+              bool fold_image_std = false, int cin_pad = 0, int split = 0, bool window = false) {
     const HostTensor* w = find(h, model, prefix + ".weight");
     if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
         return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
@@ -70,10 +72,30 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
         cw.w32 = dev_upload(h, w32);
         if (!cw.w32) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
     } else {
-        if (split3) {
+        if (split == 2) {
+            if (cin % 32 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": split precision needs Cin % 32 == 0");
+            const int K2 = 2 * cin;
+            std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * K2, 0);
+            for (int n = 0; n < cout; ++n)
+                for (int c = 0; c < cin; ++c)
+                    for (int t = 0; t < taps; ++t) {
+                        const float wv = (float)(w->data[((size_t)n * cin + c) * taps + t] * scale[n]);
+                        const uint16_t hi = f32_to_act(wv, h->cfg.act_dtype);
+                        uint16_t* row = &w16[((size_t)n * taps + t) * K2];
+                        row[c] = hi;
+                        row[cin + c] = f32_to_act(wv - act_to_f32(hi, h->cfg.act_dtype), h->cfg.act_dtype);
+                    }
+            cw.w = dev_upload(h, w16);
+            if (!cw.w || !cw.bias) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+            cw.cin = K2;
+            cw.cin_wrap = cin;
+            h->conv[prefix] = cw;
+            return LOCR_OK;
+        }
+        if (split) {
             // split-precision layer: K channels per tap are [x_hi | x_lo | x_hi] against [w_hi | w_hi | w_lo], i.e.
             // x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with ~22 significant bits on both operands
-            if (cin % 64 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": split precision needs Cin % 64 == 0");
+            if (cin % 32 != 0) return h->fail(LOCR_ERR_INVALID, prefix + ": split precision needs Cin % 32 == 0");
             const int K3 = 3 * cin;
             std::vector<uint16_t> w16((size_t)cw.cout_pad * taps * K3, 0);
             for (int n = 0; n < cout; ++n)
@@ -163,6 +185,9 @@ struct Ctx {
     // row-padded input / output (pixels per memory row) for the NEXT tc() call (consumed by it)
     long x_row_px = 0, y_row_px = 0;
     void rows(long xr, long yr) { x_row_px = xr; y_row_px = yr; }
+    // split-precision residual of the NEXT tc() call (consumed by it): offset of the lo halves in elements
+    long res_lo_off = 0;
+    void res_split(long off) { res_lo_off = off; }
     // fused 1x1 tail request for the NEXT tc() call (consumed by it)
     const float* tail_w = nullptr;
     float* tail_out = nullptr;
@@ -187,6 +212,8 @@ struct Ctx {
         c.OW = (W + 2 * pad_w - dil * (cw.kw - 1) - 1) + 1;
         c.y = y; c.y_pitch = y_pitch; c.out_fp32 = out_fp32;
         c.bias = cw.bias; c.residual = res; c.res_pitch = res_pitch; c.relu = relu;
+        c.res_lo_off = res_lo_off;
+        res_lo_off = 0;
         c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
         c.cin_wrap = cw.cin_wrap;
         c.split_out = split_out;
@@ -426,17 +453,20 @@ int engine_finalize_crnn(locr_handle* h) {
     const int M = LOCR_MODEL_CRNN;
     const std::string loc = kLoc, fe = kFe;
     int rc;
-    auto F = [&](const std::string& p, const std::string& bn, bool direct = false) {
-        return fold_conv(h, M, p, bn, direct);
-    };
-    if ((rc = F(loc + "conv.0", loc + "conv.1", true))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.0", loc + "conv.1", true))) return rc;
     // The localisation network runs in split precision (hi + lo 16-bit pairs, ~22 bits): its output moves the TPS
     // sampling grid, and a 1e-4 fiducial error of plain 16-bit storage becomes a 1e-2 error of the rectified crop.
-    if ((rc = fold_conv(h, M, loc + "conv.4", loc + "conv.5", false, false, 0, true))) return rc;
-    if ((rc = fold_conv(h, M, loc + "conv.8", loc + "conv.9", false, false, 0, true))) return rc;
-    if ((rc = fold_conv(h, M, loc + "conv.12", loc + "conv.13", false, false, 0, true))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.4", loc + "conv.5", false, false, 0, 3))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.8", loc + "conv.9", false, false, 0, 3))) return rc;
+    if ((rc = fold_conv(h, M, loc + "conv.12", loc + "conv.13", false, false, 0, 3))) return rc;
+    // LOCR_PREC_EXACT: the whole recogniser in split precision (see include/locr.h); F folds accordingly from here on
+    const int X = h->exact();
+    auto F = [&](const std::string& p, const std::string& bn, bool direct = false) {
+        return fold_conv(h, M, p, bn, direct, false, 0, (X && !direct) ? 3 : 0);
+    };
     if ((rc = F(fe + "conv0_1", fe + "bn0_1", true))) return rc;
-    if ((rc = fold_conv(h, M, fe + "conv0_2", fe + "bn0_2", false, false, 0, false, true))) return rc;   // window view
+    if (X) { if ((rc = F(fe + "conv0_2", fe + "bn0_2"))) return rc; }
+    else if ((rc = fold_conv(h, M, fe + "conv0_2", fe + "bn0_2", false, false, 0, 0, true))) return rc;   // window view
     const int nblocks[5] = {0, 1, 2, 5, 3};
     for (int l = 1; l <= 4; ++l) {
         for (int i = 0; i < nblocks[l]; ++i) {
@@ -508,9 +538,12 @@ int engine_finalize_crnn(locr_handle* h) {
         const std::string name = "lstm" + std::to_string(l) + ".xproj";
         h->host[M][name + ".weight"] = stacked;
         h->host[M][name + ".bias"] = sbias;
+        // exact: layer 0 reads the split-precision visual features, layer 1 the split-precision output of linear 0
         if ((rc = F(name, ""))) return rc;
         h->lstm_whh[l] = dev_upload(h, whh);
-        if ((rc = F("SequenceModeling." + std::to_string(l) + ".linear", ""))) return rc;
+        // the Linear after the recurrence reads plain 16-bit hidden states: exact mode splits its weights only
+        if ((rc = fold_conv(h, M, "SequenceModeling." + std::to_string(l) + ".linear", "", false, false, 0, X ? 2 : 0)))
+            return rc;
     }
     if (h->cfg.head == LOCR_HEAD_CTC) {
         if ((rc = F("Prediction", ""))) return rc;
@@ -570,15 +603,19 @@ int engine_finalize_crnn(locr_handle* h) {
 }
 
 // CRNNet.forward (reference ocr/model.py:103-118): TPS_STN -> ResNet -> 2x BiLSTM -> CTC / attention head.
+// LOCR_PREC_EXACT (X = 1): every tensor from conv0_1 to the prediction head is a split-precision pair [hi | lo] with
+// twice the channel pitch; the convolutions read [hi | lo | hi] against [w_hi | w_hi | w_lo] (see fold_conv).
 int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits) {
     if (!h->ready[LOCR_MODEL_CRNN]) return h->fail(LOCR_ERR_STATE, "CRNN weights not finalized");
     if (B <= 0) return h->fail(LOCR_ERR_INVALID, "empty crop batch");
     if (B > 65536) return h->fail(LOCR_ERR_CAPACITY, "more than 65536 crops in one recognition batch");  // 32-bit indices
     Ctx c{h};
     const int f16 = h->is_f16();
+    const int X = h->exact();
+    auto P = [X](int ch) { return (long)(X ? 2 * ch : ch); };     // channel pitch of a tensor with `ch` logical channels
     cudaStream_t s = h->stream;
     const std::string loc = kLoc, fe = kFe;
-    const size_t big = (size_t)B * 32 * 100 * 64 * 2;
+    const size_t big = (size_t)B * 32 * 100 * 64 * 2 * (X ? 2 : 1);
     void* sA = c.buf("crnn.sA", big * 2);   // the split-precision localisation tensors have 2x the channels
     void* sB = c.buf("crnn.sB", big);
     void* sC = c.buf("crnn.sC", big / 2);
@@ -586,11 +623,11 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     float* fid = (float*)c.buf("crnn.fid", (size_t)B * 40 * 4);
     float* xr = (float*)c.buf("crnn.rectified", (size_t)B * 3200 * 4);
     float* grid = (float*)c.buf("crnn.grid", (size_t)B * 3200 * 2 * 4);
-    void* vis = c.buf("crnn.visual", (size_t)B * 26 * 512 * 2);
+    void* vis = c.buf("crnn.visual", (size_t)B * 26 * P(512) * 2);
     float* xproj = (float*)c.buf("crnn.xproj", (size_t)B * 26 * 2048 * 4);
     void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * 512 * 2);
-    void* s0 = c.buf("crnn.s0", (size_t)B * 26 * 256 * 2);
-    void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * 256 * 2);
+    void* s0 = c.buf("crnn.s0", (size_t)B * 26 * P(256) * 2);
+    void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * P(256) * 2);
     const int C = h->cfg.num_classes;
     float* lg = (float*)c.buf("crnn.logits", (size_t)B * 26 * C * 4);
     if (c.rc != LOCR_OK) return c.rc;
@@ -610,14 +647,22 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
 
     // ---- ResNet feature extractor (resnet50v1.py:101-135)
     const ConvW& r0 = h->conv[fe + "conv0_1"];
-    // conv0_1 writes a row-padded tensor (103 pixels per row, pads zero) so that conv0_2 takes the 4-pixel window view
-    // (6 k-blocks of 128-byte rows instead of 9 of 64 bytes; conv_tc.cuh x_row_px)
-    void* r0out = c.zbuf_grow("crnn.res0", (size_t)B * 32 * 103 * 32 * 2);
-    if (c.rc != LOCR_OK || r0out == nullptr) return c.rc != LOCR_OK ? c.rc : h->fail(LOCR_ERR_CUDA, "allocation failed");
-    { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, r0out, 32, 1, f16, s, 0, 0, 103); }
-    c.pool(sB, 64, 1);
-    c.rows(103, 0);
-    c.tc(fe + "conv0_2", r0out, B, 32, 100, 32, nullptr, 64, 1, 1, 0);
+    if (X) {
+        void* r0out = c.buf("crnn.res0", (size_t)B * 32 * 100 * 64 * 2);
+        if (c.rc != LOCR_OK) return c.rc;
+        { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, r0out, 64, 1, f16, s, 1, 0, 0); }
+        c.pool(sB, 128, 1);
+        c.tc(fe + "conv0_2", r0out, B, 32, 100, 64, nullptr, 128, 1, 1, 1, 1, 1, 0, nullptr, 0, 1);
+    } else {
+        // conv0_1 writes a row-padded tensor (103 pixels per row, pads zero) so that conv0_2 takes the 4-pixel window view
+        // (6 k-blocks of 128-byte rows instead of 9 of 64 bytes; conv_tc.cuh x_row_px)
+        void* r0out = c.zbuf_grow("crnn.res0", (size_t)B * 32 * 103 * 32 * 2);
+        if (c.rc != LOCR_OK || r0out == nullptr) return c.rc != LOCR_OK ? c.rc : h->fail(LOCR_ERR_CUDA, "allocation failed");
+        { ProfScope ps_(h, "direct_conv.res0", 0, false); launch_direct_conv3x3(xr, 0, B, 32, 100, 32, 100, 0, 0, r0.w32, r0.bias, 1, 32, r0out, 32, 1, f16, s, 0, 0, 103); }
+        c.pool(sB, 64, 1);
+        c.rows(103, 0);
+        c.tc(fe + "conv0_2", r0out, B, 32, 100, 32, nullptr, 64, 1, 1, 0);
+    }
     h->launches += 1;
     // x lives in `cur`; BasicBlock (resnet50v1.py:33-48): relu(bn2(conv2(relu(bn1(conv1 x)))) + residual)
     void* cur = sB;
@@ -628,69 +673,73 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     for (int l = 1; l <= 4; ++l) {
         for (int i = 0; i < nblocks[l]; ++i) {
             const std::string p = fe + "layer" + std::to_string(l) + "." + std::to_string(i) + ".";
-            const int P = planes[l];
-            c.tc(p + "conv1", cur, B, Hc, Wc, Cc, sC, P, 1, 1, 1);
+            const int Pl = planes[l];
+            c.tc(p + "conv1", cur, B, Hc, Wc, P(Cc), sC, P(Pl), 1, 1, 1, 1, 1, 0, nullptr, 0, X);
             const void* res = cur;
-            long res_pitch = Cc;
+            long res_pitch = P(Cc);
+            int res_ch = Cc;
             if (h->conv.count(p + "downsample.0")) {
-                c.tc(p + "downsample.0", cur, B, Hc, Wc, Cc, sD, P, 0, 0, 0);
+                c.tc(p + "downsample.0", cur, B, Hc, Wc, P(Cc), sD, P(Pl), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
                 res = sD;
-                res_pitch = P;
+                res_pitch = P(Pl);
+                res_ch = Pl;
             }
-            c.tc(p + "conv2", sC, B, Hc, Wc, P, other, P, 1, 1, 1, 1, 1, 0, res, res_pitch);
+            if (X) c.res_split(res_ch);
+            c.tc(p + "conv2", sC, B, Hc, Wc, P(Pl), other, P(Pl), 1, 1, 1, 1, 1, 0, res, res_pitch, X);
             std::swap(cur, other);
-            Cc = P;
+            Cc = Pl;
         }
         const std::string tail = fe + "conv" + std::to_string(l);
         if (l == 1) {
             // conv1 + BN + ReLU + MaxPool2d(2, 2) (resnet50v1.py:110-112): pooled in the conv epilogue, only the pooled tensor is written
-            c.pool(other, Cc, 1);
-            c.tc(tail, cur, B, Hc, Wc, Cc, nullptr, Cc, 1, 1, 1);
+            c.pool(other, P(Cc), 1);
+            c.tc(tail, cur, B, Hc, Wc, P(Cc), nullptr, P(Cc), 1, 1, 1, 1, 1, 0, nullptr, 0, X);
             std::swap(cur, other);
             Hc /= 2; Wc /= 2;
         } else if (l <= 3) {
-            c.tc(tail, cur, B, Hc, Wc, Cc, other, Cc, 1, 1, 1);
+            c.tc(tail, cur, B, Hc, Wc, P(Cc), other, P(Cc), 1, 1, 1, 1, 1, 0, nullptr, 0, X);
             std::swap(cur, other);
         }
         if (l == 2) {
-            { ProfScope ps_(h, "maxpool.res2", 0, false); launch_maxpool(cur, Cc, B, Hc, Wc, Cc, other, Cc, 2, 2, 2, 1, 0, 1, f16, s); }
+            { ProfScope ps_(h, "maxpool.res2", 0, false); launch_maxpool(cur, P(Cc), B, Hc, Wc, Cc, other, P(Cc), 2, 2, 2, 1, 0, 1, f16, s, X); }
             Hc = (Hc - 2) / 2 + 1; Wc = Wc + 2 - 2 + 1;
             h->launches++;
             std::swap(cur, other);
         }
     }
-    dbg(h, "layer4", cur, 0, {B, Hc, Wc, 512}, 512);
-    c.tc(fe + "conv4_1", cur, B, Hc, Wc, 512, other, 512, 1, 0, 1, 1, 2);                  // k2 s(2,1) p(0,1) -> 2x27
-    c.tc(fe + "conv4_2", other, B, 2, 27, 512, vis, 512, 1, 0, 0);                        // k2 s1 p0     -> 1x26
+    dbg(h, "layer4", cur, 0, {B, Hc, Wc, 512}, P(512));
+    if (X) h->dbg["layer4"].lo_off = 512;
+    c.tc(fe + "conv4_1", cur, B, Hc, Wc, P(512), other, P(512), 1, 0, 1, 1, 2, 0, nullptr, 0, X);      // k2 s(2,1) p(0,1) -> 2x27
+    c.tc(fe + "conv4_2", other, B, 2, 27, P(512), vis, P(512), 1, 0, 0, 1, 1, 0, nullptr, 0, X);        // k2 s1 p0     -> 1x26
 
     // ---- sequence modelling (model.py:107-112; AdaptiveAvgPool over H=1 is the identity) as [B*26, C] GEMMs
     const int R = B * 26;
-    c.tc("lstm0.xproj", vis, 1, 1, R, 512, xproj, 2048, 0, 0, 0, 1, 1, 1);
+    c.tc("lstm0.xproj", vis, 1, 1, R, P(512), xproj, 2048, 0, 0, 0, 1, 1, 1);
     if (c.rc == LOCR_OK) {
         ProfScope ps_(h, "lstm", 0, false);
         if (launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s) != cudaSuccess)
             c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     }
-    c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, 256, 0, 0, 0);
-    c.tc("lstm1.xproj", s0, 1, 1, R, 256, xproj, 2048, 0, 0, 0, 1, 1, 1);
+    c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
+    c.tc("lstm1.xproj", s0, 1, 1, R, P(256), xproj, 2048, 0, 0, 0, 1, 1, 1);
     if (c.rc == LOCR_OK) {
         ProfScope ps_(h, "lstm", 0, false);
         if (launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s) != cudaSuccess)
             c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     }
-    c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, 256, 0, 0, 0);
+    c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
     h->launches += 2;
     if (h->cfg.head == LOCR_HEAD_CTC) {
-        c.tc("Prediction", s1, 1, 1, R, 256, lg, C, 0, 0, 0, 1, 1, 1);
+        c.tc("Prediction", s1, 1, 1, R, P(256), lg, C, 0, 0, 0, 1, 1, 1);
     } else {
         float* fproj = (float*)c.buf("crnn.fproj", (size_t)R * 256 * 4);
-        c.tc("Prediction.attention_cell.i2h", s1, 1, 1, R, 256, fproj, 256, 0, 0, 0, 1, 1, 1);
+        c.tc("Prediction.attention_cell.i2h", s1, 1, 1, R, P(256), fproj, 256, 0, 0, 0, 1, 1, 1);
         if (c.rc == LOCR_OK) {
             AttnWeights w;
             w.h2h_wt = (const uint16_t*)h->u16["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
             w.wg = (const uint16_t*)h->u16["att.wg"]; w.woh = h->f32["att.woh"]; w.gate_b = h->f32["att.gate_b"];
             w.gen_w = h->f32["att.gen_w"]; w.gen_b = h->f32["att.gen_b"];
-            { ProfScope ps_(h, "attention", 0, false); launch_attention(s1, fproj, w, lg, B, C, f16, s); }
+            { ProfScope ps_(h, "attention", 0, false); launch_attention(s1, fproj, w, lg, B, C, f16, s, P(256), X ? 256 : 0); }
             h->launches++;
         }
     }
@@ -699,8 +748,9 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     dbg(h, "fiducials", fid, 1, {B, 20, 2}, 2);
     dbg(h, "grid", grid, 1, {B, 3200, 2}, 2);
     dbg(h, "rectified", xr, 1, {B, 32, 100}, 100);
-    dbg(h, "visual", vis, 0, {B, 26, 512}, 512);
-    dbg(h, "contextual", s1, 0, {B, 26, 256}, 256);
+    dbg(h, "visual", vis, 0, {B, 26, 512}, P(512));
+    dbg(h, "contextual", s1, 0, {B, 26, 256}, P(256));
+    if (X) { h->dbg["visual"].lo_off = 512; h->dbg["contextual"].lo_off = 256; }
     dbg(h, "logits", lg, 1, {B, 26, C}, C);
     *logits = lg;
     return LOCR_OK;

@@ -37,6 +37,7 @@ struct DebugTensor {
     int kind;  // 0 = 16-bit activation, 1 = fp32, 2 = int32, 3 = uint8
     std::vector<int64_t> shape;
     long pitch;  // elements per innermost row (>= shape.back())
+    long lo_off = 0;  // > 0: split-precision tensor, the lo halves live lo_off elements further (value = hi + lo)
 };
 
 }  // namespace locr
@@ -76,6 +77,7 @@ struct locr_handle {
         return code;
     }
     int is_f16() const { return cfg.act_dtype == LOCR_ACT_F16 ? 1 : 0; }
+    int exact() const { return cfg.crnn_precision == LOCR_PREC_EXACT ? 1 : 0; }
 };
 
 namespace locr {

@@ -468,7 +468,7 @@ constexpr int kAttT = 26;
 template <int kAttG>
 __global__ void __launch_bounds__(512)
 attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ fproj, AttnWeights w,
-                 float* __restrict__ preds, int B, int C, int f16) {
+                 float* __restrict__ preds, int B, int C, int f16, long feat_pitch, long feat_lo_off) {
     __shared__ float hs[kAttG][256];
     __shared__ float ctx[kAttG][256];
     __shared__ float e[kAttG][32];
@@ -560,7 +560,12 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
             const int b = b0 + g;
             float v = 0.f;
             if (b < B) {
-                for (int t = 0; t < kAttT; ++t) v = fmaf(e[g][t], act2f(feats[((long)b * kAttT + t) * 256 + j], f16), v);
+                for (int t = 0; t < kAttT; ++t) {
+                    const uint16_t* fp = feats + ((long)b * kAttT + t) * feat_pitch + j;
+                    float fv = act2f(fp[0], f16);
+                    if (feat_lo_off > 0) fv += act2f(fp[feat_lo_off], f16);     // split-precision features
+                    v = fmaf(e[g][t], fv, v);
+                }
             }
             ctx[g][j] = v;
         }
@@ -806,7 +811,8 @@ void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* 
 }
 
 void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
-                      cudaStream_t s) {
+                      cudaStream_t s, long feat_pitch, long feat_lo_off) {
+    if (feat_pitch <= 0) feat_pitch = 256;
     int sms = 148;
     {
         int dev = 0;
@@ -815,8 +821,8 @@ void launch_attention(const void* feats, const float* fproj, AttnWeights w, floa
     }
     const uint16_t* f = (const uint16_t*)feats;
     // 5 crops per CTA when that brings the grid down to one resident wave (148 < B / 4, B / 5 <= 148), else 4
-    if ((B + 3) / 4 > sms && (B + 4) / 5 <= sms) attention_kernel<5><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16);
-    else attention_kernel<4><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16);
+    if ((B + 3) / 4 > sms && (B + 4) / 5 <= sms) attention_kernel<5><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+    else attention_kernel<4><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
 }
 
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,

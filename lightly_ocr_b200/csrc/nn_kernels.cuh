@@ -67,8 +67,10 @@ struct AttnWeights {
 // Attention.forward inference branch (attention.py:46-59) with B=1 semantics per crop.
 // feats 16-bit [B][26][256] (contextual features), fproj fp32 [B][26][256] (= i2h(feats), hoisted out of the loop),
 // preds fp32 [B][26][C].
+// feat_pitch: elements per time step of feats (0 = 256); feat_lo_off > 0: feats is a split-precision tensor whose lo
+// halves live feat_lo_off elements further (value = hi + lo).
 void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
-                      cudaStream_t s);
+                      cudaStream_t s, long feat_pitch = 0, long feat_lo_off = 0);
 
 // Token decode + confidence (net.py:162-167,177-190; recog_utils.py:32-47,113-119).  logits fp32 [B][26][C].
 // ids int32 [B][26]; text char [B][text_stride]; has_eos int32 [B] (CTC: always 1; Attention: 0 when no [s] was

@@ -4,7 +4,10 @@
 synthetic checkpoints of oracle/weights.py, and its outputs are committed as small fixtures.  The reference sources
 are staged in a scratch directory under /tmp by oracle/ref_env.py (shims and staging are documented there).
 
-Usage:  python -m oracle.make_golden
+Usage:  python -m oracle.make_golden [--keep-calib] [--checkpoint fp32]
+
+--checkpoint fp32 records the same fixtures for the plain-fp32-trained synthetic recogniser
+(lightly_ocr_b200/synth/calib_crnn_*_fp32.npz) as tests/golden/ref_{ctc,attention}_fp32.npz.
 """
 import contextlib
 import io
@@ -27,15 +30,18 @@ def main():
     scratch = "/tmp/locr_ref_scratch"
     os.makedirs(scratch, exist_ok=True)
 
+    ckpt = sys.argv[sys.argv.index("--checkpoint") + 1] if "--checkpoint" in sys.argv else "trained"
+    trained = "fp32" if ckpt == "fp32" else True
+    suffix = "_fp32" if ckpt == "fp32" else ""
     # ---- calibrations of the synthetic checkpoints (committed so every machine loads identical tensors)
-    if "--keep-calib" not in sys.argv:
+    if "--keep-calib" not in sys.argv and ckpt != "fp32":
         weights.build_calibrations()
     img0 = receipts.receipt(0)
     craft_calibrated = weights.craft_calibrated
 
     for head in ("CTC", "Attention"):
         craft_sd = craft_calibrated(0, ink=True)
-        crnn_sd = weights.crnn_calibrated(1, head=head)
+        crnn_sd = weights.crnn_calibrated(1, head=head, trained=trained)
         dst = ref_env.stage(head, craft_sd, crnn_sd, scratch)
         with ref_env.imported(dst):
             import net as ref_net
@@ -127,7 +133,9 @@ def main():
             out["e2e_counts"] = np.array(counts, np.int32)
             out["e2e_text"] = np.array(texts)
             out["e2e_conf"] = np.array(confs, np.float32)
-            np.savez_compressed(os.path.join(GOLDEN, "ref_%s.npz" % head.lower()), **out)
+            if suffix:      # the detector side does not depend on the recogniser's checkpoint: keep the file small
+                out = {k: v for k, v in out.items() if k.startswith(("crnn_", "e2e_"))}
+            np.savez_compressed(os.path.join(GOLDEN, "ref_%s%s.npz" % (head.lower(), suffix)), **out)
             print(head, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 

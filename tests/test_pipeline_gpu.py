@@ -103,8 +103,9 @@ def test_dropin_ctc_end_to_end(tmp_path, eager):
     assert match >= 0.985
 
 
+@pytest.mark.parametrize("ckpt", ["trained", "fp32"])
 @pytest.mark.parametrize("head", ["CTC", "Attention"])
-def test_strings_and_confidences_match_live_reference_goldens(head):
+def test_strings_and_confidences_match_live_reference_goldens(head, ckpt):
     """The receipts whose `pipeline.getText` output was recorded from the LIVE reference (tests/golden, made by
     oracle/make_golden.py): the CUDA path must return the same number of results, >= 99.5% identical strings, and
     confidences (products of 26 soft-max maxima) within 0.5% at the median and 3% at the 95th percentile where the strings
@@ -112,10 +113,13 @@ def test_strings_and_confidences_match_live_reference_goldens(head):
     because a score-map pixel crossed the threshold gives the same string from a different crop)."""
     from lightly_ocr_b200 import bridge
     from oracle import receipts, weights
-    gz = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_%s.npz" % head.lower()))
+    # ckpt = "fp32": the synthetic recogniser trained the plain way (fp32 forward, no emulation of 16-bit storage, no
+    # injected noise; tools/train_synth_crnn.py LOCR_TRAIN_MODE=fp32) and its own goldens from the live reference
+    gz = np.load(os.path.join(os.path.dirname(__file__), "golden",
+                              "ref_%s%s.npz" % (head.lower(), "_fp32" if ckpt == "fp32" else "")))
     runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head=head)
     runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
-    runner.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, head))
+    runner.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, head, trained="fp32" if ckpt == "fp32" else True))
     images = [receipts.receipt(int(r)) for r in gz["e2e_receipts"]]
     per_image, out = runner.ocr(images)
     got_t, got_c, k = [], [], 0
@@ -131,22 +135,26 @@ def test_strings_and_confidences_match_live_reference_goldens(head):
     same = [g == w for g, w in zip(got_t, want_t)]
     rel = np.array([abs(c - w) / w for c, w, s in zip(got_c, want_c, same) if s])
     ab = np.array([abs(c - w) for c, w, s in zip(got_c, want_c, same) if s])
-    print("%s: %d / %d strings identical to the live reference; confidence error: max abs %.4f, median rel %.5f, "
-          "95th percentile rel %.4f" % (head, sum(same), len(same), ab.max(), np.median(rel), np.quantile(rel, 0.95)))
+    print("%s/%s: %d / %d strings identical to the live reference; confidence error: max abs %.4f, median rel %.5f, "
+          "95th percentile rel %.4f" % (head, ckpt, sum(same), len(same), ab.max(), np.median(rel), np.quantile(rel, 0.95)))
     assert sum(same) / len(same) >= 0.995
     assert np.median(rel) < 0.005 and np.quantile(rel, 0.95) < 0.03
     runner.close()
 
 
-def test_string_gate_many_receipts():
+@pytest.mark.parametrize("ckpt,prec", [("trained", "fast"), ("fp32", "fast"), ("fp32", "exact")])
+def test_string_gate_many_receipts(ckpt, prec):
     """North-star string gate at scale: every crop the GPU detects on 8 synthetic receipts (~640 crops) is recognised
-    by the CUDA path (fp16 storage) and by the fp32 oracle; >= 99.5% of the strings must be identical.  (Detection
-    parity - boxes bit-exact given the maps, sorted rects equal to the fp32 oracle's - is covered above.)"""
+    by the CUDA path and by the fp32 oracle; >= 99.5% of the strings must be identical - on the checkpoint conditioned
+    on 16-bit storage and on the plainly fp32-trained one, in the fast (16-bit operands) and the exact (split
+    precision) arithmetic.  (Detection parity - boxes bit-exact given the maps, sorted rects equal to the fp32
+    oracle's - is covered above.)"""
     from lightly_ocr_b200 import bridge
     from oracle import ocr_ref, receipts, weights
     torch.set_num_threads(os.cpu_count())
-    crnn_sd = weights.crnn_calibrated(1, "CTC")
-    runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
+    crnn_sd = weights.crnn_calibrated(1, "CTC", trained="fp32" if ckpt == "fp32" else True)
+    runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC",
+                              precision=bridge.PREC_EXACT if prec == "exact" else bridge.PREC_FAST)
     runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
     runner.load_state_dict(bridge.MODEL_CRNN, crnn_sd)
     images = [receipts.receipt(s) for s in range(8, 16)]
@@ -166,8 +174,8 @@ def test_string_gate_many_receipts():
     truth = []
     for s in range(8, 16):
         truth.extend(w[0] for w in receipts.receipt(s, return_words=True)[1])
-    print("string gate: %d / %d identical to the fp32 oracle (%.4f); %d of them are rendered words of the receipts" %
-          (same, len(got), same / len(got), len(set(got) & set(truth))))
+    print("string gate %s/%s: %d / %d identical to the fp32 oracle (%.4f); %d of them are rendered words of the receipts" %
+          (ckpt, prec, same, len(got), same / len(got), len(set(got) & set(truth))))
     assert same / len(got) >= 0.995
     runner.close()
 
@@ -204,13 +212,14 @@ def test_dropin_attention(tmp_path):
     assert np.mean(agree) >= 0.9
 
 
-def test_attention_string_gate():
+@pytest.mark.parametrize("ckpt", ["trained", "fp32"])
+def test_attention_string_gate(ckpt):
     """BASELINE config 5 (attention decoder end to end): all crops the GPU detects on 8 receipts, recognised by the CUDA
     attention path and by the fp32 oracle (B = 1 semantics per crop); the strings cut at [s] must agree >= 99.5%."""
     from lightly_ocr_b200 import bridge
     from oracle import ocr_ref, receipts, weights
     torch.set_num_threads(os.cpu_count())
-    sd = weights.crnn_calibrated(1, "Attention")
+    sd = weights.crnn_calibrated(1, "Attention", trained="fp32" if ckpt == "fp32" else True)
     runner = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="Attention")
     runner.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
     runner.load_state_dict(bridge.MODEL_CRNN, sd)
@@ -233,7 +242,7 @@ def test_attention_string_gate():
     truth = []
     for s in range(16, 24):
         truth.extend(w[0] for w in receipts.receipt(s, return_words=True)[1])
-    print("attention string gate: %d / %d identical to the fp32 oracle (%.4f); %d are rendered words" %
-          (same, len(got), same / len(got), len(set(g for g in got if g) & set(truth))))
+    print("attention string gate (%s): %d / %d identical to the fp32 oracle (%.4f); %d are rendered words" %
+          (ckpt, same, len(got), same / len(got), len(set(g for g in got if g) & set(truth))))
     assert same / len(got) >= 0.995
     runner.close()
