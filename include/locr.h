@@ -151,6 +151,15 @@ LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flo
  * "layer-or-kernel-name milliseconds algorithmic-flops launches" (tools/prof_pipeline.py). */
 LOCR_API int locr_profile_layers(locr_handle* h, char* out, int64_t capacity);
 
+/* Range audit of the 16-bit activation storage.  Conversions to fp16 / bf16 saturate (an activation beyond the fp16
+ * range is stored as +-65504, never as an infinity), so an overflowing checkpoint degrades instead of turning into
+ * NaNs - and this audit finds it: enable, run detection / recognition on representative inputs, read text lines
+ * "layer-name abs-max" (one per convolution launch, in launch order; 16-bit outputs only).  A layer close to 65504 has
+ * no head-room in fp16: run the handle with act_dtype = LOCR_ACT_BF16 (8 exponent bits) instead.  Costs one extra pass
+ * over every activation while enabled. */
+LOCR_API int locr_audit(locr_handle* h, int enable);
+LOCR_API int locr_audit_read(locr_handle* h, char* out, int64_t capacity);
+
 /* Kernel launches issued by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 LOCR_API int64_t locr_launch_count(const locr_handle* h);
 

@@ -203,6 +203,10 @@ def _bind_engine(L):
     L.locr_debug_craft_scores.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.locr_debug_crnn.restype = C.c_int
     L.locr_debug_crnn.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp]
+    L.locr_audit.restype = C.c_int
+    L.locr_audit.argtypes = [vp, C.c_int]
+    L.locr_audit_read.restype = C.c_int
+    L.locr_audit_read.argtypes = [vp, C.c_char_p, C.c_int64]
     L.locr_debug_read.restype = C.c_int
     L.locr_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     L._engine_bound = True
@@ -248,6 +252,20 @@ class Engine:
 
     def launch_count(self):
         return int(self.L.locr_launch_count(self.h))
+
+    def audit(self, enable=True):
+        """Range audit of the 16-bit activations (include/locr.h locr_audit): enable, run forward passes, audit_read()."""
+        _check(self.L.locr_audit(self.h, int(enable)), self.h)
+
+    def audit_read(self):
+        """[(layer name, largest |activation| stored)] per convolution launch since audit(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(self.L.locr_audit_read(self.h, buf, len(buf)), self.h)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, v = line.rsplit(" ", 1)
+            rows.append((name, float(v)))
+        return rows
 
     def craft_scores(self, images):
         """images: uint8 [B,H,W,3] BGR (same size) -> fp32 [B,H32/2,W32/2,2]."""

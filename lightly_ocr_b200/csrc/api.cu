@@ -149,6 +149,45 @@ LOCR_API int locr_profile_layers(locr_handle* h, char* out, int64_t capacity) {
     return LOCR_OK;
 }
 
+/* Range audit of the 16-bit activations: locr_audit(h, 1), run any forward passes, locr_audit_read. */
+LOCR_API int locr_audit(locr_handle* h, int enable) {
+    if (h == nullptr) return fail(LOCR_ERR_INVALID, "null handle");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    if (enable) {
+        if (h->audit_slots == nullptr) {
+            void* p = nullptr;
+            LOCR_CUDA_OK(cudaMalloc(&p, kAuditSlots * sizeof(float)));
+            h->owned.push_back(p);
+            h->audit_slots = (float*)p;
+        }
+        LOCR_CUDA_OK(cudaMemsetAsync(h->audit_slots, 0, kAuditSlots * sizeof(float), h->stream));
+        h->audit_names.clear();
+    }
+    h->audit = enable != 0;
+    return LOCR_OK;
+}
+
+/* Text lines "layer-name abs-max" for every audited launch since locr_audit(h, 1), in launch order (a layer that ran
+ * several times appears several times).  65504 (fp16) means the layer saturated. */
+LOCR_API int locr_audit_read(locr_handle* h, char* out, int64_t capacity) {
+    if (h == nullptr || out == nullptr || capacity <= 0) return fail(LOCR_ERR_INVALID, "bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    std::vector<float> v(h->audit_names.size());
+    if (!v.empty()) {
+        LOCR_CUDA_OK(cudaStreamSynchronize(h->stream));
+        LOCR_CUDA_OK(cudaMemcpy(v.data(), h->audit_slots, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    std::string s;
+    char line[256];
+    for (size_t i = 0; i < v.size(); ++i) {
+        snprintf(line, sizeof(line), "%s %.9g\n", h->audit_names[i].c_str(), v[i]);
+        s += line;
+    }
+    if ((int64_t)s.size() + 1 > capacity) return h->fail(LOCR_ERR_CAPACITY, "locr_audit_read: buffer too small");
+    memcpy(out, s.c_str(), s.size() + 1);
+    return LOCR_OK;
+}
+
 /* ---- debug / test entry points ---- */
 
 LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score) {

@@ -231,6 +231,21 @@ struct Ctx {
         }
         h->launches++;
         if (e != cudaSuccess) rc = h->fail(LOCR_ERR_CUDA, layer + ": " + err);
+        if (h->audit && e == cudaSuccess && !out_fp32 && c.tail_out == nullptr && h->audit_slots != nullptr &&
+            (int)h->audit_names.size() < kAuditSlots) {
+            // range audit: largest |activation| this layer stored (pooled tensor when only that one is written; a
+            // split-precision tensor is judged by its hi halves; row pads are zero and do not matter)
+            const bool pooled = c.pool_y != nullptr && c.skip_full;
+            const void* t = pooled ? c.pool_y : y;
+            const long pitch = pooled ? c.pool_pitch : y_pitch;
+            const long rows = pooled ? (long)B * (c.OH / 2) * (c.OW / 2)
+                                     : (long)B * c.OH * (c.y_row_px > 0 ? c.y_row_px : c.OW);
+            if (t != nullptr) {
+                launch_absmax(t, rows, cw.cout / 8 * 8, pitch, h->is_f16(), h->audit_slots + h->audit_names.size(), h->stream);
+                h->audit_names.push_back(layer);
+                h->launches++;
+            }
+        }
     }
     // Row-padded buffer whose pad pixels must read as zero: zero-filled whenever it is (re)allocated or its size changes
     // (the producers only ever write the interior).
@@ -589,6 +604,19 @@ int engine_finalize_crnn(locr_handle* h) {
                 for (int q = 0; q < 4; ++q) woh[((size_t)v * 256 + j) * 4 + q] = wih->data[(size_t)(q * 256 + j) * K + 256 + v];
         for (int i = 0; i < 1024; ++i) gbias[i] = bih->data[i] + bhh->data[i];
         h->u16["att.wg"] = dev_upload(h, wg);
+        if (X) {   // exact arithmetic: the decoder's matrices stay fp32 (same layouts)
+            std::vector<float> h2h32((size_t)256 * 256), wg32((size_t)256 * 256 * 8);
+            for (int k = 0; k < 256; ++k)
+                for (int j = 0; j < 256; ++j) {
+                    h2h32[(size_t)k * 256 + j] = h2h->data[(size_t)j * 256 + k];
+                    for (int q = 0; q < 4; ++q) {
+                        wg32[((size_t)k * 256 + j) * 8 + q] = wih->data[(size_t)(q * 256 + j) * K + k];
+                        wg32[((size_t)k * 256 + j) * 8 + 4 + q] = whh->data[(size_t)(q * 256 + j) * 256 + k];
+                    }
+                }
+            upload_f32(h, "att.h2h_wt32", h2h32);
+            upload_f32(h, "att.wg32", wg32);
+        }
         upload_f32(h, "att.woh", woh);
         if (!h->u16["att.h2h_wt"] || !h->u16["att.wg"]) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
         upload_f32(h, "att.gate_b", gbias);
@@ -739,6 +767,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
             w.h2h_wt = (const uint16_t*)h->u16["att.h2h_wt"]; w.h2h_b = h->f32["att.h2h_b"]; w.score_w = h->f32["att.score"];
             w.wg = (const uint16_t*)h->u16["att.wg"]; w.woh = h->f32["att.woh"]; w.gate_b = h->f32["att.gate_b"];
             w.gen_w = h->f32["att.gen_w"]; w.gen_b = h->f32["att.gen_b"];
+            if (X) { w.h2h_wt32 = h->f32["att.h2h_wt32"]; w.wg32 = h->f32["att.wg32"]; }
             { ProfScope ps_(h, "attention", 0, false); launch_attention(s1, fproj, w, lg, B, C, f16, s, P(256), X ? 256 : 0); }
             h->launches++;
         }

@@ -70,6 +70,10 @@ struct locr_handle {
     struct ProfAgg { double ms = 0, flops = 0; int64_t n = 0; };
     std::map<std::string, ProfAgg> prof_layers;  // per-layer totals accumulated by locr_profile_read
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    // range audit (locr_audit): while enabled every 16-bit conv output is followed by an abs-max reduction
+    bool audit = false;
+    float* audit_slots = nullptr;            // device, kAuditSlots floats
+    std::vector<std::string> audit_names;    // slot i <- layer name of the i-th audited launch since locr_audit(1)
 
     int fail(int code, const std::string& m) {
         err = m;
@@ -81,6 +85,8 @@ struct locr_handle {
 };
 
 namespace locr {
+
+constexpr int kAuditSlots = 512;
 
 // Brackets one kernel launch with CUDA events on the handle's stream while profiling is enabled.
 struct ProfScope {

@@ -465,7 +465,7 @@ constexpr int kAttT = 26;
 // scores are split between the halves by time step and the context vectors by crop.
 // kAttG = crops per CTA, chosen by the launcher so that all CTAs are resident at once (one CTA of 512 threads per SM):
 // a second, nearly empty wave would double the kernel time.
-template <int kAttG>
+template <int kAttG, bool W32>
 __global__ void __launch_bounds__(512)
 attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ fproj, AttnWeights w,
                  float* __restrict__ preds, int B, int C, int f16, long feat_pitch, long feat_lo_off) {
@@ -498,7 +498,7 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
         for (int g = 0; g < kAttG; ++g) hp[g] = kh == 0 ? w.h2h_b[j] : 0.f;
 #pragma unroll 8
         for (int k = k0; k < k0 + 128; ++k) {
-            const float wv = act2f(__ldg(&w.h2h_wt[k * 256 + j]), f16);
+            const float wv = W32 ? __ldg(&w.h2h_wt32[k * 256 + j]) : act2f(__ldg(&w.h2h_wt[k * 256 + j]), f16);
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) hp[g] = fmaf(wv, hs[g][k], hp[g]);
         }
@@ -586,9 +586,16 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
         }
 #pragma unroll 4
         for (int k = k0; k < k0 + 128; ++k) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(w.wg + ((size_t)k * 256 + j) * 8));
             float wf[8];
-            unpack8(u, wf, f16);
+            if (W32) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w.wg32 + ((size_t)k * 256 + j) * 8));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(w.wg32 + ((size_t)k * 256 + j) * 8 + 4));
+                wf[0] = w0.x; wf[1] = w0.y; wf[2] = w0.z; wf[3] = w0.w;
+                wf[4] = w1.x; wf[5] = w1.y; wf[6] = w1.z; wf[7] = w1.w;
+            } else {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(w.wg + ((size_t)k * 256 + j) * 8));
+                unpack8(u, wf, f16);
+            }
 #pragma unroll
             for (int g = 0; g < kAttG; ++g) {
                 const float cv = ctx[g][k], hv = hs[g][k];
@@ -742,6 +749,26 @@ decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int
     }
 }
 
+// ------------------------------------------------------------------------------------------- range audit
+__global__ void __launch_bounds__(256)
+absmax_kernel(const uint16_t* __restrict__ t, long rows, int C, long pitch, int f16, float* __restrict__ slot) {
+    const int groups = C >> 3;
+    const long total = rows * groups;
+    float m = 0.f;
+    for (long gid = (long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long)gridDim.x * blockDim.x) {
+        const long r = gid / groups;
+        const int g = (int)(gid - r * groups);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(t + r * pitch + g * 8));
+        float f[8];
+        unpack8(u, f, f16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(f[j]));     // fmaxf drops NaN: an infinity shows up as inf
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+}
+
 inline int grid_for(long total, int block) {
     long g = (total + block - 1) / block;
     const long cap = 148L * 16;
@@ -776,6 +803,11 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
     else
         direct_conv3x3_kernel<1, false, false><<<grid, 256, smem, s>>>(in, B, H, W, H, W, 0, 0, w, bias, Cout,
                                                                        (uint16_t*)out, out_pitch, relu, is_f16, split_out);
+}
+
+void launch_absmax(const void* t, long rows, int C, long pitch, int is_f16, float* slot, cudaStream_t s) {
+    if (rows <= 0 || C < 8) return;
+    absmax_kernel<<<grid_for(rows * (C >> 3), 256), 256, 0, s>>>((const uint16_t*)t, rows, C, pitch, is_f16, slot);
 }
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
@@ -821,8 +853,14 @@ void launch_attention(const void* feats, const float* fproj, AttnWeights w, floa
     }
     const uint16_t* f = (const uint16_t*)feats;
     // 5 crops per CTA when that brings the grid down to one resident wave (148 < B / 4, B / 5 <= 148), else 4
-    if ((B + 3) / 4 > sms && (B + 4) / 5 <= sms) attention_kernel<5><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
-    else attention_kernel<4><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+    const bool w32 = w.h2h_wt32 != nullptr && w.wg32 != nullptr;
+    if ((B + 3) / 4 > sms && (B + 4) / 5 <= sms) {
+        if (w32) attention_kernel<5, true><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+        else attention_kernel<5, false><<<(B + 4) / 5, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+    } else {
+        if (w32) attention_kernel<4, true><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+        else attention_kernel<4, false><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
+    }
 }
 
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,

@@ -63,6 +63,9 @@ struct AttnWeights {
     const float* gate_b;     // [4][256]  b_ih + b_hh
     const float* gen_w;    // [C][256]
     const float* gen_b;    // [C]
+    // LOCR_PREC_EXACT: the two big matrices in fp32 (same layouts); used instead of the 16-bit copies when non-null
+    const float* h2h_wt32 = nullptr;
+    const float* wg32 = nullptr;
 };
 // Attention.forward inference branch (attention.py:46-59) with B=1 semantics per crop.
 // feats 16-bit [B][26][256] (contextual features), fproj fp32 [B][26][256] (= i2h(feats), hoisted out of the loop),
@@ -71,6 +74,10 @@ struct AttnWeights {
 // halves live feat_lo_off elements further (value = hi + lo).
 void launch_attention(const void* feats, const float* fproj, AttnWeights w, float* preds, int B, int C, int is_f16,
                       cudaStream_t s, long feat_pitch = 0, long feat_lo_off = 0);
+
+// Range audit: largest |value| of a 16-bit tensor of `rows` pixels x `C` channels (channel pitch `pitch`), combined
+// into *slot (fp32, must be zeroed by the caller) with atomicMax on the bit pattern of the non-negative maximum.
+void launch_absmax(const void* t, long rows, int C, long pitch, int is_f16, float* slot, cudaStream_t s);
 
 // Token decode + confidence (net.py:162-167,177-190; recog_utils.py:32-47,113-119).  logits fp32 [B][26][C].
 // ids int32 [B][26]; text char [B][text_stride]; has_eos int32 [B] (CTC: always 1; Attention: 0 when no [s] was

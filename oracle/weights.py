@@ -9,7 +9,8 @@ import torch
 from lightly_ocr_b200.synth import specs
 from lightly_ocr_b200.synth import weights as _w
 from lightly_ocr_b200.synth.weights import (calibrate_craft, craft_calibrated, craft_state_dict,  # noqa: F401
-                                            crnn_calibrated, crnn_state_dict, _pca_head, _plant_ink_path)
+                                            crnn_calibrated, crnn_state_dict, has_fp32_checkpoint, _pca_head,
+                                            _plant_ink_path)
 
 
 def build_calibrations():

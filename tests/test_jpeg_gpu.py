@@ -62,8 +62,9 @@ def test_imread_and_errors(pipe, tmp_path):
     cv2.imwrite(path, img)
     assert np.array_equal(pipe.imread(path), cv2.imread(path))
     ok, png = cv2.imencode(".png", img)
+    assert np.array_equal(pipe.imdecode(png.tobytes()), img)          # PNG files take the PNG reader (test_png_gpu.py)
     with pytest.raises(bridge.LocrError, match="not a JPEG"):
-        pipe.imdecode(png.tobytes())
+        pipe.imdecode(b"GIF89a" + bytes(64))
     ok, good = cv2.imencode(".jpg", img)
     data = good.tobytes()
     with pytest.raises(bridge.LocrError):

@@ -156,6 +156,60 @@ def test_crnn_logits_and_decode(oracle_mods, act, head):
     eng.close()
 
 
+def test_fp16_range_saturation_and_audit(oracle_mods):
+    """fp16 storage has 5 exponent bits: a checkpoint whose activations exceed 65504 cannot be represented.  The path
+    (a) never produces infinities / NaNs - conversions saturate -, (b) says where the range ran out (locr_audit), and
+    (c) runs the same checkpoint with bf16 storage (LOCR_ACT_BF16, 8 exponent bits) within the bf16 tolerance.
+    Checkpoint: the synthetic CRAFT weights with the first layer's BatchNorm affine scaled by 2^15 and the (fp32) last
+    layer scaled back by 2^-15, so every 16-bit activation in between is ~3e4 times larger than usual."""
+    ocr_ref, receipts, weights = oracle_mods
+    from lightly_ocr_b200 import bridge
+    base = weights.craft_calibrated(0, ink=True)
+    sd = {k: v.clone() for k, v in base.items()}
+    k = 15
+    sd["basenet.slice1.1.weight"] *= 2.0 ** k
+    sd["basenet.slice1.1.bias"] *= 2.0 ** k
+    sd["conv_cls.8.weight"] *= 2.0 ** -k
+    img = np.ascontiguousarray(receipts.receipt(0)[40:360, 40:296])
+    with torch.no_grad():
+        x = ocr_ref.craft_preproc(img, canvas_size=10 ** 6, mag_ratio=1.0)[0]
+        taps = {}
+        ref = ocr_ref.craft_forward(sd, x, taps).numpy()
+    assert float(taps["slice1.0"].abs().max()) > 6.5e4            # beyond fp16 in the fp32 reference
+    assert np.isfinite(ref).all()
+    # (a) + (b): fp16 storage saturates instead of overflowing, and the audit names the layers that ran out of range
+    e16 = bridge.Engine(act_dtype=ACT["f16"])
+    e16.load_state_dict(bridge.MODEL_CRAFT, sd)
+    e16.audit(True)
+    got16 = e16.craft_scores(img[None])
+    rows = e16.audit_read()
+    e16.audit(False)
+    assert np.isfinite(got16).all()
+    amax = dict(rows)
+    assert len(rows) >= 24 and amax["basenet.slice1.0"] == 65504.0
+    saturated = [n for n, v in rows if v >= 65504.0]
+    print("fp16 storage: %d of %d audited layers saturated (first: %s); outputs finite, max-abs diff to fp32 %.3g" %
+          (len(saturated), len(rows), saturated[0], np.abs(got16 - ref).max()))
+    e16.close()
+    # the unscaled checkpoint has plenty of head-room (what the audit is for)
+    e0 = bridge.Engine(act_dtype=ACT["f16"])
+    e0.load_state_dict(bridge.MODEL_CRAFT, base)
+    e0.audit(True)
+    e0.craft_scores(img[None])
+    rows0 = e0.audit_read()
+    print("unscaled checkpoint: largest stored activation %.1f (%s)" % max((v, n) for n, v in rows0))
+    assert max(v for _, v in rows0) < 65504.0 / 16
+    e0.close()
+    # (c) the same checkpoint with bf16 storage: in the bf16 tolerance of the fp32 reference
+    eb = bridge.Engine(act_dtype=ACT["bf16"])
+    eb.load_state_dict(bridge.MODEL_CRAFT, sd)
+    gotb = eb.craft_scores(img[None])
+    errb = np.abs(gotb - ref).max()
+    print("bf16 storage on the large-activation checkpoint: score max-abs err %.4g" % errb)
+    assert np.isfinite(gotb).all() and errb < 6e-2
+    eb.close()
+
+
 def _word_crops(receipts, seed, n):
     """Gray crops around the first n rendered words of a synthetic receipt (ground-truth boxes + a small margin)."""
     import cv2

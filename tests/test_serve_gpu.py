@@ -90,9 +90,12 @@ def test_batched_serving_equals_one_at_a_time(tmp_path):
         cv2.imwrite(p, receipts.receipt(60 + i), [cv2.IMWRITE_JPEG_QUALITY, 90])
         jpgs.append(p)
     pp = str(d / "actually_png.jpg")
-    with open(pp, "wb") as f:                 # PNG content under a .jpg name: not for the JPEG reader, OpenCV reads it
+    with open(pp, "wb") as f:                 # PNG content under a .jpg name: told apart by the signature, GPU route as well
         f.write(cv2.imencode(".png", receipts.receipt(63)[:640, :480])[1].tobytes())
     jpgs.append(pp)
+    bm = str(d / "scan.bmp")                  # a format outside the GPU ingest: read by OpenCV on the host
+    cv2.imwrite(bm, receipts.receipt(64)[:640, :480])
+    jpgs.append(bm)
     for p in jpgs:
         res = {}
         image = cv2.imread(p)
@@ -101,5 +104,5 @@ def test_batched_serving_equals_one_at_a_time(tmp_path):
                 _, res = recognizer.process(res, cv2.cvtColor(crop, cv2.COLOR_BGR2GRAY))
         before = m.encoded_batches
         assert m.predict(p) == [v for k, v in res.items() if k > thresh], p
-        assert (m.encoded_batches == before + 1) == (p != pp)
+        assert (m.encoded_batches == before + 1) == (p != bm)
     m.close()
