@@ -83,6 +83,10 @@ struct ConvParams {
     int skip_full;      // pooled output only
     const float* tail_w;   // fused 1x1 tail (see ConvCall)
     float* tail_out;
+    // first layer from the uint8 image (ConvCall::first_u8)
+    const uint8_t* first_u8;
+    int img_h, img_w;
+    long img_row_stride, img_stride;
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
 };
 
@@ -136,8 +140,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
 // fixed at compile time, which matters for the layers whose tiles are epilogue-bound: EPI & 63 = columns per warp (32 / 16:
 // 64- / 32-column staging chunks), kEpiRes = residual add, kEpiPool = fused 2x2 max-pool, kEpiSkip = pooled output only;
 // never split-precision, fp32, fused-tail or halo-pool (those stay on the generic path).
-template <int SWZ, int HALVES, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kFirstThreads = kThreads + 128;   // + four producer warps that build the first layer's A operand
+
+template <int SWZ, int HALVES, int EPI, bool FIRST = false>
+__global__ void __launch_bounds__(FIRST ? kFirstThreads : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_p,
                const ConvParams p) {
@@ -168,33 +174,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #endif
 
     if (warp == 0 && lane == 0) {
-        ptx::tma_prefetch_desc(&tmap_x);
+        if (!FIRST) ptx::tma_prefetch_desc(&tmap_x);
         ptx::tma_prefetch_desc(&tmap_w);
         if (p.tma_store && !p.skip_full && p.tail_out == nullptr) ptx::tma_prefetch_desc(&tmap_y);
         if (p.pool) ptx::tma_prefetch_desc(&tmap_p);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], FIRST ? 4 : 1);     // FIRST: one arrival per producer warp
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
             ptx::mbar_init(&tempty_bar[a], 8);
         }
-        if (p.halo) ptx::mbar_init(&full_bar[kMaxStages - 1], 1);   // resident weights landed
+        if (p.halo || FIRST) ptx::mbar_init(&full_bar[kMaxStages - 1], 1);   // resident weights landed
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
         ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
         ptx::tmem_relinquish();
     }
+    uint16_t* lut = reinterpret_cast<uint16_t*>(bias_s + 256);                                   // FIRST: [3][256]
+    if (FIRST) {
+        // normalizeMeanVariance as a table: the 16-bit value of (v - mean[c]) / std[c] for every byte v (BGR pixels meet
+        // the RGB constants exactly as in the reference, imgproc.py:19-25)
+        const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
+        const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+            const int c = i >> 8;
+            const float f = ((float)(i & 255) - mean[c]) / stdv[c];
+            lut[i] = (uint16_t)(pack2(f, 0.f, p.is_f16) & 0xffffu);
+        }
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
+    if (FIRST && warp >= kThreads / 32) {
+        // ------------------------------------------------------------ first-layer A producer (four warps)
+        // Thread pr owns row pr of both 128-pixel halves of every tile: it gathers the 3x3x3 neighbourhood of its pixel
+        // and writes one 64-byte K-major row (k = (ky * 3 + kx) * 3 + c, 27 used) in the SWIZZLE_64B layout the MMA's
+        // shared-memory descriptor expects: 16-byte piece q of row r lives at r * 64 + ((q ^ ((r >> 1) & 3)) << 4).
+        const int pr = threadIdx.x - kThreads;
+        const int rw = pr % p.bw, rh = (pr / p.bw) % p.bh, rb = pr / (p.bw * p.bh);
+        const uint32_t full0 = ptx::smem_u32(full_bar), empty0 = ptx::smem_u32(empty_bar);
+        const uint32_t row_off = (uint32_t)pr * 64u;
+        const uint32_t sw = ((uint32_t)pr >> 1) & 3u;
+        int stage = 0;
+        uint32_t phase = 1;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            ptx::mbar_wait_a(empty0 + 8u * stage, phase, 100);
+            uint8_t* a_stage = smem_a + (size_t)stage * p.a_stage_bytes;
+#pragma unroll
+            for (int hf = 0; hf < HALVES; ++hf) {
+                const int ow = t.ow0 + (p.split_b == 2 ? hf * p.bw : 0) + rw;
+                const int oh = t.oh0 + (p.split_b == 0 ? hf * p.bh : 0) + rh;
+                const int b = t.b0 + (p.split_b == 1 ? hf * p.bb : 0) + rb;
+                uint32_t h[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = 0u;
+                if (ow < p.OW && oh < p.OH && b < p.B) {
+                    const uint8_t* img = p.first_u8 + (long)b * p.img_stride;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int y = oh + ky - 1;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int x = ow + kx - 1;
+                            uint32_t v0 = 0u, v1 = 0u, v2 = 0u;                      // conv padding: zero
+                            if (y >= 0 && y < p.OH && x >= 0 && x < p.OW) {
+                                uint32_t c0 = 0u, c1 = 0u, c2 = 0u;                  // canvas padding: raw 0
+                                if (y < p.img_h && x < p.img_w) {
+                                    const uint8_t* q = img + (long)y * p.img_row_stride + x * 3;
+                                    c0 = __ldg(q); c1 = __ldg(q + 1); c2 = __ldg(q + 2);
+                                }
+                                v0 = lut[c0]; v1 = lut[256 + c1]; v2 = lut[512 + c2];
+                            }
+                            const int k = (ky * 3 + kx) * 3;                          // compile-time after unrolling
+                            h[(k + 0) >> 1] |= v0 << (((k + 0) & 1) * 16);
+                            h[(k + 1) >> 1] |= v1 << (((k + 1) & 1) * 16);
+                            h[(k + 2) >> 1] |= v2 << (((k + 2) & 1) * 16);
+                        }
+                    }
+                }
+                uint8_t* row = a_stage + (size_t)hf * (kTileM * 64) + row_off;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            }
+            ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+    } else if (FIRST && warp == 0) {
+        // resident weights: one [64 x 32] K-major slab, once
+        if (ptx::elect_one()) {
+            const uint32_t full0 = ptx::smem_u32(full_bar);
+            ptx::mbar_arrive_expect_tx_a(full0 + 8u * (kMaxStages - 1), (uint32_t)(p.n_tile * SWZ));
+            ptx::tma_load_2d_a(ptx::smem_u32(smem_b), &tmap_w, full0 + 8u * (kMaxStages - 1), 0, 0);
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         // The WHOLE warp runs the loop on warp-uniform values and one elected lane issues the TMA instructions.  With
         // the loop inside `if (lane == 0)` ptxas cannot prove uniformity: every UTMALDG / UTCHMMA then gets wrapped in
@@ -283,7 +366,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint32_t acc_cols = (uint32_t)(HALVES * p.n_tile_alloc);
             const uint32_t idesc = p.idesc;
             constexpr uint32_t kHalfStep = (uint32_t)(kTileM * SWZ) >> 4;
-            if (p.halo) {
+            if (FIRST) {
+                // one k-block per tile (K = 32 = two K16 MMAs per half) against the resident weight slab
+                ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                    ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                    ptx::mbar_wait_a(full_s, phase, 300);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+#pragma unroll
+                            for (int hf = 0; hf < HALVES; ++hf)
+                                ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
+                                                   desc_hi, b_lo0 + k * 2, desc_hi, idesc, k ? 1u : 0u);
+                        }
+                        ptx::umma_commit_a(empty_s);
+                        ptx::umma_commit_a(tfull0 + acc * 8u);
+                    }
+                    a_lo += a_step; full_s += 8; empty_s += 8;
+                    if (full_s == full_end) {
+                        a_lo = a_lo0; full_s = full0; empty_s = empty0;
+                        phase ^= 1u;
+                    }
+                    acc ^= 1u;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+            } else if (p.halo) {
                 // A patch in smem: [18 rows][24 pixels][128 B], 128B-swizzled by the TMA unit.  Tap (kh, kw) of half hf is
                 // the same patch read from pixel (kh, kw + 8 hf) on: start address + (kh * 24 + kw + 8 hf) * 128 B,
                 // 8-pixel core groups one image row (3072 B) apart.  The tensor core applies the 128B swizzle to the
@@ -371,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < kThreads / 32) {
         // ------------------------------------------------------------ epilogue (8 warps: lane quarter x column half)
         const int ew = warp & 3;
         const int half = (warp - 4) >> 2;
@@ -433,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
-        } else if (EPI == 32 && HALVES == 2 && p.n_chunks == 1 && p.tiles_n == 1 &&
+        } else if (EPI == 32 && HALVES == 2 && (FIRST || (p.n_chunks == 1 && p.tiles_n == 1)) &&
                    !(LOCR_CONV_EXPERIMENTS && (p.dbg & 256))) {
             // ---- plain 16-bit TMA-store epilogue as TWO INDEPENDENT warpgroups.  A staging chunk costs a chain of
             // latencies (buffer free -> barrier -> TMEM load -> convert -> st.shared -> proxy fence -> barrier -> TMA
@@ -921,17 +1031,17 @@ void set_err(char* err, int errlen, const char* msg) {
     }
 }
 
-template <int SWZ, int HALVES, int EPI>
+template <int SWZ, int HALVES, int EPI, bool FIRST = false>
 cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mp,
                        const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES, EPI, FIRST>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ, HALVES, EPI><<<grid, kThreads, smem, stream>>>(mx, mw, my, mp, p);
+    conv_tc_kernel<SWZ, HALVES, EPI, FIRST><<<grid, FIRST ? kFirstThreads : kThreads, smem, stream>>>(mx, mw, my, mp, p);
     return cudaGetLastError();
 }
 
@@ -953,6 +1063,14 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     if (encode == nullptr) {
         set_err(err, errlen, "cuTensorMapEncodeTiled entry point not available");
         return cudaErrorNotSupported;
+    }
+    const bool first = c.first_u8 != nullptr;
+    if (first && (c.Cin != 32 || c.KH != 1 || c.KW != 1 || c.pad_h != 0 || c.pad_w != 0 || c.stride_h != 1 ||
+                  c.Cout != 64 || c.Cout_pad != 64 || c.out_fp32 || c.split_out || c.cin_wrap != 0 || c.pool_y != nullptr ||
+                  c.residual != nullptr || c.tail_out != nullptr || c.x_row_px != 0 || c.y_row_px != 0 ||
+                  c.OH != c.H || c.OW != c.W || c.img_h > c.H || c.img_w > c.W)) {
+        set_err(err, errlen, "conv_tc: the fused first layer is a 27(+5) -> 64 channel im2col GEMM at canvas resolution");
+        return cudaErrorInvalidValue;
     }
     int swz = 0;
     if (c.Cin % 64 == 0) swz = 128;
@@ -1027,11 +1145,12 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const bool aligned_out = (c.y_pitch * elem_) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
                                  n_tile % sc_ == 0 && (rb_ == 32 || rb_ == 64 || rb_ == 128);
         int w2 = 0, h2 = 0, b2 = 0;
-        if (allow256 && n_tile <= 128 && aligned_out) {
+        if ((allow256 || first) && n_tile <= 128 && aligned_out) {
             const long tiles256 = search(256, w2, h2, b2);
             const long n_tiles_n = c.Cout_pad / n_tile;
             // worthwhile when it wastes no more pixels than the 128-row tiling and still fills the machine
-            if (tiles256 > 0 && tiles256 * 2 <= tiles128 + tiles128 / 16 && tiles256 * n_tiles_n >= 2L * device_sm_count()) {
+            // (the fused first layer always takes M = 256 tiles: its producer and epilogue are written for them)
+            if (tiles256 > 0 && (first || (tiles256 * 2 <= tiles128 + tiles128 / 16 && tiles256 * n_tiles_n >= 2L * device_sm_count()))) {
                 halves = 2;
                 if (b2 > 1) { split_b = 1; best_bw = w2; best_bh = h2; best_bb = b2 / 2; }
                 else { split_b = 0; best_bw = w2; best_bh = h2 / 2; best_bb = b2; }
@@ -1096,7 +1215,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.tma_store = ((c.y_pitch * elem) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
                    n_tile % p.stage_cols == 0 && (p.stage_rb == 32 || p.stage_rb == 64 || p.stage_rb == 128))
                       ? 1 : 0;
-    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 2 * 128 * 128 + (pool ? 2 * 32 * 128 : 0);
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 256 * 4 + 2 * 128 * 128 + (pool ? 2 * 32 * 128 : 0) +
+                              (first ? 3 * 256 * 2 : 0);
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
@@ -1108,6 +1228,12 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.halo_pool = (halo && p.skip_full) ? 1 : 0;
     p.tail_w = c.tail_w;
     p.tail_out = c.tail_out;
+    p.first_u8 = c.first_u8; p.img_h = c.img_h; p.img_w = c.img_w;
+    p.img_row_stride = c.img_row_stride; p.img_stride = c.img_stride;
+    if (first && (halves != 2 || !p.tma_store || p.stage_cols != 64)) {
+        set_err(err, errlen, "conv_tc: the fused first layer needs M = 256 tiles and an aligned 64-channel output");
+        return cudaErrorInvalidValue;
+    }
     if (c.y_row_px > 0 && (!p.tma_store || c.residual != nullptr || pool)) {
         set_err(err, errlen, "conv_tc: row-padded outputs need the plain TMA-store epilogue");
         return cudaErrorInvalidValue;
@@ -1137,7 +1263,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 
     CUtensorMap mx, mw;
-    {
+    memset(&mx, 0, sizeof(mx));
+    if (!first) {
         const int S = p.stride2 ? 2 : 1;
         cuuint64_t dims[5] = {(cuuint64_t)(c.cin_wrap > 0 ? c.cin_wrap : c.Cin), (cuuint64_t)c.W, (cuuint64_t)S, (cuuint64_t)(c.H / S),
                               (cuuint64_t)c.B};
@@ -1245,6 +1372,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     }
     bool done = false;
     e = cudaSuccess;
+    if (first) {
+        e = launch_swz<64, 2, 32, true>(mx, mw, my, mp, p, grid, smem, stream);
+        done = true;
+    }
 #define LOCR_EPI_CASE(HV, E)                                                                       \
     if (!done && halves == HV && epi == (E)) {                                                     \
         e = launch_swz<128, HV, (E)>(mx, mw, my, mp, p, grid, smem, stream);                       \

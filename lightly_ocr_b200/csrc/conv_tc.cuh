@@ -52,6 +52,15 @@ struct ConvCall {
     // KW = 1 and pad_w = 0: 3 (or 6) k-blocks of 128-byte rows instead of 9.
     long x_row_px = 0;  // pixels per memory row of x (0 = W)
     long y_row_px = 0;  // pixels per memory row of y (0 = OW); TMA-store epilogue only
+    // First layer of CRAFT straight from the uint8 image (basenet.slice1.0 with normalizeMeanVariance, reference
+    // tools/imgproc.py:19-25, fused): when first_u8 is set, x is unused and the A operand is built inside the kernel - four
+    // producer warps gather the 3x3x3 neighbourhood of every output pixel from the packed BGR image (conv padding reads
+    // as 0, canvas padding outside the image as the normalised value of 0), normalise through a 768-entry table and
+    // write K = 27 (+5 zero) 16-bit values per pixel in the tensor core's 64-byte-swizzled K-major layout.
+    // w is then [Cout_pad][32] with k = (ky * 3 + kx) * 3 + c; H x W is the canvas (= output) size.
+    const uint8_t* first_u8 = nullptr;
+    int img_h = 0, img_w = 0;
+    long img_row_stride = 0, img_stride = 0;   // bytes per image row / per image
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).

@@ -27,7 +27,7 @@ T* dev_upload(locr_handle* h, const std::vector<T>& v) {
 // split: 0 = plain; 3 = split-precision input AND weights (K per tap [x_hi | x_lo | x_hi] against [w_hi | w_hi | w_lo]);
 //        2 = split-precision weights only, plain 16-bit input (K per tap [x | x] against [w_hi | w_lo])
 int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::string& bn, bool direct,
-              bool fold_image_std = false, int cin_pad = 0, int split = 0, bool window = false) {
+              bool fold_image_std = false, int cin_pad = 0, int split = 0, bool window = false, bool im2col = false) {
     const HostTensor* w = find(h, model, prefix + ".weight");
     if (w == nullptr || (w->shape.size() != 4 && w->shape.size() != 2))
         return h->fail(LOCR_ERR_STATE, "missing or malformed tensor " + prefix + ".weight");
@@ -117,6 +117,22 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
             h->conv[prefix] = cw;
             return LOCR_OK;
         }
+        if (im2col) {
+            // first layer as an im2col GEMM (conv_tc.cuh: first_u8): K = 32 with k = (ky * 3 + kx) * cin + c, 27 used
+            if (kh != 3 || kw != 3 || cin != 3) return h->fail(LOCR_ERR_INVALID, prefix + ": im2col layout is for the 3x3 / 3-channel first layer");
+            const int K = 32;
+            std::vector<uint16_t> w16((size_t)cw.cout_pad * K, 0);
+            for (int n = 0; n < cout; ++n)
+                for (int c = 0; c < cin; ++c)
+                    for (int t = 0; t < 9; ++t)
+                        w16[(size_t)n * K + t * cin + c] =
+                            f32_to_act((float)(w->data[((size_t)n * cin + c) * 9 + t] * scale[n]), h->cfg.act_dtype);
+            cw.cin = K; cw.cin_real = cin * 9; cw.kh = 1; cw.kw = 1;
+            cw.w = dev_upload(h, w16);
+            if (!cw.w || !cw.bias) return h->fail(LOCR_ERR_CUDA, "weight upload failed");
+            h->conv[prefix] = cw;
+            return LOCR_OK;
+        }
         if (window) {
             // 3x3 conv as KH = 3 taps over a 4-pixel window (conv_tc.cuh: x_row_px): K per tap = 4 * cpp with
             // k = dx * cpp + c for the pixel x - 1 + dx; the 4th pixel and padded channels get zero weights
@@ -185,6 +201,11 @@ struct Ctx {
     // row-padded input / output (pixels per memory row) for the NEXT tc() call (consumed by it)
     long x_row_px = 0, y_row_px = 0;
     void rows(long xr, long yr) { x_row_px = xr; y_row_px = yr; }
+    // fused first layer (conv_tc.cuh first_u8) for the NEXT tc() call (consumed by it)
+    const uint8_t* first_u8 = nullptr;
+    int first_h = 0, first_w = 0;
+    long first_row = 0, first_img = 0;
+    void first(const uint8_t* p, int ih, int iw, long row, long img) { first_u8 = p; first_h = ih; first_w = iw; first_row = row; first_img = img; }
     // split-precision residual of the NEXT tc() call (consumed by it): offset of the lo halves in elements
     long res_lo_off = 0;
     void res_split(long off) { res_lo_off = off; }
@@ -214,6 +235,8 @@ struct Ctx {
         c.bias = cw.bias; c.residual = res; c.res_pitch = res_pitch; c.relu = relu;
         c.res_lo_off = res_lo_off;
         res_lo_off = 0;
+        c.first_u8 = first_u8; c.img_h = first_h; c.img_w = first_w; c.img_row_stride = first_row; c.img_stride = first_img;
+        first_u8 = nullptr;
         c.dtype = h->cfg.act_dtype == LOCR_ACT_F16 ? ACT_F16 : ACT_BF16;
         c.cin_wrap = cw.cin_wrap;
         c.split_out = split_out;
@@ -333,6 +356,13 @@ static const char* kCraftBn[][2] = {
 int engine_finalize_craft(locr_handle* h) {
     int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16, false, true);
     if (rc != LOCR_OK) return rc;
+    // the same layer as an im2col GEMM fed straight from the uint8 image (default; LOCR_FIRST_FUSED=0 keeps the
+    // preproc + window-view form above for A/B runs)
+    h->conv["basenet.slice1.0#w"] = h->conv["basenet.slice1.0"];
+    rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 0, 0, false, true);
+    if (rc != LOCR_OK) return rc;
+    h->conv["basenet.slice1.0#im2col"] = h->conv["basenet.slice1.0"];
+    h->conv["basenet.slice1.0"] = h->conv["basenet.slice1.0#w"];
     for (auto& e : kCraftBn) {
         if (std::string(e[0]) == "conv_cls.6" || std::string(e[0]) == "conv_cls.8") continue;   // fused tail, fp32
         const bool window = std::string(e[0]) == "conv_cls.0" || std::string(e[0]) == "conv_cls.2" ||
@@ -402,12 +432,20 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     if (c.rc != LOCR_OK) return c.rc;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
 
-    void* x16 = c.buf("x16", (size_t)B * H * (W + 3) * 16 * 2);   // rows padded: [zero | W pixels | zero zero]
-    if (c.rc != LOCR_OK) return c.rc;
-    { ProfScope ps_(h, "preproc_nhwc16", 0, false); launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s); }
-    h->launches++;
-    c.rows(W + 3, 0);
-    c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 0);   // 4-pixel window view: KW taps are one TMA row
+    static int first_fused = -1;
+    if (first_fused < 0) { const char* e = getenv("LOCR_FIRST_FUSED"); first_fused = e ? atoi(e) : 1; }
+    if (first_fused) {
+        // normalizeMeanVariance + basenet.slice1.0 + BN + ReLU in one kernel, straight from the uint8 image
+        c.first(d_images, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3);
+        c.tc("basenet.slice1.0#im2col", d_images, B, H, W, 32, a0, 64, 1, 0, 0);
+    } else {
+        void* x16 = c.buf("x16", (size_t)B * H * (W + 3) * 16 * 2);   // rows padded: [zero | W pixels | zero zero]
+        if (c.rc != LOCR_OK) return c.rc;
+        { ProfScope ps_(h, "preproc_nhwc16", 0, false); launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x16, f16, s); }
+        h->launches++;
+        c.rows(W + 3, 0);
+        c.tc("basenet.slice1.0", x16, B, H, W, 16, a0, 64, 1, 1, 0);   // 4-pixel window view: KW taps are one TMA row
+    }
     c.pool(p1, 64, 1);   // MaxPool2d(2, 2) fused into the epilogue; the full-resolution tensor is never needed
     c.tc("basenet.slice1.3", a0, B, H, W, 64, nullptr, 64, 1, 1, 1);
     c.tc("basenet.slice1.7", p1, B, H2, W2, 64, a2, 128, 1, 1, 1);
