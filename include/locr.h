@@ -185,7 +185,7 @@ LOCR_API int locr_test_conv_pool(const locr_conv_desc* d, const float* x, const 
  * (direction*1024 + gate*256 + unit, gates i, f, g, o); out [B][T][512] fp32 (forward | backward hidden states).
  * iters > 0 also times `iters` launches with CUDA events (ms per launch). */
 LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
-                            float* ms_per_iter);
+                            float* ms_per_iter, int split);
 
 /* CRAFT forward only: bgr uint8 [B][img_h][img_w][3] packed -> score fp32 [B][H32/2][W32/2][2]. */
 LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score);

@@ -42,7 +42,7 @@ def lib():
                                              C.c_void_p]
         _lib.locr_test_lstm.restype = C.c_int
         _lib.locr_test_lstm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                        C.POINTER(C.c_float)]
+                                        C.POINTER(C.c_float), C.c_int]
         _lib.locr_test_jpeg_coefficients.restype = C.c_int
         _lib.locr_test_jpeg_coefficients.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         _lib.locr_jpeg_info.restype = C.c_int
@@ -159,16 +159,17 @@ def test_conv_pool(x, w, bias=None, *, pad=(1, 1), relu=True, act_dtype=0, n_til
     return y, yp
 
 
-def test_lstm(xproj, whh, act_dtype=0, iters=0):
+def test_lstm(xproj, whh, act_dtype=0, iters=0, split=0):
     """The BiLSTM recurrence kernel alone: xproj [B,T,2048] fp32 (W_ih x + biases, PyTorch row order), whh [2,1024,256]
-    -> hidden states [B,T,512] fp32 (and ms per launch when iters > 0)."""
+    -> hidden states [B,T,512] fp32 (and ms per launch when iters > 0).  split=1: the split-precision feedback of
+    LOCR_PREC_EXACT (h carried as hi + lo; the returned states are hi + lo)."""
     xproj = np.ascontiguousarray(xproj, np.float32)
     whh = np.ascontiguousarray(whh, np.float32)
     B, T, n = xproj.shape
     assert n == 2048 and whh.shape == (2, 1024, 256)
     out = np.zeros((B, T, 512), np.float32)
     ms = C.c_float(0)
-    _check(lib().locr_test_lstm(_fptr(xproj), _fptr(whh), B, T, act_dtype, _fptr(out), iters, C.byref(ms)))
+    _check(lib().locr_test_lstm(_fptr(xproj), _fptr(whh), B, T, act_dtype, _fptr(out), iters, C.byref(ms), int(split)))
     return (out, ms.value) if iters > 0 else out
 
 

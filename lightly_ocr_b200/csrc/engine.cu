@@ -248,8 +248,9 @@ struct Ctx {
         x_row_px = 0; y_row_px = 0;
         char err[256] = {0};
         cudaError_t e;
+        const std::string shown = layer.substr(0, layer.find('#'));   // "layer#variant" is reported under the layer's name
         {
-            ProfScope ps(h, layer, 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin_real * cw.kh * cw.kw, true);
+            ProfScope ps(h, shown, 2.0 * B * c.OH * c.OW * (double)cw.cout * cw.cin_real * cw.kh * cw.kw, true);
             e = conv_tc_launch(c, h->stream, err, sizeof(err));
         }
         h->launches++;
@@ -265,7 +266,7 @@ struct Ctx {
                                      : (long)B * c.OH * (c.y_row_px > 0 ? c.y_row_px : c.OW);
             if (t != nullptr) {
                 launch_absmax(t, rows, cw.cout / 8 * 8, pitch, h->is_f16(), h->audit_slots + h->audit_names.size(), h->stream);
-                h->audit_names.push_back(layer);
+                h->audit_names.push_back(shown);
                 h->launches++;
             }
         }
@@ -356,8 +357,7 @@ static const char* kCraftBn[][2] = {
 int engine_finalize_craft(locr_handle* h) {
     int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16, false, true);
     if (rc != LOCR_OK) return rc;
-    // the same layer as an im2col GEMM fed straight from the uint8 image (default; LOCR_FIRST_FUSED=0 keeps the
-    // preproc + window-view form above for A/B runs)
+    // the same layer as an im2col GEMM fed straight from the uint8 image (experiment, LOCR_FIRST_FUSED=1)
     h->conv["basenet.slice1.0#w"] = h->conv["basenet.slice1.0"];
     rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 0, 0, false, true);
     if (rc != LOCR_OK) return rc;
@@ -433,9 +433,12 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
 
     static int first_fused = -1;
-    if (first_fused < 0) { const char* e = getenv("LOCR_FIRST_FUSED"); first_fused = e ? atoi(e) : 1; }
+    if (first_fused < 0) { const char* e = getenv("LOCR_FIRST_FUSED"); first_fused = e ? atoi(e) : 0; }
     if (first_fused) {
-        // normalizeMeanVariance + basenet.slice1.0 + BN + ReLU in one kernel, straight from the uint8 image
+        // EXPERIMENT (off by default, LOCR_FIRST_FUSED=1): normalizeMeanVariance + basenet.slice1.0 + BN + ReLU in one
+        // kernel, straight from the uint8 image.  Measured on B200: 1.15 ms per 8 canvases against 0.47 + 0.11 ms for
+        // preproc + the window-view layer - four producer warps gathering 27 bytes per pixel from global memory are
+        // latency-bound (~3300 cycles per 256-pixel tile); see DESIGN.md "measured and rejected".
         c.first(d_images, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3);
         c.tc("basenet.slice1.0#im2col", d_images, B, H, W, 32, a0, 64, 1, 0, 0);
     } else {
@@ -594,9 +597,8 @@ int engine_finalize_crnn(locr_handle* h) {
         // exact: layer 0 reads the split-precision visual features, layer 1 the split-precision output of linear 0
         if ((rc = F(name, ""))) return rc;
         h->lstm_whh[l] = dev_upload(h, whh);
-        // the Linear after the recurrence reads plain 16-bit hidden states: exact mode splits its weights only
-        if ((rc = fold_conv(h, M, "SequenceModeling." + std::to_string(l) + ".linear", "", false, false, 0, X ? 2 : 0)))
-            return rc;
+        // exact: the recurrence emits its hidden states as hi + lo pairs too (lstm_tc.cu SPLIT)
+        if ((rc = F("SequenceModeling." + std::to_string(l) + ".linear", ""))) return rc;
     }
     if (h->cfg.head == LOCR_HEAD_CTC) {
         if ((rc = F("Prediction", ""))) return rc;
@@ -691,7 +693,7 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     float* grid = (float*)c.buf("crnn.grid", (size_t)B * 3200 * 2 * 4);
     void* vis = c.buf("crnn.visual", (size_t)B * 26 * P(512) * 2);
     float* xproj = (float*)c.buf("crnn.xproj", (size_t)B * 26 * 2048 * 4);
-    void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * 512 * 2);
+    void* hcat = c.buf("crnn.hcat", (size_t)B * 26 * P(512) * 2);
     void* s0 = c.buf("crnn.s0", (size_t)B * 26 * P(256) * 2);
     void* s1 = c.buf("crnn.contextual", (size_t)B * 26 * P(256) * 2);
     const int C = h->cfg.num_classes;
@@ -783,17 +785,17 @@ int engine_crnn_forward(locr_handle* h, const float* d_x, int B, float** logits)
     c.tc("lstm0.xproj", vis, 1, 1, R, P(512), xproj, 2048, 0, 0, 0, 1, 1, 1);
     if (c.rc == LOCR_OK) {
         ProfScope ps_(h, "lstm", 0, false);
-        if (launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s) != cudaSuccess)
+        if (launch_lstm_tc(xproj, h->lstm_whh[0], hcat, B, 26, f16, s, X) != cudaSuccess)
             c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     }
-    c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, 512, s0, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
+    c.tc("SequenceModeling.0.linear", hcat, 1, 1, R, P(512), s0, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
     c.tc("lstm1.xproj", s0, 1, 1, R, P(256), xproj, 2048, 0, 0, 0, 1, 1, 1);
     if (c.rc == LOCR_OK) {
         ProfScope ps_(h, "lstm", 0, false);
-        if (launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s) != cudaSuccess)
+        if (launch_lstm_tc(xproj, h->lstm_whh[1], hcat, B, 26, f16, s, X) != cudaSuccess)
             c.rc = h->fail(LOCR_ERR_CUDA, "BiLSTM launch failed");
     }
-    c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, 512, s1, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
+    c.tc("SequenceModeling.1.linear", hcat, 1, 1, R, P(512), s1, P(256), 0, 0, 0, 1, 1, 0, nullptr, 0, X);
     h->launches += 2;
     if (h->cfg.head == LOCR_HEAD_CTC) {
         c.tc("Prediction", s1, 1, 1, R, P(256), lg, C, 0, 0, 0, 1, 1, 1);

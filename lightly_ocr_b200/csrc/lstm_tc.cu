@@ -49,8 +49,9 @@ constexpr int kEpiWarps = 8;
 
 struct LstmParams {
     const float* xproj;   // [B][T][2048], column = dir*1024 + unit*4 + gate
-    uint16_t* out;        // [B][T][512]
+    uint16_t* out;        // [B][T][pitch]: 512 hidden states (+ their 512 lo halves in split-precision mode)
     int B, T, is_f16;
+    int pitch;            // 512, or 1024 when SPLIT
     uint32_t idesc;
 };
 
@@ -72,9 +73,14 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b, int f16) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// SPLIT (LOCR_PREC_EXACT): h_t is carried as a hi + lo pair of 16-bit numbers - both halves go to the layer output
+// ([hi 512 | lo 512] per time step) and both are pulled back as A operands (buffer 0 = hi, buffer 1 = lo; a single
+// buffer per half is enough: the MMAs of step s have retired before any epilogue warp can publish h_s), so the step's
+// GEMM is h_hi W^T + h_lo W^T and the 26-step feedback no longer rounds h to 11 bits.
+template <bool SPLIT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsLstm, 1)
 lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                    const LstmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_hlo, const LstmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -96,6 +102,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmap_w);
         ptx::tma_prefetch_desc(&tmap_h);
+        if (SPLIT) ptx::tma_prefetch_desc(&tmap_hlo);
     }
     if (warp == 1 && lane == 0) {
         ptx::mbar_init(wfull_bar, 1);
@@ -133,11 +140,22 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
             LSTM_STAMP(step, 0);                      // all 64 arrivals seen
             if (ptx::elect_one()) {
                 ptx::fence_proxy_async_all();
+                if (SPLIT) {
 #pragma unroll
-                for (int kc = 0; kc < 4; ++kc) {
-                    ptx::mbar_arrive_expect_tx(&afull_bar[b * 4 + kc], kChunkBytes);
-                    ptx::tma_load_3d(a_buf + b * kABytes + kc * kChunkBytes, &tmap_h, &afull_bar[b * 4 + kc],
-                                     dir * 256 + kc * 64, t_prev, crop0);
+                    for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) {
+                            ptx::mbar_arrive_expect_tx(&afull_bar[hl * 4 + kc], kChunkBytes);
+                            ptx::tma_load_3d(a_buf + hl * kABytes + kc * kChunkBytes, hl ? &tmap_hlo : &tmap_h,
+                                             &afull_bar[hl * 4 + kc], dir * 256 + kc * 64, t_prev, crop0);
+                        }
+                } else {
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        ptx::mbar_arrive_expect_tx(&afull_bar[b * 4 + kc], kChunkBytes);
+                        ptx::tma_load_3d(a_buf + b * kABytes + kc * kChunkBytes, &tmap_h, &afull_bar[b * 4 + kc],
+                                         dir * 256 + kc * 64, t_prev, crop0);
+                    }
                 }
             }
         }
@@ -149,6 +167,26 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         for (int step = 1; step < T; ++step) {
             const int b = step & 1;
             const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
+            if (SPLIT) {
+                // both buffers every step: the barriers' phase flips once per step
+                const uint32_t par_s = (uint32_t)((step - 1) & 1);
+#pragma unroll
+                for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        ptx::mbar_wait(&afull_bar[hl * 4 + kc], par_s, 610);
+                        ptx::tc_fence_after();
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((hl * kABytes + kc * kChunkBytes) >> 4);
+                        const uint32_t w_lo = w_lo0 + (uint32_t)((kc * kChunkBytes) >> 4);
+                        if (ptx::elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_f16_lohi(tmem_base, a_lo + k * 2, desc_hi, w_lo + k * 2, desc_hi, p.idesc,
+                                                   (hl | kc | k) ? 1u : 0u);
+                            if (hl == 1 && kc == 3) ptx::umma_commit(tfull_bar);
+                        }
+                    }
+            } else {
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
                 ptx::mbar_wait(&afull_bar[b * 4 + kc], par, 610);
@@ -165,6 +203,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                 if (kc == 0) LSTM_STAMP(step, 1);     // first h chunk landed
                 if (kc == 3) LSTM_STAMP(step, 2);     // last chunk landed, MMAs issued
             }
+            }
         }
     } else if (warp >= 4) {
         const int quarter = warp & 3;                 // TMEM lane quarter
@@ -174,7 +213,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
         const bool valid = crop < p.B;
         const int ucol = rank * 32 + chalf * 16;      // first hidden unit of this thread
         const float* xp_base = p.xproj + (size_t)(valid ? crop : 0) * T * 2048 + dir * 1024 + ucol * 4;
-        uint16_t* out_base = p.out + (size_t)(valid ? crop : 0) * T * 512 + dir * 256 + ucol;
+        uint16_t* out_base = p.out + (size_t)(valid ? crop : 0) * T * p.pitch + dir * 256 + ucol;
         uint32_t hready_remote[2] = {0, 0};
         if (lane < kCluster) {
             hready_remote[0] = ptx::mapa(ptx::smem_u32(&hready_bar[0]), (uint32_t)lane);
@@ -197,7 +236,7 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                 ptx::tc_fence_after();
             }
             if (warp == 4) LSTM_STAMP(step, 3);       // accumulator complete
-            uint32_t hp[8];
+            uint32_t hp[8], hl_[8];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t r[32];
@@ -221,13 +260,25 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
                     hv[u] = go * tanh_f(c);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) hp[hf * 4 + q] = pack2h(hv[q * 2], hv[q * 2 + 1], p.is_f16);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t hi = pack2h(hv[q * 2], hv[q * 2 + 1], p.is_f16);
+                    hp[hf * 4 + q] = hi;
+                    if (SPLIT) {
+                        const float2 back = p.is_f16 ? __half22float2(*reinterpret_cast<const __half2*>(&hi))
+                                                     : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi));
+                        hl_[hf * 4 + q] = pack2h(hv[q * 2] - back.x, hv[q * 2 + 1] - back.y, p.is_f16);
+                    }
+                }
             }
             if (warp == 4) LSTM_STAMP(step, 4);       // gate math done
             if (valid) {
-                uint4* o = reinterpret_cast<uint4*>(out_base + (size_t)t * 512);
+                uint4* o = reinterpret_cast<uint4*>(out_base + (size_t)t * p.pitch);
                 o[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 o[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                if (SPLIT) {
+                    o[64] = make_uint4(hl_[0], hl_[1], hl_[2], hl_[3]);      // + 512 elements
+                    o[65] = make_uint4(hl_[4], hl_[5], hl_[6], hl_[7]);
+                }
             }
             if (step + 1 < T) {
                 // h_t is in global memory (generic proxy); the peers read it through TMA (async proxy)
@@ -262,7 +313,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, int B, int T, int is_f16,
-                           cudaStream_t s) {
+                           cudaStream_t s, int split) {
     static EncodeTiledFn encode = nullptr;
     if (encode == nullptr) {
         void* fp = nullptr;
@@ -274,7 +325,8 @@ cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, 
     }
     if (B <= 0 || T <= 0) return cudaErrorInvalidValue;
     const CUtensorMapDataType dt = is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    CUtensorMap mw, mh;
+    CUtensorMap mw, mh, mhlo;
+    const int pitch = split ? 1024 : 512;
     {
         cuuint64_t dims[2] = {256, 2048};
         cuuint64_t strides[1] = {512};
@@ -288,26 +340,34 @@ cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, 
     {
         // layer output [B][T][512] viewed as (column, t, crop); one box = 64 units of one time step for 128 crops
         cuuint64_t dims[3] = {512, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t strides[2] = {1024, (cuuint64_t)T * 1024};
+        cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)T * pitch * 2};
         cuuint32_t box[3] = {64, 1, 128};
         cuuint32_t estr[3] = {1, 1, 1};
         if (encode(&mh, dt, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
+        mhlo = mh;
+        if (split && encode(&mhlo, dt, 3, (uint16_t*)out + 512, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
     }
     static bool attr = false;
     const size_t smem = 1024 + kWBytes + 2 * kABytes + 16 * 8;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(lstm_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(lstm_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     LstmParams p;
-    p.xproj = xproj; p.out = (uint16_t*)out; p.B = B; p.T = T; p.is_f16 = is_f16;
+    p.xproj = xproj; p.out = (uint16_t*)out; p.B = B; p.T = T; p.is_f16 = is_f16; p.pitch = pitch;
     p.idesc = ptx::make_idesc_f16(is_f16 ? 0 : 1, 128, 128);
     dim3 grid(kCluster * ((B + 127) / 128), 2);
-    lstm_cluster_kernel<<<grid, kThreadsLstm, smem, s>>>(mw, mh, p);
+    if (split) lstm_cluster_kernel<true><<<grid, kThreadsLstm, smem, s>>>(mw, mh, mhlo, p);
+    else lstm_cluster_kernel<false><<<grid, kThreadsLstm, smem, s>>>(mw, mh, mhlo, p);
     return cudaGetLastError();
 }
 

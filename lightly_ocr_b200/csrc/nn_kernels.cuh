@@ -51,8 +51,9 @@ void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* 
 //   xproj    fp32 [B][T][2048] = x W_ih^T + b_ih + b_hh, column = dir*1024 + unit*4 + gate (gate order i, f, g, o)
 //   whh_perm 16-bit [2 dirs * 1024][256], rows in the same (unit, gate) order
 //   out      16-bit [B][T][512] (forward | backward); also the medium through which the cluster exchanges h_t
+//   split    LOCR_PREC_EXACT: out is [B][T][1024] = [hi 512 | lo 512], h_t is fed back as hi + lo (two GEMMs per step)
 cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, int B, int T, int is_f16,
-                           cudaStream_t s);
+                           cudaStream_t s, int split = 0);
 
 struct AttnWeights {
     const uint16_t* h2h_wt;  // 16-bit [256 k][256 j]

@@ -205,7 +205,7 @@ LOCR_API int locr_conv_trace(unsigned long long* out, int* counts) {
 /* The BiLSTM recurrence kernel alone.  xproj [B][T][2048] fp32 and whh [2][1024][256] fp32 come in PyTorch's row order
  * (dir*1024 + gate*256 + unit); out [B][T][512] fp32.  iters > 0 additionally times `iters` launches (ms per launch). */
 LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
-                            float* ms_per_iter) {
+                            float* ms_per_iter, int split) {
     if (xproj == nullptr || whh == nullptr || out == nullptr || B <= 0 || T <= 0) return fail(LOCR_ERR_INVALID, "bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -224,7 +224,8 @@ LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, 
             for (int np = 0; np < 1024; ++np)
                 xp[row * 2048 + d * 1024 + np] = xproj[row * 2048 + d * 1024 + (np & 3) * 256 + (np >> 2)];
     DevBuf dx, dw, dy;
-    const size_t ny = (size_t)B * T * 512;
+    const int pitch = split ? 1024 : 512;
+    const size_t ny = (size_t)B * T * pitch;
     LOCR_CUDA_OK(dx.alloc(nx * 4));
     LOCR_CUDA_OK(dw.alloc(w16.size() * 2));
     LOCR_CUDA_OK(dy.alloc(ny * 2));
@@ -232,18 +233,21 @@ LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, 
     LOCR_CUDA_OK(cudaMemcpy(dw.p, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
     LOCR_CUDA_OK(cudaMemset(dy.p, 0xff, ny * 2));
     const int f16 = act_dtype == LOCR_ACT_F16 ? 1 : 0;
-    cudaError_t e = launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0);
+    cudaError_t e = launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0, split);
     if (e != cudaSuccess) return fail(LOCR_ERR_CUDA, cudaGetErrorString(e));
     LOCR_CUDA_OK(cudaDeviceSynchronize());
     std::vector<uint16_t> hy(ny);
     LOCR_CUDA_OK(cudaMemcpy(hy.data(), dy.p, ny * 2, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < ny; ++i) out[i] = act_to_f32(hy[i], act_dtype);
+    for (size_t r = 0; r < (size_t)B * T; ++r)
+        for (int j = 0; j < 512; ++j)
+            out[r * 512 + j] = act_to_f32(hy[r * pitch + j], act_dtype) +
+                               (split ? act_to_f32(hy[r * pitch + 512 + j], act_dtype) : 0.f);
     if (iters > 0 && ms_per_iter != nullptr) {
         cudaEvent_t e0, e1;
         LOCR_CUDA_OK(cudaEventCreate(&e0));
         LOCR_CUDA_OK(cudaEventCreate(&e1));
         LOCR_CUDA_OK(cudaEventRecord(e0, 0));
-        for (int i = 0; i < iters; ++i) launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0);
+        for (int i = 0; i < iters; ++i) launch_lstm_tc(dx.as<float>(), dw.p, dy.p, B, T, f16, 0, split);
         LOCR_CUDA_OK(cudaEventRecord(e1, 0));
         LOCR_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0;

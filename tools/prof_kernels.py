@@ -44,5 +44,10 @@ else:
     r = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
     r.load_state_dict(bridge.MODEL_CRAFT, weights.craft_calibrated(0, ink=True))
     r.load_state_dict(bridge.MODEL_CRNN, weights.crnn_calibrated(1, "CTC"))
-    per_image, out = r.ocr([receipts.receipt(i) for i in range(8)])
+    imgs = [receipts.receipt(i) for i in range(8)]
+    per_image, out = r.ocr(imgs)
     print("%d crops, first strings %s" % (len(out["text"]), out["text"][:5]))
+    # the ingest kernels: the same receipts as PNG and JPEG files through locr_detect_encoded
+    import cv2
+    r.ocr_encoded([cv2.imencode(".png", im)[1].tobytes() for im in imgs[:4]] +
+                  [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in imgs[4:]])
