@@ -109,6 +109,17 @@ LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, co
                                   float* logits, int32_t* token_ids, char* text, int32_t* has_eos, float* conf,
                                   uint8_t* resized_u8);
 
+/* tools.getDetBoxes(textmap, linkmap, text_threshold, link_threshold, low_text, poly) (det_utils.py:248-256) on B host
+ * score maps [B][H][W][2] (text, link interleaved): `boxes` receives the float32 corners of det_boxes_core (:35-94) in
+ * score-map coordinates, [B][max_boxes][4][2], `counts[b]` their number.  With poly != 0 the polygon path poly_core
+ * (:97-245, what CRAFT.enablePoly switches on) runs as well: `polys` [B][max_boxes][14][2] float64 and `poly_valid`
+ * [B][max_boxes] (1 = polygon, 0 = the reference's None).  Note: the reference's CRAFT.getCoords overwrites the
+ * polygons with the boxes before using them (net.py:86-87), so enablePoly never changes what CRAFT.process returns;
+ * this entry point serves callers of getDetBoxes itself. */
+LOCR_API int locr_get_det_boxes(locr_handle* h, const float* score, int B, int H, int W, float text_threshold,
+                                float link_threshold, float low_text, int poly, int max_boxes, float* boxes,
+                                int32_t* counts, double* polys, int32_t* poly_valid);
+
 /* locr_detect on the images left resident on the device by the previous locr_detect call (no host-to-device copy). */
 LOCR_API int locr_detect_resident(locr_handle* h, int max_boxes_total, int32_t* rects, float* boxes,
                                   int32_t* box_counts, float* score_maps);

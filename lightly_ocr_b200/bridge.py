@@ -314,6 +314,9 @@ def _bind_pipeline(L):
     L.locr_debug_postproc.restype = C.c_int
     L.locr_debug_postproc.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp, vp,
                                       vp, vp]
+    L.locr_get_det_boxes.restype = C.c_int
+    L.locr_get_det_boxes.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                     vp, vp, vp, vp]
     L.locr_debug_resize.restype = C.c_int
     L.locr_debug_resize.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]
     L.locr_imdecode.restype = C.c_int
@@ -448,6 +451,25 @@ class Pipeline(Engine):
             out.append(dict(boxes=boxes[b, :k].copy(), rects=rects[b, :k].copy(), box_label=lab[b, :k].copy(),
                             n_components=int(counts[b, 1]), labels=None if labels is None else labels[b]))
         return out
+
+    def get_det_boxes(self, textmap, linkmap, text_threshold=0.7, link_threshold=0.4, low_text=0.4, poly=False,
+                      max_boxes=4096):
+        """tools.getDetBoxes of the reference (ocr/tools/det_utils.py:248-256): (boxes, polys) for one pair of score
+        maps - boxes as a list of float32 [4, 2] arrays in score-map coordinates, polys as a list holding a float64
+        [14, 2] array or None per box (all None when poly is False)."""
+        score = np.ascontiguousarray(np.stack([np.asarray(textmap, np.float32), np.asarray(linkmap, np.float32)], -1))
+        H, W, _ = score.shape
+        boxes = np.empty((max_boxes, 4, 2), np.float32)
+        counts = np.zeros(1, np.int32)
+        polys = np.empty((max_boxes, 14, 2), np.float64) if poly else None
+        valid = np.zeros(max_boxes, np.int32) if poly else None
+        _check(self.L.locr_get_det_boxes(self.h, _fptr(score), 1, H, W, text_threshold, link_threshold, low_text,
+                                         int(bool(poly)), max_boxes, _fptr(boxes), _fptr(counts), _fptr(polys),
+                                         _fptr(valid)), self.h)
+        n = int(counts[0])
+        out_b = [boxes[i].copy() for i in range(n)]
+        out_p = [polys[i].copy() if (poly and valid[i]) else None for i in range(n)]
+        return out_b, out_p
 
     def resize_linear(self, img, out_w, out_h):
         img = np.ascontiguousarray(img, np.uint8)

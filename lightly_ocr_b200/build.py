@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
 ] + os.environ.get("LOCR_NVCC_EXTRA", "").split()
 # Translation units whose float arithmetic must match cv2 / PIL / numpy bit for bit: no FMA contraction.
-EXACT_UNITS = {"postproc.cu", "imgops.cu"}
+EXACT_UNITS = {"postproc.cu", "imgops.cu", "polys.cu"}
 
 
 def _nvcc():

@@ -8,6 +8,7 @@
 #include "imgops.cuh"
 #include "jpeg.cuh"
 #include "png.cuh"
+#include "polys.cuh"
 #include "postproc.cuh"
 
 using namespace locr;
@@ -459,6 +460,58 @@ LOCR_API int locr_debug_postproc(locr_handle* h, const float* score, int B, int 
     LOCR_CUDA_OK(cudaMemcpyAsync(counts, d_counts, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
     if (labels) LOCR_CUDA_OK(cudaMemcpyAsync(labels, d_labels, npix * 4, cudaMemcpyDeviceToHost, s));
     LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    return LOCR_OK;
+}
+
+/* getDetBoxes(textmap, linkmap, text_threshold, link_threshold, low_text, poly) of the reference's tools package
+ * (det_utils.py:248-256) on host score maps: boxes in score-map coordinates (det_boxes_core) and, with poly != 0, the
+ * polygon of every box (poly_core, :97-245) or "none". */
+LOCR_API int locr_get_det_boxes(locr_handle* h, const float* score, int B, int H, int W, float text_threshold,
+                                float link_threshold, float low_text, int poly, int max_boxes, float* boxes,
+                                int32_t* counts, double* polys, int32_t* poly_valid) {
+    if (h == nullptr || score == nullptr || B <= 0 || max_boxes <= 0 || boxes == nullptr || counts == nullptr ||
+        (poly && (polys == nullptr || poly_valid == nullptr)))
+        return fail(LOCR_ERR_INVALID, "locr_get_det_boxes: bad argument");
+    LOCR_CUDA_OK(cudaSetDevice(h->cfg.device_id));
+    cudaStream_t s = h->stream;
+    const size_t npix = (size_t)B * H * W;
+    float* d_sc = (float*)engine_buffer(h, "score", npix * 2 * 4);
+    void* ws = engine_buffer(h, "pp.ws", postproc_workspace_bytes(B, H, W));
+    float* d_boxes = (float*)engine_buffer(h, "pp.boxes", (size_t)B * max_boxes * 8 * 4);
+    int32_t* d_rects = (int32_t*)engine_buffer(h, "pp.rects", (size_t)B * max_boxes * 4 * 4);
+    int32_t* d_lab = (int32_t*)engine_buffer(h, "pp.lab", (size_t)B * max_boxes * 4);
+    int32_t* d_counts = (int32_t*)engine_buffer(h, "pp.counts", (size_t)B * 2 * 4);
+    int32_t* d_labels = poly ? (int32_t*)engine_buffer(h, "pp.labels", npix * 4) : nullptr;
+    double* d_polys = poly ? (double*)engine_buffer(h, "pp.polys", (size_t)B * max_boxes * 28 * 8) : nullptr;
+    int32_t* d_pvalid = poly ? (int32_t*)engine_buffer(h, "pp.pvalid", (size_t)B * max_boxes * 4) : nullptr;
+    if (!d_sc || !ws || !d_boxes || !d_rects || !d_lab || !d_counts || (poly && (!d_labels || !d_polys || !d_pvalid)))
+        return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_sc, score, npix * 8, cudaMemcpyHostToDevice, s));
+    PostprocParams pp;
+    pp.B = B; pp.H = H; pp.W = W;
+    pp.low_text = low_text; pp.link_threshold = link_threshold; pp.text_threshold = text_threshold;
+    pp.scale_x = 2.0; pp.scale_y = 2.0; pp.max_boxes = max_boxes;
+    const int nl = launch_postproc(d_sc, pp, ws, d_boxes, d_rects, d_lab, d_counts, d_labels, s);
+    if (nl < 0) return h->fail(LOCR_ERR_INVALID, "score map larger than 1024 x 1024");
+    h->launches += nl;
+    if (poly) {
+        ProfScope ps_(h, "polys", 0, false);
+        launch_polys(d_boxes, d_lab, d_counts, d_labels, B, H, W, max_boxes, d_polys, d_pvalid, s);
+        h->launches++;
+    }
+    LOCR_CUDA_OK(cudaGetLastError());
+    std::vector<int32_t> c2((size_t)B * 2);
+    LOCR_CUDA_OK(cudaMemcpyAsync(c2.data(), d_counts, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(boxes, d_boxes, (size_t)B * max_boxes * 32, cudaMemcpyDeviceToHost, s));
+    if (poly) {
+        LOCR_CUDA_OK(cudaMemcpyAsync(polys, d_polys, (size_t)B * max_boxes * 28 * 8, cudaMemcpyDeviceToHost, s));
+        LOCR_CUDA_OK(cudaMemcpyAsync(poly_valid, d_pvalid, (size_t)B * max_boxes * 4, cudaMemcpyDeviceToHost, s));
+    }
+    LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b) {
+        if (c2[2 * b] > max_boxes) return h->fail(LOCR_ERR_CAPACITY, "locr_get_det_boxes: max_boxes too small");
+        counts[b] = c2[2 * b];
+    }
     return LOCR_OK;
 }
 

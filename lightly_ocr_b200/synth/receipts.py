@@ -2,6 +2,7 @@
 
 receipt(seed)        white 1280x960 BGR "receipt" with ~70 rendered words (cv2.putText), config 2/4/5
 score_maps(seed)     synthetic region/affinity score-map pairs for bit-exact post-processing tests
+curved_score_maps(seed)  the same for words on wavy base lines (the polygon path, det_utils.py:97-245)
 crops(n, seed)       gray uint8 crops of ragged sizes, config 3
 """
 import cv2
@@ -89,3 +90,34 @@ def crops(n=512, seed=3):
         x0 = int(np.clip(x + rng.integers(-10, 11), 0, gray.shape[1] - w))
         out.append(np.ascontiguousarray(gray[y0:y0 + h, x0:x0 + w]))
     return out
+
+
+def curved_score_maps(seed=0, height=480, width=640, n_words=12):
+    """Score-map pairs of words whose characters follow a sine-shaped base line: character blobs in the text map,
+    blobs between neighbouring characters in the link map.  About half of the resulting boxes are curved enough for the
+    reference's poly_core to produce a polygon, the others exercise its early exits."""
+    rng = np.random.default_rng(int(seed))
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    text = np.zeros((height, width), np.float32)
+    link = np.zeros((height, width), np.float32)
+    for _ in range(n_words):
+        cx0, cy0 = rng.uniform(60, width - 200), rng.uniform(60, height - 60)
+        nchar = int(rng.integers(4, 10))
+        pitch = rng.uniform(14, 22)
+        amp = rng.uniform(0, 14) * (1 if rng.random() < 0.7 else 0)
+        period = rng.uniform(80, 200)
+        ch = rng.uniform(5, 9)
+        pts = []
+        for i in range(nchar):
+            x = cx0 + i * pitch
+            y = cy0 + amp * np.sin(2 * np.pi * i * pitch / period)
+            pts.append((x, y))
+            g = np.exp(-(((xx - np.float32(x)) ** 2) / np.float32(2 * (pitch * 0.28) ** 2) +
+                         ((yy - np.float32(y)) ** 2) / np.float32(2 * ch ** 2)))
+            text = np.maximum(text, (np.float32(rng.uniform(0.8, 1.0)) * g).astype(np.float32))
+        for (x0, y0), (x1, y1) in zip(pts[:-1], pts[1:]):
+            x, y = (x0 + x1) / 2, (y0 + y1) / 2
+            g = np.exp(-(((xx - np.float32(x)) ** 2) / np.float32(2 * (pitch * 0.3) ** 2) +
+                         ((yy - np.float32(y)) ** 2) / np.float32(2 * (ch * 0.6) ** 2)))
+            link = np.maximum(link, (np.float32(0.8) * g).astype(np.float32))
+    return text, link

@@ -4,10 +4,12 @@
 synthetic checkpoints of oracle/weights.py, and its outputs are committed as small fixtures.  The reference sources
 are staged in a scratch directory under /tmp by oracle/ref_env.py (shims and staging are documented there).
 
-Usage:  python -m oracle.make_golden [--keep-calib] [--checkpoint fp32]
+Usage:  python -m oracle.make_golden [--keep-calib] [--checkpoint fp32] | --poly
 
 --checkpoint fp32 records the same fixtures for the plain-fp32-trained synthetic recogniser
 (lightly_ocr_b200/synth/calib_crnn_*_fp32.npz) as tests/golden/ref_{ctc,attention}_fp32.npz.
+--poly records only tests/golden/ref_poly.npz: the live reference's getDetBoxes(..., poly=True) (ocr/tools/det_utils.py
+:97-256) on the curved synthetic score maps.
 """
 import contextlib
 import io
@@ -22,6 +24,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def poly_goldens(scratch):
+    """getDetBoxes(textmap, linkmap, 0.7, 0.4, 0.4, poly=True) of the live reference on curved_score_maps(0..5)."""
+    from oracle import receipts, ref_env, weights
+    dst = ref_env.stage("CTC", {"x": torch.zeros(1)}, {"x": torch.zeros(1)}, scratch)
+    out = {}
+    with ref_env.imported(dst):
+        import tools as ref_tools
+        for seed in range(6):
+            t, l = receipts.curved_score_maps(seed)
+            boxes, polys = ref_tools.getDetBoxes(t, l, 0.7, 0.4, 0.4, True)
+            out["s%d_boxes" % seed] = np.array(boxes, np.float32).reshape(-1, 4, 2)
+            out["s%d_valid" % seed] = np.array([p is not None for p in polys], np.int32)
+            out["s%d_polys" % seed] = np.array([p if p is not None else np.zeros((14, 2)) for p in polys],
+                                               np.float64).reshape(-1, 14, 2)
+    np.savez_compressed(os.path.join(GOLDEN, "ref_poly.npz"), **out)
+    print("poly", {k: v.shape for k, v in out.items() if k.endswith("valid")},
+          sum(int(v.sum()) for k, v in out.items() if k.endswith("valid")), "polygons")
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import ocr_ref, receipts, ref_env, weights
@@ -29,6 +50,9 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     scratch = "/tmp/locr_ref_scratch"
     os.makedirs(scratch, exist_ok=True)
+    if "--poly" in sys.argv:
+        poly_goldens(scratch)
+        return
 
     ckpt = sys.argv[sys.argv.index("--checkpoint") + 1] if "--checkpoint" in sys.argv else "trained"
     trained = "fp32" if ckpt == "fp32" else True

@@ -208,3 +208,15 @@ def test_serving_front_batches_and_filters_without_gpu(tmp_path, monkeypatch):
     assert got3[1][0]["results"] == got3[0][0]["results"]                   # OpenCV's partly grey 300-row image
     assert m.retried_batches == before + 1
     m.close()
+
+
+def test_installed_reference_copy_is_unmodified():
+    """baseline/_ref/ocr (git-ignored, made by oracle/ref_env.install) must be the reference's files, byte for byte:
+    checked wherever both the copy and /root/reference are present (the authoring container)."""
+    from oracle import ref_env
+    if not (os.path.isdir(ref_env.INSTALLED) and os.path.isdir(ref_env.UPSTREAM)):
+        pytest.skip("needs both baseline/_ref/ocr and /root/reference")
+    assert ref_env._tree_digest(ref_env.INSTALLED) == ref_env._tree_digest(ref_env.UPSTREAM)
+    for name in ("pipeline.py", "net.py", "server.py", "tools/det_utils.py"):
+        with open(os.path.join(ref_env.INSTALLED, name), "rb") as a, open(os.path.join(ref_env.UPSTREAM, name), "rb") as b:
+            assert a.read() == b.read(), name

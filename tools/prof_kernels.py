@@ -4,6 +4,8 @@
                                      BiLSTM cluster kernel at 650 crops
   python tools/prof_kernels.py mem   one detect+recognize pass over 8 synthetic receipts: the HBM-bound kernels
                                      (pre-processing, pooling, up-sampling, labelling, boxes, crops, TPS, decode)
+  python tools/prof_kernels.py memi  the same plus a second pass with the receipts handed over as PNG / JPEG files
+                                     (the ingest kernels: png_unfilter, png_color, jpeg_idct, jpeg_color)
 """
 import ctypes as C
 import os
@@ -49,5 +51,6 @@ else:
     print("%d crops, first strings %s" % (len(out["text"]), out["text"][:5]))
     # the ingest kernels: the same receipts as PNG and JPEG files through locr_detect_encoded
     import cv2
-    r.ocr_encoded([cv2.imencode(".png", im)[1].tobytes() for im in imgs[:4]] +
-                  [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in imgs[4:]])
+    if mode == "memi":
+        r.ocr_encoded([cv2.imencode(".png", im)[1].tobytes() for im in imgs[:4]] +
+                      [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for im in imgs[4:]])
