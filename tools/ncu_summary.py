@@ -1,10 +1,14 @@
 """Text summary of the two `ncu --set full` captures of tools/prof_round.sh (read on the CPU box with `ncu -i`).
-Usage: python tools/ncu_summary.py r01d > profiles/r01d_ncu_full_summary.txt"""
+Usage: python tools/ncu_summary.py r01d [dir] > profiles/r01d_ncu_full_summary.txt
+`dir` (default gpurun_out) holds prof_{tc,mem}_<tag>.ncu-rep; a capture too large to bring back from the GPU box can be
+replaced by its raw-page csv made there (prof_{tc,mem}_<tag>_raw.csv: `ncu -i rep --page raw --csv --metrics ...`)."""
 import csv
+import os
 import subprocess
 import sys
 
 tag = sys.argv[1]
+root = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out"
 M = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,"
      "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,"
@@ -19,9 +23,16 @@ labels_tc = ["slice1.0 16->64 @1280x960 x8, plain 9-tap form (first launch of th
              "slice1.3 64->64 @1280x960 x8, haloed-patch path, only the 2x2 max-pooled tensor written (as in the pipeline)", "slice1.10 128->128 @640x480 x8", "slice3.27 512->512 @160x120 x8",
              "conv_cls.0 32->32 @640x480 x8, plain 9-tap form", "CRNN 512->512 @4x26 x640 crops",
              "BiLSTM recurrence, 650 crops x 26 steps x 2 directions"]
-for rep, labels in (("gpurun_out/prof_tc_%s.ncu-rep" % tag, labels_tc), ("gpurun_out/prof_mem_%s.ncu-rep" % tag, None)):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", M], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+for rep, labels in (("%s/prof_tc_%s.ncu-rep" % (root, tag), labels_tc), ("%s/prof_mem_%s.ncu-rep" % (root, tag), None)):
+    raw = rep.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", M], capture_output=True, text=True).stdout
+    elif os.path.exists(raw):
+        out = open(raw).read()
+    else:
+        print("(no capture %s)" % rep)
+        continue
+    rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
     hdr, units = rows[0], rows[1]
     for i, r in enumerate(rows[2:]):
         d, u = dict(zip(hdr, r)), dict(zip(hdr, units))
