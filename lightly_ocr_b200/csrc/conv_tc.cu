@@ -57,6 +57,7 @@ struct ConvParams {
     int halves;          // 1 or 2 half boxes per tile (M = 128 or 256), stacked along h (split_b = 0), b (1) or w (2)
     int split_b;
     int tiles_w, tiles_h, tiles_n, num_tiles;
+    int num_pair_tiles;   // CTA pairs: ceil(m-tiles / 2) * tiles_n
     int n_tile, n_tile_alloc, tmem_cols;
     int cin_chunks, KW, dil_h, dil_w, pad_h, pad_w, stride2;
     int num_kblocks, stages;
@@ -142,7 +143,12 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
 // never split-precision, fp32, fused-tail or halo-pool (those stay on the generic path).
 constexpr int kFirstThreads = kThreads + 128;   // + four producer warps that build the first layer's A operand
 
-template <int SWZ, int HALVES, int EPI, bool FIRST = false>
+// CTA2: two CTAs of a cluster (one TPC) share every MMA (tcgen05 cta_group::2, M = 256 = 128 rows per CTA): each CTA
+// stages the A boxes of its own m-tile and HALF of the weight slab's N rows, the leader CTA issues the instruction for
+// both, so per CTA the tensor core reads A + B/2 from shared memory instead of A + B and the weight fills halve.  Used
+// for the N <= 128 layers, which are bound by shared-memory operand traffic.  A pair walks "pair tiles": the same n-tile
+// over two consecutive m-tiles (rank 0 / rank 1).
+template <int SWZ, int HALVES, int EPI, bool FIRST = false, bool CTA2 = false>
 __global__ void __launch_bounds__(FIRST ? kFirstThreads : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_p,
@@ -172,6 +178,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #if LOCR_CONV_EXPERIMENTS
     int trace_n = 0;
 #endif
+    // tile walk: CTAs (or CTA pairs) take tiles (pair tiles) round-robin
+    const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;
+    const int t_begin = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int t_end = CTA2 ? p.num_pair_tiles : p.num_tiles;
+    // pair tile q -> this CTA's tile: same n-tile, m-tile 2 * (q / tiles_n) + rank (may lie past the end: its loads
+    // are zero-filled and its stores clipped by the TMA unit)
+    auto tile_of = [&](int q) { return CTA2 ? ((2 * (q / p.tiles_n) + (int)rank) * p.tiles_n + q % p.tiles_n) : q; };
 
     if (warp == 0 && lane == 0) {
         if (!FIRST) ptx::tma_prefetch_desc(&tmap_x);
@@ -186,14 +200,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull_bar[a], 1);
-            ptx::mbar_init(&tempty_bar[a], 8);
+            ptx::mbar_init(&tempty_bar[a], CTA2 ? 16 : 8);   // CTA2: the leader also waits for the peer's epilogue warps
         }
         if (p.halo || FIRST) ptx::mbar_init(&full_bar[kMaxStages - 1], 1);   // resident weights landed
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
-        ptx::tmem_relinquish();
+        if (CTA2) {
+            ptx::tmem_alloc_2sm(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     uint16_t* lut = reinterpret_cast<uint16_t*>(bias_s + 256);                                   // FIRST: [3][256]
     if (FIRST) {
@@ -210,7 +229,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (CTA2) {      // the peer's barriers exist before anything is signalled across the pair
+        ptx::cluster_arrive_release();
+        ptx::cluster_wait_acquire();
+    }
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // tempty hand-back of an epilogue warp: in a pair the accumulators of BOTH CTAs are rewritten by the leader's MMAs
+    const uint32_t tempty_remote0 = CTA2 ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0u) : 0u;
+    auto tempty_arrive = [&](int a) {
+        if (CTA2) ptx::mbar_arrive_remote_release(tempty_remote0 + 8u * (uint32_t)a);
+        else ptx::mbar_arrive(&tempty_bar[a]);
+    };
 
     if (FIRST && warp >= kThreads / 32) {
         // ------------------------------------------------------------ first-layer A producer (four warps)
@@ -224,8 +253,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const uint32_t sw = ((uint32_t)pr >> 1) & 3u;
         int stage = 0;
         uint32_t phase = 1;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
+            const TileCoord t = decode_tile(p, tile_of(tile));
             ptx::mbar_wait_a(empty0 + 8u * stage, phase, 100);
             uint8_t* a_stage = smem_a + (size_t)stage * p.a_stage_bytes;
 #pragma unroll
@@ -284,7 +313,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // a per-thread election loop with R2UR moves (~10 extra instructions per issue), which bounded the k-block
         // rate of every layer with N <= 128.
         {
-            uint32_t tx_bytes = (uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
+            // CTA2: the leader's barrier counts the boxes of both CTAs (each: its A boxes + half of the weight slab)
+            uint32_t tx_bytes = CTA2 ? 2u * ((uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile / 2 * SWZ))
+                                     : (uint32_t)(p.halves * kTileM * SWZ) + (uint32_t)(p.n_tile * SWZ);
             if (LOCR_CONV_EXPERIMENTS && (p.dbg & 2)) tx_bytes -= (uint32_t)(p.halves * kTileM * SWZ);
             if (LOCR_CONV_EXPERIMENTS && (p.dbg & 4)) tx_bytes -= (uint32_t)(p.n_tile * SWZ);
             const uint32_t a0 = ptx::smem_u32(smem_a), b0s = ptx::smem_u32(smem_b);
@@ -292,6 +323,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint32_t a_end = a0 + (uint32_t)p.stages * p.a_stage_bytes;
             uint32_t a_s = a0, b_s = b0s, full_s = full0, empty_s = empty0, phase = 1;
             const int KH = p.num_kblocks / (p.KW * p.cin_chunks);
+            const uint32_t full_lead0 = CTA2 ? ptx::mapa(full0, 0u) : 0u;     // the leader's full barriers (shared::cluster)
+            const int n_half = CTA2 ? (int)rank * (p.n_tile / 2) : 0;
             if (p.halo) {
                 // resident weights: nine [64 x 64] tap slabs, once; then ONE haloed patch (18 rows x 24 pixels) per tile
                 if (ptx::elect_one()) {
@@ -299,8 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     for (int tp = 0; tp < 9; ++tp)
                         ptx::tma_load_2d_a(b0s + (uint32_t)tp * 8192u, &tmap_w, full0 + 8u * (kMaxStages - 1), tp * 64, 0);
                 }
-                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                    const TileCoord t = decode_tile(p, tile);
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
+                    const TileCoord t = decode_tile(p, tile_of(tile));
                     LOCR_TRACE(0, 0);
                     ptx::mbar_wait_a(empty_s, phase, 110);
                     LOCR_TRACE(0, 1);
@@ -316,8 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     }
                 }
             } else
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
+                const TileCoord t = decode_tile(p, tile_of(tile));
                 LOCR_TRACE(0, 0);
                 int kcoord = 0;
                 for (int kh = 0; kh < KH; ++kh) {
@@ -331,12 +364,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             int cch = cc * BLOCK_K;
                             if (cch >= p.cin_wrap) cch -= p.cin_wrap;   // [hi | lo | hi] of a split-precision input
                             if (ptx::elect_one()) {
+                                if (CTA2) {
+                                    const uint32_t lead = full_lead0 + (full_s - full0);
+                                    if (rank == 0) ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
+                                    ptx::tma_load_5d_2sm(a_s, &tmap_x, lead, cch, iw0, c2, c3, t.b0);
+                                    ptx::tma_load_2d_2sm(b_s, &tmap_w, lead, kcoord, t.n0 + n_half);
+                                } else {
                                 if (LOCR_CONV_EXPERIMENTS && tx_bytes == 0) ptx::mbar_arrive(&full_bar[(full_s - full0) >> 3]);
                                 else ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
                                 if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 2)))
                                     ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
                                 if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 4)))
                                     ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
+                                }
                             }
                             LOCR_TRACE(0, 2);
                             a_s += p.a_stage_bytes; b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
@@ -349,8 +389,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
+    } else if (warp == 1 && !(CTA2 && rank != 0)) {
+        // ------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues;
+        // in a CTA pair only the leader's)
         {
             // descriptors as 32-bit running values: hi word constant, lo word = (addr >> 4) | LBO field
             const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, SWZ) >> 32);
@@ -369,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             if (FIRST) {
                 // one k-block per tile (K = 32 = two K16 MMAs per half) against the resident weight slab
                 ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
-                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
                     ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
                     ptx::mbar_wait_a(full_s, phase, 300);
                     ptx::tc_fence_after();
@@ -401,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 // exactly where the TMA unit put the data.
                 ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
                 const uint32_t hi_common = (3072u >> 4) | (1u << 14) | (2u << 29);
-                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
                     LOCR_TRACE(1, 0);
                     ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
                     LOCR_TRACE(1, 1);
@@ -440,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (acc == 0) acc_phase ^= 1u;
                 }
             } else
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
                 LOCR_TRACE(1, 0);
                 ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
                 LOCR_TRACE(1, 1);
@@ -457,12 +498,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
                             for (int hf = 0; hf < HALVES; ++hf) {
                                 // independent accumulators (M = 256 tiles) alternate, hiding the MMA pipeline latency
-                                if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 1)))
+                                if (CTA2)
+                                ptx::umma_f16_lohi_2sm(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
+                                                       desc_hi, b_lo + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
+                                else if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 1)))
                                 ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_lo + hf * kHalfStep + k * 2,
                                                    desc_hi, b_lo + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
                             }
                         }
-                        if (LOCR_CONV_EXPERIMENTS && (p.dbg & 64))   // skeleton runs: plain arrive instead of the commit
+                        if (CTA2) ptx::umma_commit_2sm(empty_s);      // frees the slot in both CTAs
+                        else if (LOCR_CONV_EXPERIMENTS && (p.dbg & 64))   // skeleton runs: plain arrive instead of the commit
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_s) : "memory");
                         else
                         ptx::umma_commit_a(empty_s);  // frees the smem slot once these MMAs retire
@@ -475,7 +520,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         phase ^= 1u;
                     }
                 }
-                if (ptx::elect_one()) ptx::umma_commit_a(tfull0 + acc * 8u);  // accumulators complete -> epilogue
+                if (ptx::elect_one()) {                                       // accumulators complete -> epilogue(s)
+                    if (CTA2) ptx::umma_commit_2sm(tfull0 + acc * 8u);
+                    else ptx::umma_commit_a(tfull0 + acc * 8u);
+                }
                 LOCR_TRACE(1, 4);
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
@@ -500,8 +548,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             for (int i = etid; i < 306; i += 256) tw[i] = __ldg(&p.tail_w[i]);
             if (etid < 16) tw[306 + etid] = __ldg(&p.bias[etid]);
             ptx::named_bar_sync(1, 256);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
+                const TileCoord t = decode_tile(p, tile_of(tile));
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 ptx::tc_fence_after();
                 const int hf = half;
@@ -514,7 +562,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) tempty_arrive(acc);
                 if (work) {
                     const int oh0 = t.oh0 + (p.split_b == 0 ? hf * p.bh : 0), b0 = t.b0 + (p.split_b == 1 ? hf * p.bb : 0);
                     const int ow = t.ow0 + (p.split_b == 2 ? hf * p.bw : 0) + rw, oh = oh0 + rh, b = b0 + rb;
@@ -564,14 +612,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int units = p.halves * p.n_chunks;
             int last_u = -1;
             for (int u = g; u < units; u += 2) last_u = u;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
+                const TileCoord t = decode_tile(p, tile_of(tile));
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 ptx::tc_fence_after();
                 if (last_u < 0) {          // single-unit tiles: this group only takes part in the TMEM hand-back
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) tempty_arrive(acc);
                 }
                 for (int u = g; u < units; u += 2) {
                     const int hf = u / p.n_chunks, c = u - hf * p.n_chunks;
@@ -588,7 +636,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (u == last_u) {     // accumulators fully read by this group
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) tempty_arrive(acc);
                     }
 #pragma unroll
                     for (int q = 0; q < kCols / 8; ++q) {
@@ -659,8 +707,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const bool bias_once = p.tiles_n == 1;
             if (bias_once)
                 for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[i]);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
+                const TileCoord t = decode_tile(p, tile_of(tile));
                 if (etid == 0) LOCR_TRACE(2, 0);
                 if (!bias_once)
                     for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
@@ -670,7 +718,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 if (LOCR_CONV_EXPERIMENTS && (p.dbg & 16)) {   // epilogue reduced to the TMEM hand-shake
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) tempty_arrive(acc);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                     continue;
@@ -693,7 +741,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (etid == 0) LOCR_TRACE(2, 3);
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) tempty_arrive(acc);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         uint32_t hv[16];
@@ -777,7 +825,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (c == p.n_chunks - 1 && hf == p.halves - 1) {  // accumulators fully read: hand the TMEM stage back to the MMA warp
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) tempty_arrive(acc);
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -924,16 +972,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             if (etid == 0) ptx::tma_store_wait_all();
         } else if (half == 1) {
             // direct-store path uses four warps; the second warpgroup only keeps the TMEM hand-shake balanced
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) tempty_arrive(acc);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
         } else
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
+            const TileCoord t = decode_tile(p, tile_of(tile));
             const int ow = t.ow0 + rw, oh = t.oh0 + rh, b = t.b0 + rb;
             const bool valid = (ow < p.OW) && (oh < p.OH) && (b < p.B);
             const long pix = ((long)b * p.OH + oh) * p.OW + ow;
@@ -992,7 +1040,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) tempty_arrive(acc);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -1000,9 +1048,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CTA2) {      // neither CTA frees its TMEM (or exits) while the pair's MMAs / remote arrivals may still touch it
+        ptx::cluster_arrive_release();
+        ptx::cluster_wait_acquire();
+    }
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (CTA2) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -1031,17 +1084,33 @@ void set_err(char* err, int errlen, const char* msg) {
     }
 }
 
-template <int SWZ, int HALVES, int EPI, bool FIRST = false>
+template <int SWZ, int HALVES, int EPI, bool FIRST = false, bool CTA2 = false>
 cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& mp,
                        const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES, EPI, FIRST>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<SWZ, HALVES, EPI, FIRST, CTA2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<SWZ, HALVES, EPI, FIRST><<<grid, FIRST ? kFirstThreads : kThreads, smem, stream>>>(mx, mw, my, mp, p);
+    if (CTA2) {      // clusters of two CTAs (one TPC): the pair shares every MMA
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<SWZ, HALVES, EPI, FIRST, CTA2>, mx, mw, my, mp, p);
+    }
+    conv_tc_kernel<SWZ, HALVES, EPI, FIRST, CTA2><<<grid, FIRST ? kFirstThreads : kThreads, smem, stream>>>(mx, mw, my, mp, p);
     return cudaGetLastError();
 }
 
@@ -1200,8 +1269,25 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.KW = c.KW; p.dil_h = c.dil_h; p.dil_w = c.dil_w; p.pad_h = c.pad_h; p.pad_w = c.pad_w;
     p.stride2 = (c.stride_h == 2) ? 1 : 0;
     p.num_kblocks = c.KH * c.KW * p.cin_chunks;
+    // CTA pairs (conv_tc_kernel CTA2) for the N = 128 layers with M = 256 tiles and K >= 1152 (18 k-blocks): measured
+    // -11 % on slice1.10 (128 -> 128, 3x3) and -7 % on the CRNN's conv1, neutral at 9 k-blocks, and +30 % on 1x1 layers
+    // with one or two k-blocks per tile, where the cross-CTA barrier round trips are not amortised.
+    // LOCR_CONV_CTA2=0 switches them off, LOCR_CONV_CTA2=2 takes every eligible layer (tests, A/B runs).
+    static int allow_cta2 = -1;
+    if (allow_cta2 < 0) {
+        const char* e = getenv("LOCR_CONV_CTA2");
+        const char* ee = getenv("LOCR_CONV_EPI");
+        allow_cta2 = (ee ? atoi(ee) : 1) ? (e ? atoi(e) : 1) : 0;  // the pair kernels exist for the compile-time epilogues
+    }
+    const int elem_c = c.out_fp32 ? 4 : 2;
+    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && halves == 2 && n_tile == 128 && !c.out_fp32 &&
+                      !c.split_out && c.cin_wrap == 0 && c.tail_out == nullptr && c.x_row_px == 0 && c.y_row_px == 0 &&
+                      (c.y_pitch * elem_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
+                      (long)p.tiles_w * p.tiles_h * tiles_b >= 2 && (allow_cta2 >= 2 || c.KH * c.KW * p.cin_chunks >= 18);
+    const int n_load = cta2 ? n_tile / 2 : n_tile;      // weight rows each CTA stages per k-block
+    p.num_pair_tiles = (int)((((long)p.tiles_w * p.tiles_h * tiles_b + 1) / 2) * p.tiles_n);
     p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
-    p.b_stage_bytes = (uint32_t)((n_tile * swz + 1023) / 1024 * 1024);
+    p.b_stage_bytes = (uint32_t)((n_load * swz + 1023) / 1024 * 1024);
     if (halo) {
         p.a_stage_bytes = 18u * 24u * 128u;          // haloed patch
         p.b_stage_bytes = 9u * 8192u / 2u;           // x 2 "stages" = the nine resident [64 x 64] tap slabs
@@ -1223,7 +1309,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     if (stages < 2 || halo) stages = 2;
     if (first && stages > 4) stages = 4;   // barrier slot kMaxStages - 1 belongs to the resident weights (like halo)
     p.stages = stages;
-    p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, kTileM, n_tile);
+    p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, cta2 ? 2 * kTileM : kTileM, n_tile);
     p.pool = pool;
     p.skip_full = (pool && c.skip_full) ? 1 : 0;
     p.halo_pool = (halo && p.skip_full) ? 1 : 0;
@@ -1289,7 +1375,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const cuuint64_t ktot = (cuuint64_t)c.KH * c.KW * c.Cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)c.Cout_pad};
         cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)n_tile};
+        cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)n_load};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&mw, dt, 2, const_cast<void*>(c.w), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1359,6 +1445,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                 "kblocks %d tiles %d halo %d pool %d smem %zu\n", c.B, c.OH, c.OW, c.Cin, c.Cout, c.KH, c.KW, swz, halves,
                 split_b, p.bw, p.bh, p.bb, n_tile, p.stages, p.num_kblocks, p.num_tiles, p.halo, p.pool, smem);
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    if (cta2) {
+        const int pairs_max = device_sm_count() / 2;
+        grid = 2 * (p.num_pair_tiles < pairs_max ? p.num_pair_tiles : pairs_max);
+    }
     cudaError_t e;
     // 16-bit TMA-store epilogues with compile-time options (see conv_tc_kernel); anything else takes the generic one
     static int allow_epi = -1;
@@ -1376,6 +1466,16 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     if (first) {
         e = launch_swz<64, 2, 32, true>(mx, mw, my, mp, p, grid, smem, stream);
         done = true;
+    }
+    if (cta2 && !done) {
+        if (epi == 32) { e = launch_swz<128, 2, 32, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
+        else if (epi == (32 | kEpiRes)) { e = launch_swz<128, 2, 32 | kEpiRes, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
+        else if (epi == (32 | kEpiPool)) { e = launch_swz<128, 2, 32 | kEpiPool, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
+        else if (epi == (32 | kEpiPool | kEpiSkip)) { e = launch_swz<128, 2, 32 | kEpiPool | kEpiSkip, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
+        else {
+            set_err(err, errlen, "conv_tc: no CTA-pair instantiation for this epilogue");
+            return cudaErrorInvalidValue;
+        }
     }
 #define LOCR_EPI_CASE(HV, E)                                                                       \
     if (!done && halves == HV && epi == (E)) {                                                     \

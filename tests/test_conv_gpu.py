@@ -46,6 +46,12 @@ CASES = [
     ("deep_k_multi_tile", 64, 4, 26, 512, 512, 3, 3, (1, 1), (1, 1), 1, True, True, False, 1, 0, 0, 0),
     ("n_tile_128_of_512", 2, 16, 16, 64, 512, 3, 3, (1, 1), (1, 1), 1, False, False, True, 1, 0, 0, 128),
     ("big_plane", 1, 160, 120, 64, 64, 3, 3, (1, 1), (1, 1), 1, True, False, False, 1, 0, 0, 0),
+    # N = 128 with enough M = 256 tiles for the CTA-pair kernels (cta_group::2): plain, residual, 1x1, odd tile counts
+    ("cta2_c64_c128", 4, 160, 128, 64, 128, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
+    ("cta2_residual", 4, 160, 128, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    ("cta2_1x1_views", 3, 200, 136, 192, 128, 1, 1, (1, 1), (0, 0), 1, True, False, False, 1, 64, 64, 0),
+    ("cta2_odd_tiles", 5, 122, 126, 64, 128, 3, 3, (1, 1), (1, 1), 1, False, False, False, 0, 0, 0, 0),
+    ("cta2_crnn_layer1", 125, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
 ]
 
 
@@ -88,6 +94,8 @@ POOL_CASES = [
     ("odd_hw", 3, 9, 25, 64, 64, 1, 0),
     ("vgg_c64_ragged", 2, 50, 70, 64, 64, 0, 0),
     ("c32_sw64", 2, 16, 36, 32, 32, 0, 0),
+    ("cta2_vgg_c128", 4, 160, 128, 128, 128, 0, 0),      # the slice1.10 pattern on the CTA-pair kernels
+    ("cta2_crnn_conv1", 125, 16, 50, 128, 128, 0, 0),
 ]
 
 
@@ -129,3 +137,21 @@ def test_conv_halo_mode_64_to_64(shape, act):
     tol = 2e-3 * scale + scale * (2.0 ** -8 if act == 1 else 2.0 ** -11)
     err = float(np.abs(y - ref).max())
     assert err <= tol, "max abs err %g > tol %g" % (err, tol)
+
+
+def test_cta_pair_kernels_on_every_eligible_layer():
+    """By default only the K >= 1152 layers with N = 128 take the CTA-pair kernels (cta_group::2).  The switch is read
+    once per process, so the `cta2_*` cases above are re-run in a child process with LOCR_CONV_CTA2=2, where every
+    eligible layer - small K, 1x1, residual, fused pools, odd tile counts - goes through them."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("LOCR_CONV_CTA2") == "2":
+        pytest.skip("already inside the child process")
+    env = dict(os.environ, LOCR_CONV_CTA2="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "cta2 and not every_eligible"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    tail = (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
