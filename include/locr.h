@@ -98,6 +98,24 @@ LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int
                             const int* strides, const int* channels, int n, float* logits, int32_t* token_ids,
                             char* text, int32_t* has_eos, float* conf);
 
+/* evaluation() of the reference's training script for ONE validation batch (ocr/train/crnn.py:142-240; SURVEY 8f row
+ * 4): the crops are recognised like locr_recognize, then the loss and the accuracy flags are computed on the GPU from
+ * the logits still in HBM.
+ *   CTC head       : targets = concatenated class indices, target_len [n] (CTCLabelConverter.encode,
+ *                    tools/recog_utils.py:24-30); loss[i] = torch.nn.CTCLoss(zero_infinity=True, reduction='none') of
+ *                    preds.log_softmax(2) (crnn.py:119,190); *cost = its 'mean' reduction (loss / target length,
+ *                    averaged over the batch)
+ *   Attention head : targets = [n][batch_max_len + 2] rows of AttnLabelConverter.encode (:84-96: [GO], tokens, [s],
+ *                    [GO] padding), target_len unused but required; loss[i] = sum over the non-padding steps of the
+ *                    cross entropy against targets[i][1:], *cost = CrossEntropyLoss(ignore_index=0) of the batch
+ *                    (crnn.py:121,203-208)
+ *   correct[i]     : 1 iff the greedy prediction equals the label under evaluation()'s comparison (:222-230)
+ *   token_ids / text / conf : as locr_recognize (any may be NULL). */
+LOCR_API int locr_evaluate(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,
+                           const int* strides, const int* channels, int n, const int32_t* targets,
+                           const int32_t* target_len, int64_t targets_total, float* loss, int32_t* correct,
+                           int32_t* token_ids, char* text, float* conf, float* cost);
+
 /* Second half of the fused throughput path (getText, pipeline.py:65-87): recognises boxes of the images of the LAST
  * locr_detect call without the pixels leaving the GPU.  The caller sorts the rects in between exactly like the
  * reference does on the host (sorted(rects, key=cmp_to_key(compare_rects)), net.py:108 - the comparator is not a
@@ -197,6 +215,13 @@ LOCR_API int locr_test_conv_pool(const locr_conv_desc* d, const float* x, const 
  * iters > 0 also times `iters` launches with CUDA events (ms per launch). */
 LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, int act_dtype, float* out, int iters,
                             float* ms_per_iter, int split);
+
+/* The evaluation-loss kernels of locr_evaluate alone, on host logits [n][26][C] (greedy ids come from the decode
+ * kernel): head_attn = 0 CTC (targets concatenated, target_len [n]); head_attn = 1 attention cross entropy (targets
+ * [n][targets_total / n]; count [n] = steps counted, may be NULL for CTC). */
+LOCR_API int locr_test_eval_loss(int head_attn, const float* logits, int n, int C, const int32_t* targets,
+                                 const int32_t* target_len, int64_t targets_total, float* loss, int32_t* count,
+                                 int32_t* correct);
 
 /* CRAFT forward only: bgr uint8 [B][img_h][img_w][3] packed -> score fp32 [B][H32/2][W32/2][2]. */
 LOCR_API int locr_debug_craft_scores(locr_handle* h, const uint8_t* bgr, int B, int img_h, int img_w, float* score);

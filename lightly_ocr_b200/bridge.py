@@ -51,6 +51,9 @@ def lib():
         _lib.locr_image_info.restype = C.c_int
         _lib.locr_image_info.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.locr_test_eval_loss.restype = C.c_int
+        _lib.locr_test_eval_loss.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.locr_test_png_scanlines.restype = C.c_int
         _lib.locr_test_png_scanlines.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     return _lib
@@ -171,6 +174,24 @@ def test_lstm(xproj, whh, act_dtype=0, iters=0, split=0):
     ms = C.c_float(0)
     _check(lib().locr_test_lstm(_fptr(xproj), _fptr(whh), B, T, act_dtype, _fptr(out), iters, C.byref(ms), int(split)))
     return (out, ms.value) if iters > 0 else out
+
+
+def test_eval_loss(logits, targets, target_len, head="CTC"):
+    """The evaluation-loss kernels alone on host logits [n,26,C].  CTC: targets = concatenated class indices,
+    target_len [n] -> (loss [n], correct [n]).  Attention: targets [n, batch_max_len + 2] (AttnLabelConverter.encode
+    rows) -> (loss sums [n], counted steps [n], correct [n])."""
+    logits = np.ascontiguousarray(logits, np.float32)
+    n, T, nc = logits.shape
+    assert T == 26
+    tg = np.ascontiguousarray(targets, np.int32)
+    tl = np.ascontiguousarray(target_len, np.int32)
+    loss = np.zeros(n, np.float32)
+    count = np.zeros(n, np.int32)
+    correct = np.zeros(n, np.int32)
+    attn = head != "CTC"
+    _check(lib().locr_test_eval_loss(int(attn), _fptr(logits), n, nc, _fptr(tg), _fptr(tl), tg.size, _fptr(loss),
+                                     _fptr(count), _fptr(correct)))
+    return (loss, count, correct) if attn else (loss, correct)
 
 
 class Config(C.Structure):
@@ -309,6 +330,9 @@ def _bind_pipeline(L):
     L.locr_detect.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.locr_recognize.restype = C.c_int
     L.locr_recognize.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.locr_evaluate.restype = C.c_int
+    L.locr_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int64, vp, vp, vp, vp, vp,
+                                C.POINTER(C.c_float)]
     L.locr_recognize_boxes.restype = C.c_int
     L.locr_recognize_boxes.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.locr_debug_postproc.restype = C.c_int
@@ -403,6 +427,28 @@ class Pipeline(Engine):
                                      _fptr(o["logits"]), _fptr(o["ids"]), _fptr(o["text"]), _fptr(o["has_eos"]),
                                      _fptr(o["conf"])), self.h)
         o["text"] = _texts(o["text"])
+        return o
+
+    def evaluate(self, crops, targets, target_len):
+        """One validation batch of the reference's evaluation() (ocr/train/crnn.py:142-240): recognition + the loss and
+        the label == prediction flags on the GPU.  targets / target_len as the reference's converter.encode returns them
+        (CTC: concatenated indices + lengths; Attention: [n, batch_max_len + 2] rows + lengths).  Returns a dict with
+        cost (the scalar loss_fn returns), loss [n], correct [n], ids, text, conf."""
+        cs = [np.ascontiguousarray(c, np.uint8) for c in crops]
+        n = len(cs)
+        tg = np.ascontiguousarray(targets, np.int32)
+        tl = np.ascontiguousarray(target_len, np.int32)
+        assert tl.size == n
+        o = dict(loss=np.zeros(n, np.float32), correct=np.zeros(n, np.int32), ids=np.empty((n, 26), np.int32),
+                 text=np.zeros((n, TEXT_STRIDE), np.uint8), conf=np.empty(n, np.float32))
+        ch = [1 if c.ndim == 2 else c.shape[2] for c in cs]
+        cost = C.c_float(0)
+        _check(self.L.locr_evaluate(self.h, _ptr_array(cs), _int_array([c.shape[0] for c in cs]),
+                                    _int_array([c.shape[1] for c in cs]), None, _int_array(ch), n, _fptr(tg), _fptr(tl),
+                                    tg.size, _fptr(o["loss"]), _fptr(o["correct"]), _fptr(o["ids"]), _fptr(o["text"]),
+                                    _fptr(o["conf"]), C.byref(cost)), self.h)
+        o["text"] = _texts(o["text"])
+        o["cost"] = cost.value
         return o
 
     def recognize_boxes(self, image_index, rects, want_logits=False, want_u8=False):

@@ -230,6 +230,7 @@ LOCR_API int locr_debug_crnn(locr_handle* h, const uint8_t* u8, int n, float* lo
     launch_decode(lg, n, C, h->cfg.head == LOCR_HEAD_ATTN, d_ids, d_text, text_stride, d_eos, d_conf, h->stream);
     h->launches++;
     LOCR_CUDA_OK(cudaGetLastError());
+    h->last_logits = lg; h->last_ids = d_ids; h->last_n = n;
     if (logits) LOCR_CUDA_OK(cudaMemcpyAsync(logits, lg, (size_t)n * 26 * C * 4, cudaMemcpyDeviceToHost, h->stream));
     if (ids) LOCR_CUDA_OK(cudaMemcpyAsync(ids, d_ids, (size_t)n * 26 * 4, cudaMemcpyDeviceToHost, h->stream));
     if (text) LOCR_CUDA_OK(cudaMemcpyAsync(text, d_text, (size_t)n * text_stride, cudaMemcpyDeviceToHost, h->stream));

@@ -1280,10 +1280,17 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         allow_cta2 = (ee ? atoi(ee) : 1) ? (e ? atoi(e) : 1) : 0;  // the pair kernels exist for the compile-time epilogues
     }
     const int elem_c = c.out_fp32 ? 4 : 2;
-    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && halves == 2 && n_tile == 128 && !c.out_fp32 &&
+    // N = 256 tiles (M = 128 per CTA, the 256- and 512-channel layers): a pair runs M = 256 x N = 256 MMAs, each CTA
+    // staging 16 KB of A and 16 KB (half) of B per k-block instead of 16 + 32 KB.  LOCR_CONV_CTA2_N256=1 enables it.
+    static int allow_cta2_n256 = -1;
+    if (allow_cta2_n256 < 0) { const char* e = getenv("LOCR_CONV_CTA2_N256"); allow_cta2_n256 = e ? atoi(e) : 0; }
+    const bool cta2_shape = (halves == 2 && n_tile == 128 && (allow_cta2 >= 2 || c.KH * c.KW * p.cin_chunks >= 18)) ||
+                            (halves == 1 && n_tile == 256 && allow_cta2_n256 &&
+                             (allow_cta2_n256 >= 2 || c.KH * c.KW * p.cin_chunks >= 18));
+    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && cta2_shape && !c.out_fp32 &&
                       !c.split_out && c.cin_wrap == 0 && c.tail_out == nullptr && c.x_row_px == 0 && c.y_row_px == 0 &&
                       (c.y_pitch * elem_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
-                      (long)p.tiles_w * p.tiles_h * tiles_b >= 2 && (allow_cta2 >= 2 || c.KH * c.KW * p.cin_chunks >= 18);
+                      (long)p.tiles_w * p.tiles_h * tiles_b >= 2;
     const int n_load = cta2 ? n_tile / 2 : n_tile;      // weight rows each CTA stages per k-block
     p.num_pair_tiles = (int)((((long)p.tiles_w * p.tiles_h * tiles_b + 1) / 2) * p.tiles_n);
     p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
@@ -1468,11 +1475,17 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         done = true;
     }
     if (cta2 && !done) {
-        if (epi == 32) { e = launch_swz<128, 2, 32, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
-        else if (epi == (32 | kEpiRes)) { e = launch_swz<128, 2, 32 | kEpiRes, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
-        else if (epi == (32 | kEpiPool)) { e = launch_swz<128, 2, 32 | kEpiPool, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
-        else if (epi == (32 | kEpiPool | kEpiSkip)) { e = launch_swz<128, 2, 32 | kEpiPool | kEpiSkip, false, true>(mx, mw, my, mp, p, grid, smem, stream); done = true; }
-        else {
+#define LOCR_PAIR_CASE(HV, E)                                                                      \
+        if (!done && halves == HV && epi == (E)) {                                                 \
+            e = launch_swz<128, HV, (E), false, true>(mx, mw, my, mp, p, grid, smem, stream);      \
+            done = true;                                                                           \
+        }
+        LOCR_PAIR_CASE(2, 32) LOCR_PAIR_CASE(2, 32 | kEpiRes) LOCR_PAIR_CASE(2, 32 | kEpiPool)
+        LOCR_PAIR_CASE(2, 32 | kEpiPool | kEpiSkip)
+        LOCR_PAIR_CASE(1, 32) LOCR_PAIR_CASE(1, 32 | kEpiRes) LOCR_PAIR_CASE(1, 32 | kEpiPool)
+        LOCR_PAIR_CASE(1, 32 | kEpiPool | kEpiSkip)
+#undef LOCR_PAIR_CASE
+        if (!done) {
             set_err(err, errlen, "conv_tc: no CTA-pair instantiation for this epilogue");
             return cudaErrorInvalidValue;
         }

@@ -74,6 +74,10 @@ struct locr_handle {
     bool audit = false;
     float* audit_slots = nullptr;            // device, kAuditSlots floats
     std::vector<std::string> audit_names;    // slot i <- layer name of the i-th audited launch since locr_audit(1)
+    // logits / greedy ids of the last recognition forward (device), for locr_evaluate
+    const float* last_logits = nullptr;
+    const int32_t* last_ids = nullptr;
+    int last_n = 0;
 
     int fail(int code, const std::string& m) {
         err = m;

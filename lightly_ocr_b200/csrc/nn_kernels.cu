@@ -749,6 +749,151 @@ decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int
     }
 }
 
+// ------------------------------------------------------------------------------------------- evaluation losses
+// evaluation() of the reference's training script (ocr/train/crnn.py:142-240) for one batch, given the logits the
+// recogniser left in HBM: the loss of each crop (torch.nn.CTCLoss(zero_infinity=True) over preds.log_softmax(2), or
+// CrossEntropyLoss(ignore_index=0) over the attention decoder's steps), and whether the greedy prediction equals the
+// label.  One warp per crop; T = 26 steps.
+constexpr int kEvalT = 26;
+constexpr int kEvalMaxS = 2 * 64 + 1;   // CTC states of a target of up to 64 symbols
+
+__device__ __forceinline__ float warp_lse(const float* __restrict__ row, int C, int lane) {
+    float m = -INFINITY;
+    for (int v = lane; v < C; v += 32) m = fmaxf(m, row[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int v = lane; v < C; v += 32) s += expf(row[v] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return m + logf(s);
+}
+
+// targets: concatenated class indices (CTCLabelConverter.encode, recog_utils.py:24-30), tgt_off[b] = start of crop b's,
+// tgt_len[b] its length.  loss[b] = -log p(target | logits) (0 when infeasible: zero_infinity), the alpha recursion of
+// the connectionist temporal classification forward pass in log space, fp32 like torch's CPU kernel.
+// correct[b] = 1 iff the collapsed arg-max path (ids, from decode_kernel) spells the target.
+__global__ void __launch_bounds__(128)
+ctc_loss_kernel(const float* __restrict__ logits, int B, int C, const int32_t* __restrict__ targets,
+                const int32_t* __restrict__ tgt_off, const int32_t* __restrict__ tgt_len,
+                const int32_t* __restrict__ ids, float* __restrict__ loss, int32_t* __restrict__ correct) {
+    __shared__ float alpha_s[4][2][kEvalMaxS + 3];
+    __shared__ float lse_s[4][kEvalT];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + wib;
+    if (b >= B) return;
+    const float* lg = logits + (long)b * kEvalT * C;
+    const int32_t* tg = targets + tgt_off[b];
+    const int L = tgt_len[b];
+    const int S = 2 * L + 1;
+    if (L > 64) {                 // longer than any 26-step path anyway: infeasible
+        if (lane == 0) {
+            loss[b] = 0.f;
+            correct[b] = 0;
+        }
+        return;
+    }
+    for (int t = 0; t < kEvalT; ++t) {
+        const float l = warp_lse(lg + t * C, C, lane);
+        if (lane == 0) lse_s[wib][t] = l;
+    }
+    __syncwarp();
+    float* a0 = alpha_s[wib][0];
+    float* a1 = alpha_s[wib][1];
+    for (int s = lane; s < S; s += 32) {
+        float v = -INFINITY;
+        if (s == 0) v = lg[0] - lse_s[wib][0];                         // blank = class 0
+        else if (s == 1) v = lg[tg[0]] - lse_s[wib][0];
+        a0[s] = v;
+    }
+    __syncwarp();
+    for (int t = 1; t < kEvalT; ++t) {
+        const float* row = lg + t * C;
+        const float l = lse_s[wib][t];
+        for (int s = lane; s < S; s += 32) {
+            const int cls = (s & 1) ? tg[s >> 1] : 0;
+            const float la1 = a0[s];
+            const float la2 = s > 0 ? a0[s - 1] : -INFINITY;
+            const float la3 = ((s & 1) && s > 1 && tg[s >> 1] != tg[(s >> 1) - 1]) ? a0[s - 2] : -INFINITY;
+            float mx = fmaxf(la1, fmaxf(la2, la3));
+            if (mx == -INFINITY) mx = 0.f;
+            a1[s] = logf(expf(la1 - mx) + expf(la2 - mx) + expf(la3 - mx)) + mx + (row[cls] - l);
+        }
+        __syncwarp();
+        float* tmp = a0; a0 = a1; a1 = tmp;
+    }
+    if (lane == 0) {
+        const float l1 = a0[S - 1];
+        const float l2 = L > 0 ? a0[S - 2] : -INFINITY;
+        float mx = fmaxf(l1, l2);
+        if (mx == -INFINITY) mx = 0.f;
+        float v = -(logf(expf(l1 - mx) + expf(l2 - mx)) + mx);
+        if (isinf(v) || isnan(v)) v = 0.f;                             // zero_infinity=True
+        loss[b] = v;
+        // greedy path collapsed like CTCLabelConverter.decode (recog_utils.py:32-47) against the label
+        const int32_t* id = ids + b * kEvalT;
+        int n = 0, ok = 1;
+        for (int t = 0; t < kEvalT; ++t) {
+            const int c = id[t];
+            if (c != 0 && !(t > 0 && id[t - 1] == c)) {
+                if (n >= L || tg[n] != c) ok = 0;
+                ++n;
+            }
+        }
+        correct[b] = (ok && n == L) ? 1 : 0;
+    }
+}
+
+// targets [B][tw]: AttnLabelConverter.encode rows (recog_utils.py:84-96): [GO], the label's tokens, [s], then [GO]
+// padding.  The loss compares step t of the decoder with targets[b][t + 1] and ignores padding (class 0):
+// loss[b] = sum over the counted steps of -log_softmax(preds[b][t])[target], count[b] = their number.
+// correct[b] follows evaluation()'s string comparison: label and prediction are cut at their first "[s]"; a prediction
+// without "[s]" loses its last CHARACTER instead (str.find returns -1 there, crnn.py:226-228).
+__global__ void __launch_bounds__(128)
+attn_ce_kernel(const float* __restrict__ logits, int B, int C, const int32_t* __restrict__ targets, int tw,
+               const int32_t* __restrict__ ids, float* __restrict__ loss, int32_t* __restrict__ count,
+               int32_t* __restrict__ correct) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float* lg = logits + (long)b * kEvalT * C;
+    const int32_t* tg = targets + (long)b * tw;
+    const int steps = tw - 1 < kEvalT ? tw - 1 : kEvalT;
+    float sum = 0.f;
+    int cnt = 0;
+    for (int t = 0; t < steps; ++t) {
+        const int c = tg[t + 1];
+        if (c == 0) continue;                       // warp-uniform
+        const float l = warp_lse(lg + t * C, C, lane);
+        sum += l - lg[t * C + c];
+        ++cnt;
+    }
+    if (lane != 0) return;
+    loss[b] = sum;
+    count[b] = cnt;
+    const int32_t* id = ids + b * kEvalT;
+    int gl = 0;                                     // label tokens before its [s]
+    while (gl < steps && tg[gl + 1] != 1) ++gl;
+    int pe = -1;
+    for (int t = 0; t < kEvalT; ++t)
+        if (id[t] == 1) {
+            pe = t;
+            break;
+        }
+    int ok = 1;
+    if (pe >= 0) {
+        if (pe != gl) ok = 0;
+        for (int t = 0; ok && t < pe; ++t)
+            if (id[t] != tg[t + 1]) ok = 0;
+    } else {
+        // 26 tokens minus the last character: equal to a label only if every token is a single character
+        if (gl != kEvalT - 1 || id[kEvalT - 1] < 2) ok = 0;
+        for (int t = 0; ok && t < kEvalT - 1; ++t)
+            if (id[t] != tg[t + 1]) ok = 0;
+    }
+    correct[b] = ok;
+}
+
 // ------------------------------------------------------------------------------------------- range audit
 __global__ void __launch_bounds__(256)
 absmax_kernel(const uint16_t* __restrict__ t, long rows, int C, long pitch, int f16, float* __restrict__ slot) {
@@ -861,6 +1006,16 @@ void launch_attention(const void* feats, const float* fproj, AttnWeights w, floa
         if (w32) attention_kernel<4, true><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
         else attention_kernel<4, false><<<(B + 3) / 4, 512, 0, s>>>(f, fproj, w, preds, B, C, is_f16, feat_pitch, feat_lo_off);
     }
+}
+
+void launch_ctc_loss(const float* logits, int B, int C, const int32_t* targets, const int32_t* tgt_off,
+                     const int32_t* tgt_len, const int32_t* ids, float* loss, int32_t* correct, cudaStream_t s) {
+    ctc_loss_kernel<<<(B + 3) / 4, 128, 0, s>>>(logits, B, C, targets, tgt_off, tgt_len, ids, loss, correct);
+}
+
+void launch_attn_ce(const float* logits, int B, int C, const int32_t* targets, int tw, const int32_t* ids, float* loss,
+                    int32_t* count, int32_t* correct, cudaStream_t s) {
+    attn_ce_kernel<<<(B + 3) / 4, 128, 0, s>>>(logits, B, C, targets, tw, ids, loss, count, correct);
 }
 
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,

@@ -86,4 +86,12 @@ void launch_absmax(const void* t, long rows, int C, long pitch, int is_f16, floa
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,
                    int32_t* has_eos, float* conf, cudaStream_t s);
 
+// Evaluation losses of the reference's training script (ocr/train/crnn.py:142-240) on logits fp32 [B][26][C] and the
+// greedy ids of launch_decode: per-crop CTC loss (CTCLoss(zero_infinity=True), unreduced) / attention cross-entropy
+// sums and counts (CrossEntropyLoss(ignore_index=0)), and label == prediction flags.
+void launch_ctc_loss(const float* logits, int B, int C, const int32_t* targets, const int32_t* tgt_off,
+                     const int32_t* tgt_len, const int32_t* ids, float* loss, int32_t* correct, cudaStream_t s);
+void launch_attn_ce(const float* logits, int B, int C, const int32_t* targets, int tw, const int32_t* ids, float* loss,
+                    int32_t* count, int32_t* correct, cudaStream_t s);
+
 }  // namespace locr

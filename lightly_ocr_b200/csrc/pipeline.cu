@@ -75,6 +75,7 @@ int run_crnn_and_decode(locr_handle* h, const float* d_x, int n, float* logits, 
     launch_decode(lg, n, C, h->cfg.head == LOCR_HEAD_ATTN, d_ids, d_text, kTextStride, d_eos, d_conf, h->stream); }
     h->launches++;
     LOCR_CUDA_OK(cudaGetLastError());
+    h->last_logits = lg; h->last_ids = d_ids; h->last_n = n;
     cudaStream_t s = h->stream;
     if (logits) LOCR_CUDA_OK(cudaMemcpyAsync(logits, lg, (size_t)n * 26 * C * 4, cudaMemcpyDeviceToHost, s));
     if (ids) LOCR_CUDA_OK(cudaMemcpyAsync(ids, d_ids, (size_t)n * 26 * 4, cudaMemcpyDeviceToHost, s));
@@ -389,6 +390,74 @@ LOCR_API int locr_recognize(locr_handle* h, const uint8_t* const* img, const int
     }
     LOCR_CUDA_OK(cudaMemcpyAsync(d_buf, h_buf, total, cudaMemcpyHostToDevice, h->stream));
     return run_crops(h, descs, logits, token_ids, text, has_eos, conf, nullptr);
+}
+
+/* evaluation() of the reference's training script (ocr/train/crnn.py:142-240) for one validation batch: recognises the
+ * crops like locr_recognize, then computes on the GPU, from the logits still in HBM, the loss of every crop and whether
+ * its greedy prediction spells the label; *cost is the scalar the reference's loss_fn returns for the batch. */
+LOCR_API int locr_evaluate(locr_handle* h, const uint8_t* const* img, const int* heights, const int* widths,
+                           const int* strides, const int* channels, int n, const int32_t* targets,
+                           const int32_t* target_len, int64_t targets_total, float* loss, int32_t* correct,
+                           int32_t* token_ids, char* text, float* conf, float* cost) {
+    if (h == nullptr || targets == nullptr || target_len == nullptr || n <= 0 || targets_total < 0)
+        return fail(LOCR_ERR_INVALID, "locr_evaluate: bad argument");
+    const int attn = h->cfg.head == LOCR_HEAD_ATTN;
+    const int C = h->cfg.num_classes;
+    std::vector<int32_t> off(n);
+    int tw = 0;
+    if (attn) {
+        if (targets_total % n != 0 || targets_total / n < 2)
+            return h->fail(LOCR_ERR_INVALID, "locr_evaluate: attention targets must be [n][batch_max_len + 2]");
+        tw = (int)(targets_total / n);
+    } else {
+        int64_t tot = 0;
+        for (int i = 0; i < n; ++i) {
+            if (target_len[i] < 0) return h->fail(LOCR_ERR_INVALID, "locr_evaluate: negative target length");
+            off[i] = (int32_t)tot;
+            tot += target_len[i];
+        }
+        if (tot != targets_total) return h->fail(LOCR_ERR_INVALID, "locr_evaluate: target lengths do not add up");
+    }
+    for (int64_t i = 0; i < targets_total; ++i)
+        if (targets[i] < 0 || targets[i] >= C || (!attn && targets[i] == 0))
+            return h->fail(LOCR_ERR_INVALID, "locr_evaluate: target class out of range");
+    std::vector<int32_t> eos(n);
+    int rc = locr_recognize(h, img, heights, widths, strides, channels, n, nullptr, token_ids, text, eos.data(), conf);
+    if (rc != LOCR_OK) return rc;
+    if (h->last_n != n || h->last_logits == nullptr) return h->fail(LOCR_ERR_STATE, "locr_evaluate: no logits");
+    cudaStream_t s = h->stream;
+    const size_t tb = (size_t)(targets_total > 0 ? targets_total : 1) * 4;
+    int32_t* d_tg = (int32_t*)engine_buffer(h, "eval.targets", tb);
+    int32_t* d_meta = (int32_t*)engine_buffer(h, "eval.meta", (size_t)n * 4 * 4);   // off | len | count | correct
+    float* d_loss = (float*)engine_buffer(h, "eval.loss", (size_t)n * 4);
+    if (!d_tg || !d_meta || !d_loss) return h->fail(LOCR_ERR_CUDA, "allocation failed");
+    int32_t* d_off = d_meta, *d_len = d_meta + n, *d_cnt = d_meta + 2 * n, *d_ok = d_meta + 3 * n;
+    if (targets_total > 0) LOCR_CUDA_OK(cudaMemcpyAsync(d_tg, targets, (size_t)targets_total * 4, cudaMemcpyHostToDevice, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_off, off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(d_len, target_len, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    { ProfScope ps_(h, "eval_loss", 0, false);
+    if (attn) launch_attn_ce(h->last_logits, n, C, d_tg, tw, h->last_ids, d_loss, d_cnt, d_ok, s);
+    else launch_ctc_loss(h->last_logits, n, C, d_tg, d_off, d_len, h->last_ids, d_loss, d_ok, s); }
+    h->launches++;
+    LOCR_CUDA_OK(cudaGetLastError());
+    std::vector<float> hl(n);
+    std::vector<int32_t> hc(n), hk(n);
+    LOCR_CUDA_OK(cudaMemcpyAsync(hl.data(), d_loss, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaMemcpyAsync(hk.data(), d_ok, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (attn) LOCR_CUDA_OK(cudaMemcpyAsync(hc.data(), d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    LOCR_CUDA_OK(cudaStreamSynchronize(s));
+    // the batch scalar: CTCLoss 'mean' = mean over crops of loss / max(target length, 1); CrossEntropyLoss 'mean' =
+    // sum over counted steps / their number (fp32 like torch)
+    float acc = 0.f;
+    int64_t cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        if (attn) { acc += hl[i]; cnt += hc[i]; }
+        else acc += hl[i] / (float)(target_len[i] > 1 ? target_len[i] : 1);
+    }
+    if (cost) *cost = attn ? acc / (float)cnt : acc / (float)n;   // 0 / 0 = NaN like torch for an all-padding batch
+    if (loss) memcpy(loss, hl.data(), (size_t)n * 4);
+    if (correct) memcpy(correct, hk.data(), (size_t)n * 4);
+    return LOCR_OK;
 }
 
 LOCR_API int locr_recognize_boxes(locr_handle* h, const int32_t* image_index, const int32_t* rects, int n,

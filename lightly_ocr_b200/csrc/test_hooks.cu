@@ -259,4 +259,52 @@ LOCR_API int locr_test_lstm(const float* xproj, const float* whh, int B, int T, 
     return LOCR_OK;
 }
 
+/* The evaluation-loss kernels alone on host logits [n][26][C] (same kernels as locr_evaluate): greedy ids through the
+ * decode kernel, then the CTC loss (head_attn = 0; targets concatenated, target_len [n]) or the attention cross entropy
+ * (head_attn = 1; targets [n][targets_total / n], count [n] receives the counted steps). */
+LOCR_API int locr_test_eval_loss(int head_attn, const float* logits, int n, int C, const int32_t* targets,
+                                 const int32_t* target_len, int64_t targets_total, float* loss, int32_t* count,
+                                 int32_t* correct) {
+    if (logits == nullptr || targets == nullptr || target_len == nullptr || loss == nullptr || correct == nullptr ||
+        n <= 0 || C <= 1 || targets_total < 0)
+        return fail(LOCR_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LOCR_ERR_CUDA, "no CUDA device: liblocr has no CPU fallback");
+    std::vector<int32_t> off(n);
+    int64_t tot = 0;
+    for (int i = 0; i < n; ++i) {
+        off[i] = (int32_t)tot;
+        tot += target_len[i];
+    }
+    if (!head_attn && tot != targets_total) return fail(LOCR_ERR_INVALID, "target lengths do not add up");
+    if (head_attn && (targets_total % n != 0 || targets_total / n < 2)) return fail(LOCR_ERR_INVALID, "bad target width");
+    DevBuf dl, dt, dm, dloss, dids, dtext, dconf;
+    LOCR_CUDA_OK(dl.alloc((size_t)n * 26 * C * 4));
+    LOCR_CUDA_OK(dt.alloc((size_t)targets_total * 4 + 16));
+    LOCR_CUDA_OK(dm.alloc((size_t)n * 5 * 4));
+    LOCR_CUDA_OK(dloss.alloc((size_t)n * 4));
+    LOCR_CUDA_OK(dids.alloc((size_t)n * 26 * 4));
+    LOCR_CUDA_OK(dtext.alloc((size_t)n * 128));
+    LOCR_CUDA_OK(dconf.alloc((size_t)n * 4));
+    int32_t* m = dm.as<int32_t>();
+    LOCR_CUDA_OK(cudaMemcpy(dl.p, logits, (size_t)n * 26 * C * 4, cudaMemcpyHostToDevice));
+    if (targets_total) LOCR_CUDA_OK(cudaMemcpy(dt.p, targets, (size_t)targets_total * 4, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemcpy(m, off.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemcpy(m + n, target_len, (size_t)n * 4, cudaMemcpyHostToDevice));
+    LOCR_CUDA_OK(cudaMemset(m + 2 * n, 0, (size_t)n * 3 * 4));
+    launch_decode(dl.as<float>(), n, C, head_attn, dids.as<int32_t>(), dtext.as<char>(), 128, m + 4 * n, dconf.as<float>(), 0);
+    if (head_attn)
+        launch_attn_ce(dl.as<float>(), n, C, dt.as<int32_t>(), (int)(targets_total / n), dids.as<int32_t>(),
+                       dloss.as<float>(), m + 2 * n, m + 3 * n, 0);
+    else
+        launch_ctc_loss(dl.as<float>(), n, C, dt.as<int32_t>(), m, m + n, dids.as<int32_t>(), dloss.as<float>(), m + 3 * n, 0);
+    LOCR_CUDA_OK(cudaGetLastError());
+    LOCR_CUDA_OK(cudaDeviceSynchronize());
+    LOCR_CUDA_OK(cudaMemcpy(loss, dloss.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    LOCR_CUDA_OK(cudaMemcpy(correct, m + 3 * n, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (count) LOCR_CUDA_OK(cudaMemcpy(count, m + 2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return LOCR_OK;
+}
+
 }  // extern "C"

@@ -36,6 +36,12 @@ class CTCLabelConverter:
         self.dict = {c: i + 1 for i, c in enumerate(character)}
         self.character = ["[blank]"] + list(character)
 
+    def encode(self, text, batch_max_len=25):
+        """(concatenated class indices int32, lengths int32) of a list of labels (recog_utils.py:24-30)."""
+        import numpy as np
+        length = [len(t) for t in text]
+        return (np.array([self.dict[c] for c in "".join(text)], np.int32), np.array(length, np.int32))
+
     def decode(self, text, length):
         texts, index = [], 0
         for l in length:
@@ -54,6 +60,18 @@ class AttnLabelConverter:
     def __init__(self, character):
         self.character = ["[GO]", "[s]"] + list(character)
         self.dict = {c: i for i, c in enumerate(self.character)}
+
+    def encode(self, text, batch_max_len=25):
+        """([n, batch_max_len + 2] int32 rows: [GO], the label's tokens, [s], [GO] padding; lengths + 1) of a list of
+        labels (recog_utils.py:84-96).  The reference returns from inside its loop, i.e. fills row 0 only; every row is
+        filled here."""
+        import numpy as np
+        length = [len(t) + 1 for t in text]
+        out = np.zeros((len(text), batch_max_len + 2), np.int32)
+        for i, t in enumerate(text):
+            ids = [self.dict[c] for c in t] + [self.dict["[s]"]]
+            out[i, 1:1 + len(ids)] = ids
+        return out, np.array(length, np.int32)
 
     def decode(self, text, length):
         return ["".join(self.character[int(i)] for i in text[index]) for index, _ in enumerate(length)]

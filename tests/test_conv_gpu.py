@@ -52,6 +52,11 @@ CASES = [
     ("cta2_1x1_views", 3, 200, 136, 192, 128, 1, 1, (1, 1), (0, 0), 1, True, False, False, 1, 64, 64, 0),
     ("cta2_odd_tiles", 5, 122, 126, 64, 128, 3, 3, (1, 1), (1, 1), 1, False, False, False, 0, 0, 0, 0),
     ("cta2_crnn_layer1", 125, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    # N = 256 tiles on CTA pairs (LOCR_CONV_CTA2_N256): the 512-channel CRNN / VGG patterns, odd m-tile counts, 1x1
+    ("cta2_n256_crnn_c512", 33, 4, 26, 512, 512, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    ("cta2_n256_vgg_c256", 2, 80, 60, 128, 256, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
+    ("cta2_n256_dil6_c1024", 1, 40, 30, 256, 1024, 3, 3, (6, 6), (6, 6), 1, False, False, False, 0, 0, 0, 0),
+    ("cta2_n256_1x1", 3, 40, 30, 1024, 512, 1, 1, (1, 1), (0, 0), 1, True, False, False, 1, 0, 0, 0),
 ]
 
 
@@ -96,6 +101,8 @@ POOL_CASES = [
     ("c32_sw64", 2, 16, 36, 32, 32, 0, 0),
     ("cta2_vgg_c128", 4, 160, 128, 128, 128, 0, 0),      # the slice1.10 pattern on the CTA-pair kernels
     ("cta2_crnn_conv1", 125, 16, 50, 128, 128, 0, 0),
+    ("cta2_n256_vgg_c256", 2, 80, 60, 256, 256, 0, 0),   # the slice3.20 pattern (N = 256 tiles on CTA pairs)
+    ("cta2_n256_vgg_c512", 2, 40, 30, 512, 512, 1, 0),
 ]
 
 
@@ -142,13 +149,14 @@ def test_conv_halo_mode_64_to_64(shape, act):
 def test_cta_pair_kernels_on_every_eligible_layer():
     """By default only the K >= 1152 layers with N = 128 take the CTA-pair kernels (cta_group::2).  The switch is read
     once per process, so the `cta2_*` cases above are re-run in a child process with LOCR_CONV_CTA2=2, where every
-    eligible layer - small K, 1x1, residual, fused pools, odd tile counts - goes through them."""
+    eligible layer - small K, 1x1, residual, fused pools, odd tile counts, and (LOCR_CONV_CTA2_N256=2) the N = 256 tiles of
+    the 256- / 512- / 1024-channel layers - goes through them."""
     import os
     import subprocess
     import sys
     if os.environ.get("LOCR_CONV_CTA2") == "2":
         pytest.skip("already inside the child process")
-    env = dict(os.environ, LOCR_CONV_CTA2="2")
+    env = dict(os.environ, LOCR_CONV_CTA2="2", LOCR_CONV_CTA2_N256="2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "cta2 and not every_eligible"],
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
