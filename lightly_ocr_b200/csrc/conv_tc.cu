@@ -61,6 +61,7 @@ struct ConvParams {
     int n_tile, n_tile_alloc, tmem_cols;
     int cin_chunks, KW, dil_h, dil_w, pad_h, pad_w, stride2;
     int num_kblocks, stages;
+    int kgroup;          // k-blocks per barrier round (1..4): the slots of a group share one full / empty barrier pair
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
     void* y;
@@ -348,6 +349,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         phase ^= 1u;
                     }
                 }
+            } else if (!CTA2 && p.kgroup > 1) {
+                // Grouped barrier rounds (layers whose k-block holds fewer MMA cycles than one producer -> issuer ->
+                // commit hand-shake costs, N <= 64): the G consecutive slots of a group share ONE full / empty barrier
+                // pair - one wait, one expect-tx of the whole group's bytes, G pairs of loads.  A group never spans
+                // two tiles; a short last group leaves its remaining slots unused.
+                const int G = p.kgroup;
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
+                    const TileCoord t = decode_tile(p, tile_of(tile));
+                    int kcoord = 0, g = 0, rem = p.num_kblocks;
+                    for (int kh = 0; kh < KH; ++kh) {
+                        const int c2 = p.stride2 ? kh : 0;
+                        const int c3 = p.stride2 ? t.oh0 : t.oh0 + kh * p.dil_h - p.pad_h;
+                        int iw0 = t.ow0 - p.pad_w;
+                        for (int kw = 0; kw < p.KW; ++kw, iw0 += p.dil_w) {
+                            for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
+                                if (g == 0) ptx::mbar_wait_a(empty_s, phase, 100);
+                                int cch = cc * BLOCK_K;
+                                if (cch >= p.cin_wrap) cch -= p.cin_wrap;
+                                if (ptx::elect_one()) {
+                                    if (g == 0) ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes * (uint32_t)(rem < G ? rem : G));
+                                    ptx::tma_load_5d_a(a_s + (uint32_t)g * p.a_stage_bytes, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
+                                    ptx::tma_load_2d_a(b_s + (uint32_t)g * p.b_stage_bytes, &tmap_w, full_s, kcoord, t.n0);
+                                }
+                                ++g; --rem;
+                                if (g == G || rem == 0) {
+                                    g = 0;
+                                    a_s += (uint32_t)G * p.a_stage_bytes; b_s += (uint32_t)G * p.b_stage_bytes;
+                                    full_s += 8; empty_s += 8;
+                                    if (a_s == a_end) {
+                                        a_s = a0; b_s = b0s; full_s = full0; empty_s = empty0;
+                                        phase ^= 1u;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
             } else
             for (int tile = t_begin; tile < t_end; tile += t_step) {
                 const TileCoord t = decode_tile(p, tile_of(tile));
@@ -477,6 +515,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         a_lo = a_lo0; full_s = full0; empty_s = empty0;
                         phase ^= 1u;
                     }
+                    acc ^= 1u;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+            } else if (!CTA2 && p.kgroup > 1) {
+                // grouped barrier rounds (see the producer): one wait and one commit per group of G k-blocks
+                const int G = p.kgroup;
+                const uint32_t full_gend = full0 + 8u * (uint32_t)(p.stages / G);
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
+                    ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    uint32_t accum = 0;
+                    for (int kb = 0; kb < p.num_kblocks; kb += G) {
+                        const int gc = p.num_kblocks - kb < G ? p.num_kblocks - kb : G;
+                        ptx::mbar_wait_a(full_s, phase, 300);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            uint32_t aj = a_lo, bj = b_lo;
+                            for (int j = 0; j < gc; ++j, aj += a_step, bj += b_step) {
+#pragma unroll
+                                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+#pragma unroll
+                                    for (int hf = 0; hf < HALVES; ++hf)
+                                        ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), aj + hf * kHalfStep + k * 2,
+                                                           desc_hi, bj + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
+                                }
+                                accum = 1;
+                            }
+                            ptx::umma_commit_a(empty_s);
+                        }
+                        accum = 1;
+                        a_lo += (uint32_t)G * a_step; b_lo += (uint32_t)G * b_step; full_s += 8; empty_s += 8;
+                        if (full_s == full_gend) {
+                            a_lo = a_lo0; b_lo = b_lo0; full_s = full0; empty_s = empty0;
+                            phase ^= 1u;
+                        }
+                    }
+                    if (ptx::elect_one()) ptx::umma_commit_a(tfull0 + acc * 8u);
                     acc ^= 1u;
                     if (acc == 0) acc_phase ^= 1u;
                 }
@@ -1276,21 +1352,29 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     static int allow_cta2 = -1;
     if (allow_cta2 < 0) {
         const char* e = getenv("LOCR_CONV_CTA2");
-        const char* ee = getenv("LOCR_CONV_EPI");
-        allow_cta2 = (ee ? atoi(ee) : 1) ? (e ? atoi(e) : 1) : 0;  // the pair kernels exist for the compile-time epilogues
+        allow_cta2 = e ? atoi(e) : 1;
     }
     const int elem_c = c.out_fp32 ? 4 : 2;
-    // N = 256 tiles (M = 128 per CTA, the 256- and 512-channel layers): a pair runs M = 256 x N = 256 MMAs, each CTA
-    // staging 16 KB of A and 16 KB (half) of B per k-block instead of 16 + 32 KB.  LOCR_CONV_CTA2_N256=1 enables it.
-    static int allow_cta2_n256 = -1;
-    if (allow_cta2_n256 < 0) { const char* e = getenv("LOCR_CONV_CTA2_N256"); allow_cta2_n256 = e ? atoi(e) : 0; }
-    const bool cta2_shape = (halves == 2 && n_tile == 128 && (allow_cta2 >= 2 || c.KH * c.KW * p.cin_chunks >= 18)) ||
+    // N = 256 tiles (M = 128 per CTA, the 256- / 512- / 1024-channel layers) run as pairs too: M = 256 x N = 256 MMAs,
+    // each CTA staging 16 KB of A and 16 KB (half) of B per k-block instead of 16 + 32 KB - measured 1497 -> 1617 TFLOP/s
+    // on the 512-channel VGG layers (98 % of the burst peak) and, because the halved operand traffic also lowers the
+    // power per FLOP, +6.5 % on the power-capped end-to-end bench.  LOCR_CONV_CTA2_N256=0 switches it off, =2 takes
+    // every eligible layer; LOCR_CONV_CTA2_MINKB overrides the k-block threshold.
+    static int allow_cta2_n256 = -1, cta2_min_kb = 18;
+    if (allow_cta2_n256 < 0) {
+        const char* e = getenv("LOCR_CONV_CTA2_N256");
+        allow_cta2_n256 = e ? atoi(e) : 1;
+        const char* m = getenv("LOCR_CONV_CTA2_MINKB");
+        if (m) cta2_min_kb = atoi(m);
+    }
+    const int kblocks_all = c.KH * c.KW * p.cin_chunks;
+    const bool cta2_shape = (halves == 2 && n_tile == 128 && (allow_cta2 >= 2 || kblocks_all >= cta2_min_kb)) ||
                             (halves == 1 && n_tile == 256 && allow_cta2_n256 &&
-                             (allow_cta2_n256 >= 2 || c.KH * c.KW * p.cin_chunks >= 18));
-    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && cta2_shape && !c.out_fp32 &&
-                      !c.split_out && c.cin_wrap == 0 && c.tail_out == nullptr && c.x_row_px == 0 && c.y_row_px == 0 &&
-                      (c.y_pitch * elem_c) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
-                      (long)p.tiles_w * p.tiles_h * tiles_b >= 2;
+                             (allow_cta2_n256 >= 2 || kblocks_all >= (cta2_min_kb < 16 ? cta2_min_kb : 16)));
+    // split-precision inputs / outputs and fp32 outputs take the pair form of the generic epilogue (EPI = 0)
+    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && cta2_shape && c.tail_out == nullptr &&
+                      c.x_row_px == 0 && c.y_row_px == 0 && (long)p.tiles_w * p.tiles_h * tiles_b >= 2;
+    (void)elem_c;
     const int n_load = cta2 ? n_tile / 2 : n_tile;      // weight rows each CTA stages per k-block
     p.num_pair_tiles = (int)((((long)p.tiles_w * p.tiles_h * tiles_b + 1) / 2) * p.tiles_n);
     p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
@@ -1312,9 +1396,28 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                               (first ? 3 * 256 * 2 : 0);
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
+    const int stages_fit = stages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
     if (stages < 2 || halo) stages = 2;
     if (first && stages > 4) stages = 4;   // barrier slot kMaxStages - 1 belongs to the resident weights (like halo)
+    // Grouped barrier rounds for the narrow layers (N <= 64: a k-block holds fewer MMA cycles than the ~380-cycle
+    // producer -> issuer -> commit hand-shake): G k-blocks per round, at least two groups in the ring.
+    // LOCR_CONV_KGROUP=1 switches it off, 2..4 forces a group size.
+    p.kgroup = 1;
+    {
+        static int kg_env = -1;
+        if (kg_env < 0) { const char* e = getenv("LOCR_CONV_KGROUP"); kg_env = e ? atoi(e) : 0; }
+        if (!first && !halo && !cta2 && n_tile <= 64 && p.num_kblocks >= 2 && kg_env != 1) {
+            int G = kg_env >= 2 ? kg_env : (stages_fit >= 6 && p.num_kblocks % 3 == 0 ? 3 : 2);
+            if (G > 4) G = 4;
+            if (G > p.num_kblocks) G = p.num_kblocks;
+            while (G > 1 && stages_fit / G < 2) --G;
+            if (G > 1) {
+                p.kgroup = G;
+                stages = stages_fit / G * G;
+            }
+        }
+    }
     p.stages = stages;
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, cta2 ? 2 * kTileM : kTileM, n_tile);
     p.pool = pool;
@@ -1485,9 +1588,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         LOCR_PAIR_CASE(1, 32) LOCR_PAIR_CASE(1, 32 | kEpiRes) LOCR_PAIR_CASE(1, 32 | kEpiPool)
         LOCR_PAIR_CASE(1, 32 | kEpiPool | kEpiSkip)
 #undef LOCR_PAIR_CASE
-        if (!done) {
-            set_err(err, errlen, "conv_tc: no CTA-pair instantiation for this epilogue");
-            return cudaErrorInvalidValue;
+        if (!done) {     // generic epilogue: fp32 / split-precision outputs, unaligned outputs
+            if (halves == 2) e = launch_swz<128, 2, 0, false, true>(mx, mw, my, mp, p, grid, smem, stream);
+            else e = launch_swz<128, 1, 0, false, true>(mx, mw, my, mp, p, grid, smem, stream);
+            done = true;
         }
     }
 #define LOCR_EPI_CASE(HV, E)                                                                       \

@@ -52,6 +52,13 @@ CASES = [
     ("cta2_1x1_views", 3, 200, 136, 192, 128, 1, 1, (1, 1), (0, 0), 1, True, False, False, 1, 64, 64, 0),
     ("cta2_odd_tiles", 5, 122, 126, 64, 128, 3, 3, (1, 1), (1, 1), 1, False, False, False, 0, 0, 0, 0),
     ("cta2_crnn_layer1", 125, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    # narrow layers (N <= 64) on grouped barrier rounds (conv_tc.cu kgroup): the decoder-tail patterns
+    ("kg_c64_n32_9kb", 2, 64, 48, 64, 32, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
+    ("kg_c32_n32", 2, 64, 48, 32, 32, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
+    ("kg_1x1_c192_n64", 2, 64, 48, 192, 64, 1, 1, (1, 1), (0, 0), 1, True, False, False, 0, 0, 0, 0),
+    ("kg_c128_n64_18kb", 3, 20, 30, 128, 64, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
+    ("kg_c32_n16_fp32", 1, 33, 47, 32, 16, 3, 3, (1, 1), (1, 1), 1, False, False, True, 1, 0, 0, 0),
+    ("kg_k2_5kb", 16, 4, 26, 80, 64, 2, 2, (1, 1), (0, 1), 2, True, False, True, 1, 0, 0, 0),
     # N = 256 tiles on CTA pairs (LOCR_CONV_CTA2_N256): the 512-channel CRNN / VGG patterns, odd m-tile counts, 1x1
     ("cta2_n256_crnn_c512", 33, 4, 26, 512, 512, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
     ("cta2_n256_vgg_c256", 2, 80, 60, 128, 256, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
@@ -158,6 +165,25 @@ def test_cta_pair_kernels_on_every_eligible_layer():
         pytest.skip("already inside the child process")
     env = dict(os.environ, LOCR_CONV_CTA2="2", LOCR_CONV_CTA2_N256="2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "cta2 and not every_eligible"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    tail = (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
+
+
+@pytest.mark.parametrize("group", ["1", "2", "3", "4"])
+def test_grouped_barrier_rounds_every_group_size(group):
+    """The narrow layers (N <= 64) share one barrier round between G k-blocks (2 or 3 by default).  The switch is read once
+    per process: the `kg_*` and small-N cases are re-run in child processes with the group size forced to 1 (off) ... 4."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("LOCR_CONV_KGROUP"):
+        pytest.skip("already inside the child process")
+    env = dict(os.environ, LOCR_CONV_KGROUP=group)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "(kg_ or sw64 or sw32 or head_c37 or k2_ or 1x1_c192 or c32_sw64 or crnn_32x100) and not every"],
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     tail = (r.stdout + r.stderr)[-2000:]
