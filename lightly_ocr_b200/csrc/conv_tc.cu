@@ -61,7 +61,6 @@ struct ConvParams {
     int n_tile, n_tile_alloc, tmem_cols;
     int cin_chunks, KW, dil_h, dil_w, pad_h, pad_w, stride2;
     int num_kblocks, stages;
-    int kgroup;          // k-blocks per barrier round (1..4): the slots of a group share one full / empty barrier pair
     uint32_t a_stage_bytes, b_stage_bytes;
     uint32_t idesc;
     void* y;
@@ -327,11 +326,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const uint32_t full_lead0 = CTA2 ? ptx::mapa(full0, 0u) : 0u;     // the leader's full barriers (shared::cluster)
             const int n_half = CTA2 ? (int)rank * (p.n_tile / 2) : 0;
             if (p.halo) {
-                // resident weights: nine [64 x 64] tap slabs, once; then ONE haloed patch (18 rows x 24 pixels) per tile
+                // resident weights: nine [n_tile x Cin] tap slabs (Cin = one swizzled row), once; then ONE haloed patch
+                // (18 rows x 24 pixels) per tile
                 if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx_a(full0 + 8u * (kMaxStages - 1), 9u * 8192u);
+                    const uint32_t slab = (uint32_t)(p.n_tile * SWZ);
+                    ptx::mbar_arrive_expect_tx_a(full0 + 8u * (kMaxStages - 1), 9u * slab);
                     for (int tp = 0; tp < 9; ++tp)
-                        ptx::tma_load_2d_a(b0s + (uint32_t)tp * 8192u, &tmap_w, full0 + 8u * (kMaxStages - 1), tp * 64, 0);
+                        ptx::tma_load_2d_a(b0s + (uint32_t)tp * slab, &tmap_w, full0 + 8u * (kMaxStages - 1), tp * BLOCK_K, 0);
                 }
                 for (int tile = t_begin; tile < t_end; tile += t_step) {
                     const TileCoord t = decode_tile(p, tile_of(tile));
@@ -347,43 +348,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (a_s == a_end) {
                         a_s = a0; full_s = full0; empty_s = empty0;
                         phase ^= 1u;
-                    }
-                }
-            } else if (!CTA2 && p.kgroup > 1) {
-                // Grouped barrier rounds (layers whose k-block holds fewer MMA cycles than one producer -> issuer ->
-                // commit hand-shake costs, N <= 64): the G consecutive slots of a group share ONE full / empty barrier
-                // pair - one wait, one expect-tx of the whole group's bytes, G pairs of loads.  A group never spans
-                // two tiles; a short last group leaves its remaining slots unused.
-                const int G = p.kgroup;
-                for (int tile = t_begin; tile < t_end; tile += t_step) {
-                    const TileCoord t = decode_tile(p, tile_of(tile));
-                    int kcoord = 0, g = 0, rem = p.num_kblocks;
-                    for (int kh = 0; kh < KH; ++kh) {
-                        const int c2 = p.stride2 ? kh : 0;
-                        const int c3 = p.stride2 ? t.oh0 : t.oh0 + kh * p.dil_h - p.pad_h;
-                        int iw0 = t.ow0 - p.pad_w;
-                        for (int kw = 0; kw < p.KW; ++kw, iw0 += p.dil_w) {
-                            for (int cc = 0; cc < p.cin_chunks; ++cc, kcoord += BLOCK_K) {
-                                if (g == 0) ptx::mbar_wait_a(empty_s, phase, 100);
-                                int cch = cc * BLOCK_K;
-                                if (cch >= p.cin_wrap) cch -= p.cin_wrap;
-                                if (ptx::elect_one()) {
-                                    if (g == 0) ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes * (uint32_t)(rem < G ? rem : G));
-                                    ptx::tma_load_5d_a(a_s + (uint32_t)g * p.a_stage_bytes, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
-                                    ptx::tma_load_2d_a(b_s + (uint32_t)g * p.b_stage_bytes, &tmap_w, full_s, kcoord, t.n0);
-                                }
-                                ++g; --rem;
-                                if (g == G || rem == 0) {
-                                    g = 0;
-                                    a_s += (uint32_t)G * p.a_stage_bytes; b_s += (uint32_t)G * p.b_stage_bytes;
-                                    full_s += 8; empty_s += 8;
-                                    if (a_s == a_end) {
-                                        a_s = a0; b_s = b0s; full_s = full0; empty_s = empty0;
-                                        phase ^= 1u;
-                                    }
-                                }
-                            }
-                        }
                     }
                 }
             } else
@@ -479,7 +443,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 // absolute shared-memory address (measured: the descriptor's base-offset field must stay 0), which is
                 // exactly where the TMA unit put the data.
                 ptx::mbar_wait_a(full0 + 8u * (kMaxStages - 1), 0, 310);
-                const uint32_t hi_common = (3072u >> 4) | (1u << 14) | (2u << 29);
+                // (SWZ = 64: 32-channel layers, 64-byte pixels - the same construction on 64-byte rows)
+                const uint32_t hi_common = ((24u * (uint32_t)SWZ) >> 4) | (1u << 14) | ((SWZ == 128 ? 2u : 4u) << 29);
+                const uint32_t slab16 = (uint32_t)(p.n_tile * SWZ) >> 4;
                 for (int tile = t_begin; tile < t_end; tile += t_step) {
                     LOCR_TRACE(1, 0);
                     ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
@@ -494,12 +460,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
                             for (int kw = 0; kw < 3; ++kw) {
                                 const uint32_t a_hi = hi_common;
-                                const uint32_t b_tap = b_lo0 + (uint32_t)((kh * 3 + kw) * 8192 >> 4);
+                                const uint32_t b_tap = b_lo0 + (uint32_t)(kh * 3 + kw) * slab16;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
+                                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
 #pragma unroll
                                     for (int hf = 0; hf < 2; ++hf) {
-                                        const uint32_t a_tap = a_lo + (uint32_t)(((kh * 24 + kw + 8 * hf) * 128) >> 4) + k * 2;
+                                        const uint32_t a_tap = a_lo + (uint32_t)(((kh * 24 + kw + 8 * hf) * SWZ) >> 4) + k * 2;
                                         ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_tap, a_hi, b_tap + k * 2,
                                                            desc_hi, idesc, (kh | kw | k) ? 1u : 0u);
                                     }
@@ -515,44 +481,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         a_lo = a_lo0; full_s = full0; empty_s = empty0;
                         phase ^= 1u;
                     }
-                    acc ^= 1u;
-                    if (acc == 0) acc_phase ^= 1u;
-                }
-            } else if (!CTA2 && p.kgroup > 1) {
-                // grouped barrier rounds (see the producer): one wait and one commit per group of G k-blocks
-                const int G = p.kgroup;
-                const uint32_t full_gend = full0 + 8u * (uint32_t)(p.stages / G);
-                for (int tile = t_begin; tile < t_end; tile += t_step) {
-                    ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
-                    ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
-                    uint32_t accum = 0;
-                    for (int kb = 0; kb < p.num_kblocks; kb += G) {
-                        const int gc = p.num_kblocks - kb < G ? p.num_kblocks - kb : G;
-                        ptx::mbar_wait_a(full_s, phase, 300);
-                        ptx::tc_fence_after();
-                        if (ptx::elect_one()) {
-                            uint32_t aj = a_lo, bj = b_lo;
-                            for (int j = 0; j < gc; ++j, aj += a_step, bj += b_step) {
-#pragma unroll
-                                for (int k = 0; k < MMAS_PER_STAGE; ++k) {
-#pragma unroll
-                                    for (int hf = 0; hf < HALVES; ++hf)
-                                        ptx::umma_f16_lohi(d_tmem + (uint32_t)(hf * p.n_tile_alloc), aj + hf * kHalfStep + k * 2,
-                                                           desc_hi, bj + k * 2, desc_hi, idesc, (k == 0) ? accum : 1u);
-                                }
-                                accum = 1;
-                            }
-                            ptx::umma_commit_a(empty_s);
-                        }
-                        accum = 1;
-                        a_lo += (uint32_t)G * a_step; b_lo += (uint32_t)G * b_step; full_s += 8; empty_s += 8;
-                        if (full_s == full_gend) {
-                            a_lo = a_lo0; b_lo = b_lo0; full_s = full0; empty_s = empty0;
-                            phase ^= 1u;
-                        }
-                    }
-                    if (ptx::elect_one()) ptx::umma_commit_a(tfull0 + acc * 8u);
                     acc ^= 1u;
                     if (acc == 0) acc_phase ^= 1u;
                 }
@@ -1309,11 +1237,20 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     static int allow_halo = -1;
     if (allow_halo < 0) { const char* e = getenv("LOCR_CONV_HALO"); allow_halo = e ? atoi(e) : 1; }
     const int elem_h = 2;
+    // The same form serves the narrow decoder-tail layers (64 -> 32, and 32 -> 64 / 32 / 16 channels on 64-byte pixels,
+    // incl. the fused 1x1 tail): with one box per tap those layers pull 9 - 12 x their input through L2 -> SM and are
+    // bound by it.  LOCR_CONV_HALO=2 restricts the mode to the 64 -> 64 layers again (A/B runs).
+    const bool halo_wide = c.Cin == 64 && c.Cout_pad == 64 && n_tile == 64 && c.tail_out == nullptr;
+    const bool halo_narrow = allow_halo == 1 && !pool &&
+                             ((c.Cin == 64 && c.Cout_pad == 32 && n_tile == 32 && c.tail_out == nullptr) ||
+                              (c.Cin == 32 && (c.Cout_pad == 64 || c.Cout_pad == 32 || c.Cout_pad == 16) &&
+                               n_tile == c.Cout_pad));
     const bool halo = allow_halo && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
-                      c.pad_w == 1 && c.stride_h == 1 && c.Cin == 64 && c.cin_wrap == 0 && c.Cout_pad == 64 &&
-                      n_tile == 64 && !c.out_fp32 && !c.split_out && c.x_row_px == 0 && c.y_row_px == 0 &&
-                      c.tail_out == nullptr && c.residual == nullptr && (c.y_pitch * elem_h) % 16 == 0 &&
-                      (reinterpret_cast<uintptr_t>(c.y) % 16) == 0;
+                      c.pad_w == 1 && c.stride_h == 1 && (halo_wide || halo_narrow) && c.cin_wrap == 0 &&
+                      !c.out_fp32 && !c.split_out && c.x_row_px == 0 && (c.y_row_px == 0 || halo_narrow) &&
+                      c.residual == nullptr &&
+                      (c.tail_out != nullptr ||
+                       ((c.y_pitch * elem_h) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0));
     if (halo) {
         halves = 2; split_b = 2;
         best_bw = 8; best_bh = 16; best_bb = 1;
@@ -1380,10 +1317,10 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.a_stage_bytes = (uint32_t)(halves * kTileM * swz);
     p.b_stage_bytes = (uint32_t)((n_load * swz + 1023) / 1024 * 1024);
     if (halo) {
-        p.a_stage_bytes = 18u * 24u * 128u;          // haloed patch
-        p.b_stage_bytes = 9u * 8192u / 2u;           // x 2 "stages" = the nine resident [64 x 64] tap slabs
+        p.a_stage_bytes = 18u * 24u * (uint32_t)swz;               // haloed patch
+        p.b_stage_bytes = 9u * (uint32_t)(n_tile * swz) / 2u;      // x 2 "stages" = the nine resident tap slabs
     }
-    const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     // epilogue staging: only when the output rows keep 16-byte alignment and the n-tile splits into whole chunks
     const int elem = c.out_fp32 ? 4 : 2;
     p.stage_cols = n_tile < 128 / elem ? n_tile : 128 / elem;
@@ -1396,28 +1333,24 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                               (first ? 3 * 256 * 2 : 0);
     int stages = (int)((227 * 1024 - 1024 - tail_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    const int stages_fit = stages;
     if (stages > p.num_kblocks && p.num_kblocks >= 2) stages = p.num_kblocks;
     if (stages < 2 || halo) stages = 2;
-    if (first && stages > 4) stages = 4;   // barrier slot kMaxStages - 1 belongs to the resident weights (like halo)
-    // Grouped barrier rounds for the narrow layers (N <= 64: a k-block holds fewer MMA cycles than the ~380-cycle
-    // producer -> issuer -> commit hand-shake): G k-blocks per round, at least two groups in the ring.
-    // LOCR_CONV_KGROUP=1 switches it off, 2..4 forces a group size.
-    p.kgroup = 1;
-    {
-        static int kg_env = -1;
-        if (kg_env < 0) { const char* e = getenv("LOCR_CONV_KGROUP"); kg_env = e ? atoi(e) : 0; }
-        if (!first && !halo && !cta2 && n_tile <= 64 && p.num_kblocks >= 2 && kg_env != 1) {
-            int G = kg_env >= 2 ? kg_env : (stages_fit >= 6 && p.num_kblocks % 3 == 0 ? 3 : 2);
-            if (G > 4) G = 4;
-            if (G > p.num_kblocks) G = p.num_kblocks;
-            while (G > 1 && stages_fit / G < 2) --G;
-            if (G > 1) {
-                p.kgroup = G;
-                stages = stages_fit / G * G;
-            }
+    if (halo) {
+        // patch ring as deep as the resident slabs leave room for (one barrier round per tile: the prefetch distance is
+        // what hides the load latency); the slabs are spread over `stages` equal, 1024-byte-aligned shares
+        const size_t slabs = 9u * (size_t)(n_tile * swz);
+        static int halo_stages_max = -1;
+        if (halo_stages_max < 0) { const char* e = getenv("LOCR_CONV_HALO_STAGES"); halo_stages_max = e ? atoi(e) : 6; }
+        int st = (int)((227 * 1024 - 1024 - tail_bytes - slabs - 6 * 1024) / p.a_stage_bytes);
+        if (st > halo_stages_max) st = halo_stages_max;
+        if (st > kMaxStages - 2) st = kMaxStages - 2;      // barrier slot kMaxStages - 1 belongs to the resident weights
+        if (st > 2) {
+            stages = st;
+            p.b_stage_bytes = (uint32_t)(((slabs + st - 1) / st + 1023) / 1024 * 1024);
+            stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
         }
     }
+    if (first && stages > 4) stages = 4;   // barrier slot kMaxStages - 1 belongs to the resident weights (like halo)
     p.stages = stages;
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, cta2 ? 2 * kTileM : kTileM, n_tile);
     p.pool = pool;
@@ -1564,7 +1497,9 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     static int allow_epi = -1;
     if (allow_epi < 0) { const char* ev = getenv("LOCR_CONV_EPI"); allow_epi = ev ? atoi(ev) : 1; }
     int epi = 0;
-    if (allow_epi && swz == 128 && p.tma_store && c.tail_out == nullptr && !c.split_out && !c.out_fp32 && !p.halo_pool &&
+    // (64-byte operand rows: only the plain M = 256 / 64-column form, the 8-channel first layer)
+    const bool epi_swz = swz == 128 || (swz == 64 && halves == 2 && c.residual == nullptr && !pool);
+    if (allow_epi && epi_swz && p.tma_store && c.tail_out == nullptr && !c.split_out && !c.out_fp32 && !p.halo_pool &&
         c.res_lo_off == 0 &&
         (p.stage_cols == 64 || p.stage_cols == 32)) {
         epi = p.stage_cols / 2;
@@ -1593,6 +1528,14 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
             else e = launch_swz<128, 1, 0, false, true>(mx, mw, my, mp, p, grid, smem, stream);
             done = true;
         }
+    }
+    if (!done && swz == 64 && epi == 32) {
+        e = launch_swz<64, 2, 32>(mx, mw, my, mp, p, grid, smem, stream);
+        done = true;
+    }
+    if (!done && swz == 64 && epi == 16) {
+        e = launch_swz<64, 2, 16>(mx, mw, my, mp, p, grid, smem, stream);
+        done = true;
     }
 #define LOCR_EPI_CASE(HV, E)                                                                       \
     if (!done && halves == HV && epi == (E)) {                                                     \

@@ -137,8 +137,8 @@ int fold_conv(locr_handle* h, int model, const std::string& prefix, const std::s
             // 3x3 conv as KH = 3 taps over a 4-pixel window (conv_tc.cuh: x_row_px): K per tap = 4 * cpp with
             // k = dx * cpp + c for the pixel x - 1 + dx; the 4th pixel and padded channels get zero weights
             const int cpp = cin_pad > 0 ? cin_pad : cin;
-            if (kh != 3 || kw != 3 || (4 * cpp) % 64 != 0)
-                return h->fail(LOCR_ERR_INVALID, prefix + ": window view needs a 3x3 conv with 16 or 32 channels per pixel");
+            if (kh != 3 || kw != 3 || (4 * cpp) % 32 != 0 || cin > cpp)
+                return h->fail(LOCR_ERR_INVALID, prefix + ": window view needs a 3x3 conv with 8, 16 or 32 channels per pixel");
             const int K = 4 * cpp;
             std::vector<uint16_t> w16((size_t)cw.cout_pad * 3 * K, 0);
             for (int n = 0; n < cout; ++n)
@@ -338,6 +338,13 @@ void engine_release(locr_handle* h, const std::string& name) {
 }
 
 // ------------------------------------------------------------------------------------------------ CRAFT
+// LOCR_FIRST_CH8=0 goes back to the 16-channel input tensor of the first CRAFT layer (A/B runs).
+static bool first_c8() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LOCR_FIRST_CH8"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 static const char* kCraftBn[][2] = {
     {"basenet.slice1.3", "basenet.slice1.4"},   {"basenet.slice1.7", "basenet.slice1.8"},
     {"basenet.slice1.10", "basenet.slice1.11"}, {"basenet.slice2.14", "basenet.slice2.15"},
@@ -357,8 +364,12 @@ static const char* kCraftBn[][2] = {
 int engine_finalize_craft(locr_handle* h) {
     int rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 16, false, true);
     if (rc != LOCR_OK) return rc;
-    // the same layer as an im2col GEMM fed straight from the uint8 image (experiment, LOCR_FIRST_FUSED=1)
+    // the same layer over an 8-channel input tensor (16-byte pixels: half the pre-processing write and half the A traffic)
     h->conv["basenet.slice1.0#w"] = h->conv["basenet.slice1.0"];
+    rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 8, false, true);
+    if (rc != LOCR_OK) return rc;
+    h->conv["basenet.slice1.0#c8"] = h->conv["basenet.slice1.0"];
+    // the same layer as an im2col GEMM fed straight from the uint8 image (experiment, LOCR_FIRST_FUSED=1)
     rc = fold_conv(h, LOCR_MODEL_CRAFT, "basenet.slice1.0", "basenet.slice1.1", false, false, 0, 0, false, true);
     if (rc != LOCR_OK) return rc;
     h->conv["basenet.slice1.0#im2col"] = h->conv["basenet.slice1.0"];
@@ -369,6 +380,12 @@ int engine_finalize_craft(locr_handle* h) {
                             std::string(e[0]) == "conv_cls.4";
         rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false, false, 0, false, window);
         if (rc != LOCR_OK) return rc;
+        if (window) {
+            // "#w": packed for the 4-pixel window view (LOCR_HEAD_HALO=0); the plain layout serves the haloed-patch form
+            h->conv[std::string(e[0]) + "#w"] = h->conv[e[0]];
+            rc = fold_conv(h, LOCR_MODEL_CRAFT, e[0], e[1], false, false, 0, false, false);
+            if (rc != LOCR_OK) return rc;
+        }
     }
     {
         const HostTensor* w6 = find(h, LOCR_MODEL_CRAFT, "conv_cls.6.weight");
@@ -423,11 +440,14 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     void* y3 = c.buf("y3", px / 16 * 64 * 2);
     void* u4a = c.buf("u4a", px / 4 * 64 * 2);
     // inputs of the 32-channel 3x3 head convs: rows padded to W/2 + 3 pixels (zero pixel left, two right), see conv_tc.cuh
+    // (LOCR_HEAD_HALO=0, the round-1 form; by default these layers take the haloed-patch form of conv_tc and plain tensors)
+    static int head_halo = -1;
+    if (head_halo < 0) { const char* e = getenv("LOCR_HEAD_HALO"); head_halo = e ? atoi(e) : 1; }
     const long W2p = W / 2 + 3;
-    const size_t padded32 = (size_t)B * (H / 2) * W2p * 32 * 2;
-    uint16_t* feat = (uint16_t*)c.zbuf("feature", padded32);
-    uint16_t* c0 = (uint16_t*)c.zbuf("c0", padded32);
-    uint16_t* c2 = (uint16_t*)c.zbuf("c2", padded32);
+    const size_t padded32 = (size_t)B * (H / 2) * W2p * 32 * 2, plain32 = (size_t)B * (H / 2) * (W / 2) * 32 * 2;
+    uint16_t* feat = head_halo ? (uint16_t*)c.buf("feature", plain32) : (uint16_t*)c.zbuf("feature_p", padded32);
+    uint16_t* c0 = head_halo ? (uint16_t*)c.buf("c0", plain32) : (uint16_t*)c.zbuf("c0_p", padded32);
+    uint16_t* c2 = head_halo ? (uint16_t*)c.buf("c2", plain32) : (uint16_t*)c.zbuf("c2_p", padded32);
     float* sc = (float*)c.buf("score", px / 4 * 2 * 4);
     if (c.rc != LOCR_OK) return c.rc;
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
@@ -441,6 +461,14 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
         // latency-bound (~3300 cycles per 256-pixel tile); see DESIGN.md "measured and rejected".
         c.first(d_images, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3);
         c.tc("basenet.slice1.0#im2col", d_images, B, H, W, 32, a0, 64, 1, 0, 0);
+    } else if (first_c8()) {
+        // 8 channels per pixel (3 used): the 4-pixel window is a 64-byte row (K = 32 per vertical tap)
+        void* x8 = c.buf("x16", (size_t)B * H * (W + 3) * 8 * 2);   // rows padded: [zero | W pixels | zero zero]
+        if (c.rc != LOCR_OK) return c.rc;
+        { ProfScope ps_(h, "preproc_nhwc16", 0, false); launch_preproc_nhwc16(d_images, B, H, W, img_h, img_w, (long)img_w * 3, (long)img_h * img_w * 3, x8, f16, s, 8); }
+        h->launches++;
+        c.rows(W + 3, 0);
+        c.tc("basenet.slice1.0#c8", x8, B, H, W, 8, a0, 64, 1, 1, 0);
     } else {
         void* x16 = c.buf("x16", (size_t)B * H * (W + 3) * 16 * 2);   // rows padded: [zero | W pixels | zero zero]
         if (c.rc != LOCR_OK) return c.rc;
@@ -479,16 +507,25 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     c.tc("upconv3.conv.3", u3a, B, H4, W4, 128, y3, 64, 1, 1, 1);
     { ProfScope ps_(h, "upsample.3", 0, false); launch_upsample2x(y3, 64, B, H4, W4, 64, cat4, 192, f16, s); }
     c.tc("upconv4.conv.0", cat4, B, H2, W2, 192, u4a, 64, 1, 0, 0);
-    c.rows(0, W2p);
-    c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat + 32, 32, 1, 1, 1);
-    c.rows(W2p, W2p);
-    c.tc("conv_cls.0", feat, B, H2, W2, 32, c0 + 32, 32, 1, 1, 0);
-    c.rows(W2p, W2p);
-    c.tc("conv_cls.2", c0, B, H2, W2, 32, c2 + 32, 32, 1, 1, 0);
-    c.rows(W2p, 0);
-    // conv_cls.4 + ReLU with conv_cls.6 + ReLU + conv_cls.8 (both 1x1) applied in the epilogue registers (fp32)
-    c.tail(h->f32["craft.cls_tail"], sc);
-    c.tc("conv_cls.4", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 0);
+    if (head_halo) {
+        // 3x3 layers with <= 64 input and <= 64 output channels: one haloed patch per 16 x 16 tile (conv_tc.cu halo mode)
+        c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat, 32, 1, 1, 1);
+        c.tc("conv_cls.0", feat, B, H2, W2, 32, c0, 32, 1, 1, 1);
+        c.tc("conv_cls.2", c0, B, H2, W2, 32, c2, 32, 1, 1, 1);
+        // conv_cls.4 + ReLU with conv_cls.6 + ReLU + conv_cls.8 (both 1x1) applied in the epilogue registers (fp32)
+        c.tail(h->f32["craft.cls_tail"], sc);
+        c.tc("conv_cls.4", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 1);
+    } else {
+        c.rows(0, W2p);
+        c.tc("upconv4.conv.3", u4a, B, H2, W2, 64, feat + 32, 32, 1, 1, 1);
+        c.rows(W2p, W2p);
+        c.tc("conv_cls.0#w", feat, B, H2, W2, 32, c0 + 32, 32, 1, 1, 0);
+        c.rows(W2p, W2p);
+        c.tc("conv_cls.2#w", c0, B, H2, W2, 32, c2 + 32, 32, 1, 1, 0);
+        c.rows(W2p, 0);
+        c.tail(h->f32["craft.cls_tail"], sc);
+        c.tc("conv_cls.4#w", c2, B, H2, W2, 32, nullptr, 16, 1, 1, 0);
+    }
     h->launches += 4;  // 1 max-pool (3x3 s1) + 3 up-samplings
     if (c.rc != LOCR_OK) return c.rc;
     LOCR_CUDA_OK(cudaGetLastError());
@@ -498,7 +535,8 @@ int engine_craft_forward(locr_handle* h, const uint8_t* d_images, int B, int img
     dbg(h, "relu4_3", cat2 + 256, 0, {B, H8, W8, 512}, 768);
     dbg(h, "relu5_3", cat1 + 1024, 0, {B, H16, W16, 512}, 1536);
     dbg(h, "fc7", cat1, 0, {B, H16, W16, 1024}, 1536);
-    dbg(h, "feature", feat, 0, {B, H2, (int)W2p, 32}, 32);   // row-padded: columns 1 .. W/2 hold the tensor
+    if (head_halo) dbg(h, "feature", feat, 0, {B, H2, W2, 32}, 32);
+    else dbg(h, "feature", feat, 0, {B, H2, (int)W2p, 32}, 32);   // row-padded: columns 1 .. W/2 hold the tensor
     dbg(h, "score", sc, 1, {B, H2, W2, 2}, 2);
     *score = sc;
     return LOCR_OK;

@@ -250,6 +250,33 @@ preproc_nhwc16_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int i
     }
 }
 
+// Same with 8 channels per pixel (3 used): one thread and one 16-byte store per pixel.
+__global__ void __launch_bounds__(256)
+preproc_nhwc8_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int img_h, int img_w, long row_stride,
+                     long img_stride, uint16_t* __restrict__ out, int f16) {
+    const float mean[3] = {(float)(0.485 * 255.0), (float)(0.456 * 255.0), (float)(0.406 * 255.0)};
+    const float stdv[3] = {(float)(0.229 * 255.0), (float)(0.224 * 255.0), (float)(0.225 * 255.0)};
+    const uint32_t Wp = (uint32_t)W + 3;
+    const uint32_t total = (uint32_t)B * H * Wp;
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+        const int xp = (int)(pix % Wp);
+        const uint32_t rest = pix / Wp;
+        const int y = (int)(rest % (uint32_t)H);
+        const int b = (int)(rest / (uint32_t)H);
+        const int x = xp - 1;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (x >= 0 && x < W) {
+            const bool inside = (y < img_h) && (x < img_w);
+            const uint8_t* p = in + (long)b * img_stride + (long)y * row_stride + x * 3;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = ((inside ? (float)p[c] : 0.0f) - mean[c]) / stdv[c];
+            val = pack8(v, f16);
+        }
+        reinterpret_cast<uint4*>(out)[pix] = val;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- max pool
 __device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b, int f16) {
     if (f16) {
@@ -956,7 +983,13 @@ void launch_absmax(const void* t, long rows, int C, long pitch, int is_f16, floa
 }
 
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
-                           long img_stride, void* out, int is_f16, cudaStream_t s) {
+                           long img_stride, void* out, int is_f16, cudaStream_t s, int channels) {
+    if (channels == 8) {
+        const long total8 = (long)B * H * (W + 3);
+        preproc_nhwc8_kernel<<<grid_for(total8, 256), 256, 0, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
+                                                                   (uint16_t*)out, is_f16);
+        return;
+    }
     const long total = (long)B * H * (W + 3) * 2;
     preproc_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, B, H, W, img_h, img_w, row_stride, img_stride,
                                                                (uint16_t*)out, is_f16);

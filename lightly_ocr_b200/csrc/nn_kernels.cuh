@@ -27,8 +27,9 @@ void launch_direct_conv3x3(const void* in, int u8_mode, int B, int H, int W, int
 // CRAFT.preproc's normalisation (imgproc.py:19-25) of the zero-padded canvas: uint8 BGR -> 16-bit NHWC with 16
 // channels (3 used), the input layout of the tensor-core path of basenet.slice1.0.  Output rows are padded to W + 3
 // pixels (one zero pixel on the left, two on the right): out is [B][H][W + 3][16] (conv_tc.cuh: x_row_px).
+// channels = 8: the same with 8 channels per pixel (16-byte pixels; half the bytes written and read back).
 void launch_preproc_nhwc16(const uint8_t* in, int B, int H, int W, int img_h, int img_w, long row_stride,
-                           long img_stride, void* out, int is_f16, cudaStream_t s);
+                           long img_stride, void* out, int is_f16, cudaStream_t s, int channels = 16);
 
 void launch_maxpool(const void* in, long in_pitch, int B, int H, int W, int C, void* out, long out_pitch, int kh,
                     int kw, int sh, int sw, int ph, int pw, int is_f16, cudaStream_t s, int split = 0);

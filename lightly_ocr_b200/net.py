@@ -147,7 +147,10 @@ class CRAFT(Placeholder):
         arr = x.detach().cpu().numpy()
         canvas = np.rint(arr.transpose(0, 2, 3, 1) * _STD + _MEAN).clip(0, 255).astype(np.uint8)
         y = self.engine.craft_scores(canvas)
-        feat = self.engine.debug_read("feature").transpose(0, 3, 1, 2)
+        feat = self.engine.debug_read("feature")
+        if feat.shape[2] == y.shape[2] + 3:       # row-padded tensor (LOCR_HEAD_HALO=0): one zero pixel left, two right
+            feat = feat[:, :, 1:-2]
+        feat = feat.transpose(0, 3, 1, 2)
         return torch.from_numpy(y), torch.from_numpy(np.ascontiguousarray(feat))
 
     def preproc(self, image):

@@ -52,7 +52,8 @@ CASES = [
     ("cta2_1x1_views", 3, 200, 136, 192, 128, 1, 1, (1, 1), (0, 0), 1, True, False, False, 1, 64, 64, 0),
     ("cta2_odd_tiles", 5, 122, 126, 64, 128, 3, 3, (1, 1), (1, 1), 1, False, False, False, 0, 0, 0, 0),
     ("cta2_crnn_layer1", 125, 16, 50, 128, 128, 3, 3, (1, 1), (1, 1), 1, True, True, False, 0, 0, 0, 0),
-    # narrow layers (N <= 64) on grouped barrier rounds (conv_tc.cu kgroup): the decoder-tail patterns
+    # narrow layers (N <= 64): the decoder-tail patterns, odd k-block counts
+    ("c32_n64_m256_sw64", 2, 64, 48, 32, 64, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
     ("kg_c64_n32_9kb", 2, 64, 48, 64, 32, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
     ("kg_c32_n32", 2, 64, 48, 32, 32, 3, 3, (1, 1), (1, 1), 1, True, False, False, 0, 0, 0, 0),
     ("kg_1x1_c192_n64", 2, 64, 48, 192, 64, 1, 1, (1, 1), (0, 0), 1, True, False, False, 0, 0, 0, 0),
@@ -153,6 +154,27 @@ def test_conv_halo_mode_64_to_64(shape, act):
     assert err <= tol, "max abs err %g > tol %g" % (err, tol)
 
 
+@pytest.mark.parametrize("chan", [(64, 32), (32, 64), (32, 32), (32, 16)], ids=str)
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 80, 60), (3, 20, 100)], ids=str)
+@pytest.mark.parametrize("act", [0, 1])
+def test_conv_halo_mode_narrow_layers(shape, chan, act):
+    """The haloed-patch form on the decoder-tail shapes: 64 -> 32 channels (128-byte pixels, N = 32) and 32 -> 64 / 32 /
+    16 channels (64-byte pixels: the nine taps as descriptor offsets into a 64-byte-swizzled patch)."""
+    from lightly_ocr_b200 import bridge
+    B, H, W = shape
+    cin, cout = chan
+    rng = np.random.default_rng(B * 1000 + H * 10 + W + act + 7 * cin + cout)
+    x = rng.standard_normal((B, H, W, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, cin)) / np.sqrt(9 * cin)).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    y = bridge.test_conv(x, w, bias, None, pad=(1, 1), relu=True, out_fp32=False, act_dtype=act)
+    ref = _ref(x, w, bias, None, (1, 1), (1, 1), 1, True, act)
+    scale = float(np.abs(ref).max())
+    tol = 2e-3 * scale + scale * (2.0 ** -8 if act == 1 else 2.0 ** -11)
+    err = float(np.abs(y - ref).max())
+    assert err <= tol, "max abs err %g > tol %g" % (err, tol)
+
+
 def test_cta_pair_kernels_on_every_eligible_layer():
     """By default only the K >= 1152 layers with N = 128 take the CTA-pair kernels (cta_group::2).  The switch is read
     once per process, so the `cta2_*` cases above are re-run in a child process with LOCR_CONV_CTA2=2, where every
@@ -171,21 +193,3 @@ def test_cta_pair_kernels_on_every_eligible_layer():
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
 
-
-@pytest.mark.parametrize("group", ["1", "2", "3", "4"])
-def test_grouped_barrier_rounds_every_group_size(group):
-    """The narrow layers (N <= 64) share one barrier round between G k-blocks (2 or 3 by default).  The switch is read once
-    per process: the `kg_*` and small-N cases are re-run in child processes with the group size forced to 1 (off) ... 4."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("LOCR_CONV_KGROUP"):
-        pytest.skip("already inside the child process")
-    env = dict(os.environ, LOCR_CONV_KGROUP=group)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "(kg_ or sw64 or sw32 or head_c37 or k2_ or 1x1_c192 or c32_sw64 or crnn_32x100) and not every"],
-                       env=env, capture_output=True, text=True, timeout=600,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    tail = (r.stdout + r.stderr)[-2000:]
-    assert r.returncode == 0, tail
-    assert " passed" in r.stdout and "failed" not in r.stdout, tail
