@@ -79,6 +79,8 @@ struct ConvParams {
     int cin_wrap;       // channel coordinate wraps at this value (split-precision inputs), huge when unused
     int split_out;      // write hi / lo halves (split-precision outputs)
     int halo;           // 3x3 / 64-channel layers: one haloed input patch per tile, the nine taps are descriptor offsets
+    int hstream;        // CTA pairs only: haloed patches (one per 64-channel chunk, ring of two) + a streamed weight ring
+    int a_slots;        // A slots in shared memory in front of the B ring (= stages; 2 patches with hstream)
     int halo_pool;      // halo tiles whose only output is the 2x2 max-pooled tensor: pooling by warp shuffles
     int pool;           // fused 2x2/2 max-pool of the activated output (TMA-store epilogue only)
     int skip_full;      // pooled output only
@@ -161,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
+    uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_stage_bytes;
     // all stage sizes are multiples of 1024 bytes, so the epilogue staging tiles that follow stay 1024-aligned
     uint8_t* staging = smem_b + (size_t)p.stages * p.b_stage_bytes;                            // 2 x [128][stage_rb]
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * 128 * 128 + (p.pool ? 2 * 32 * 128 : 0));
@@ -203,6 +205,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             ptx::mbar_init(&tempty_bar[a], CTA2 ? 16 : 8);   // CTA2: the leader also waits for the peer's epilogue warps
         }
         if (p.halo || FIRST) ptx::mbar_init(&full_bar[kMaxStages - 1], 1);   // resident weights landed
+        if (CTA2 && p.hstream)                                                // patch ring: slots kMaxStages - 2, - 1
+            for (int s = kMaxStages - 2; s < kMaxStages; ++s) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -325,7 +332,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int KH = p.num_kblocks / (p.KW * p.cin_chunks);
             const uint32_t full_lead0 = CTA2 ? ptx::mapa(full0, 0u) : 0u;     // the leader's full barriers (shared::cluster)
             const int n_half = CTA2 ? (int)rank * (p.n_tile / 2) : 0;
-            if (p.halo) {
+            if (CTA2 && p.hstream) {
+                // weight ring only (the patches come from warp 3): per tile, chunk-major, one [n_tile / 2 x 64] slab per
+                // (chunk, tap) and CTA; the leader's barrier counts the halves of both CTAs
+                const uint32_t b_bytes = 2u * (uint32_t)(p.n_tile / 2 * SWZ);
+                const uint32_t b_end = b0s + (uint32_t)p.stages * p.b_stage_bytes;
+                const int cin = p.cin_chunks * BLOCK_K;
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
+                    const TileCoord t = decode_tile(p, tile_of(tile));
+                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                        for (int tp = 0; tp < 9; ++tp) {
+                            ptx::mbar_wait_a(empty_s, phase, 120);
+                            if (ptx::elect_one()) {
+                                const uint32_t lead = full_lead0 + (full_s - full0);
+                                if (rank == 0) ptx::mbar_arrive_expect_tx_a(full_s, b_bytes);
+                                ptx::tma_load_2d_2sm(b_s, &tmap_w, lead, tp * cin + cc * BLOCK_K, t.n0 + n_half);
+                            }
+                            b_s += p.b_stage_bytes; full_s += 8; empty_s += 8;
+                            if (b_s == b_end) {
+                                b_s = b0s; full_s = full0; empty_s = empty0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            } else if (p.halo) {
                 // resident weights: nine [n_tile x Cin] tap slabs (Cin = one swizzled row), once; then ONE haloed patch
                 // (18 rows x 24 pixels) per tile
                 if (ptx::elect_one()) {
@@ -436,6 +467,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     acc ^= 1u;
                     if (acc == 0) acc_phase ^= 1u;
                 }
+            } else if (CTA2 && p.hstream) {
+                // Patches [18 rows][24 pixels][128 B] per 64-channel chunk (ring of two, barrier slots kMaxStages - 2 / - 1)
+                // against the streamed weight ring: tap (kh, kw) of half hf reads the patch from pixel (kh, kw + 8 hf) on,
+                // exactly like the resident-weight halo form below; M = 256 over the pair, N = 128.
+                const uint32_t hi_patch = ((24u * (uint32_t)SWZ) >> 4) | (1u << 14) | (2u << 29);
+                const uint32_t pfull0 = full0 + 8u * (kMaxStages - 2), pempty0 = empty0 + 8u * (kMaxStages - 2);
+                uint32_t pslot = 0, pphase = 0;
+                for (int tile = t_begin; tile < t_end; tile += t_step) {
+                    ptx::mbar_wait_a(tempty0 + acc * 8u, acc_phase, 200);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                    for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                        ptx::mbar_wait_a(pfull0 + 8u * pslot, pphase, 320);
+                        const uint32_t a_patch = a_lo0 + pslot * a_step;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                ptx::mbar_wait_a(full_s, phase, 300);
+                                ptx::tc_fence_after();
+                                if (ptx::elect_one()) {
+#pragma unroll
+                                    for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+#pragma unroll
+                                        for (int hf = 0; hf < 2; ++hf) {
+                                            const uint32_t a_tap = a_patch + (uint32_t)(((kh * 24 + kw + 8 * hf) * SWZ) >> 4) + k * 2;
+                                            ptx::umma_f16_lohi_2sm(d_tmem + (uint32_t)(hf * p.n_tile_alloc), a_tap, hi_patch,
+                                                                   b_lo + k * 2, desc_hi, idesc, (cc | kh | kw | k) ? 1u : 0u);
+                                        }
+                                    }
+                                    ptx::umma_commit_2sm(empty_s);
+                                }
+                                b_lo += b_step; full_s += 8; empty_s += 8;
+                                if (full_s == full_end) {
+                                    b_lo = b_lo0; full_s = full0; empty_s = empty0;
+                                    phase ^= 1u;
+                                }
+                            }
+                        }
+                        if (ptx::elect_one()) ptx::umma_commit_2sm(pempty0 + 8u * pslot);   // patch slot free in both CTAs
+                        pslot ^= 1u;
+                        if (pslot == 0) pphase ^= 1u;
+                    }
+                    if (ptx::elect_one()) ptx::umma_commit_2sm(tfull0 + acc * 8u);
+                    acc ^= 1u;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
             } else if (p.halo) {
                 // A patch in smem: [18 rows][24 pixels][128 B], 128B-swizzled by the TMA unit.  Tap (kh, kw) of half hf is
                 // the same patch read from pixel (kh, kw + 8 hf) on: start address + (kh * 24 + kw + 8 hf) * 128 B,
@@ -531,6 +609,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 LOCR_TRACE(1, 4);
                 acc ^= 1u;
                 if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (CTA2 && warp == 3 && p.hstream) {
+        // ------------------------------------------------------------ patch producer (hstream): one haloed patch per tile
+        // and 64-channel chunk into a ring of two; the leader's barrier counts the patches of both CTAs
+        const uint32_t a0 = ptx::smem_u32(smem_a);
+        const uint32_t pfull0 = ptx::smem_u32(full_bar) + 8u * (kMaxStages - 2);
+        const uint32_t pempty0 = ptx::smem_u32(empty_bar) + 8u * (kMaxStages - 2);
+        const uint32_t pfull_lead0 = ptx::mapa(pfull0, 0u);
+        uint32_t pslot = 0, pphase = 1;
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
+            const TileCoord t = decode_tile(p, tile_of(tile));
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                ptx::mbar_wait_a(pempty0 + 8u * pslot, pphase, 130);
+                if (ptx::elect_one()) {
+                    if (rank == 0) ptx::mbar_arrive_expect_tx_a(pfull0 + 8u * pslot, 2u * p.a_stage_bytes);
+                    ptx::tma_load_5d_2sm(a0 + pslot * p.a_stage_bytes, &tmap_x, pfull_lead0 + 8u * pslot, cc * BLOCK_K,
+                                         t.ow0 - 1, 0, t.oh0 - 1, t.b0);
+                }
+                pslot ^= 1u;
+                if (pslot == 0) pphase ^= 1u;
             }
         }
     } else if (warp >= 4 && warp < kThreads / 32) {
@@ -1251,7 +1350,21 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                       c.residual == nullptr &&
                       (c.tail_out != nullptr ||
                        ((c.y_pitch * elem_h) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0));
-    if (halo) {
+    // hstream: the N = 128 3x3 layers at high resolution (slice1.7, slice1.10) as CTA pairs over haloed patches (one per
+    // 64-channel chunk, ring of two) against a streamed weight ring: per 256-pixel tile and CTA 55 KB of A per chunk
+    // instead of nine 32 KB boxes - these layers are bound by shared-memory traffic (fills + operand reads), and the
+    // fills drop from 40 KB to ~14 KB per k-block.  Only where 16 x 16 tiles waste <= 5 % of the pixels.
+    static int allow_hstream = -1;
+    if (allow_hstream < 0) { const char* e = getenv("LOCR_CONV_HSTREAM"); allow_hstream = e ? atoi(e) : 1; }
+    bool hstream = false;
+    if (allow_hstream && !halo && !first && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
+        c.pad_w == 1 && c.stride_h == 1 && (c.Cin == 64 || c.Cin == 128) && c.cin_wrap == 0 && c.Cout_pad == 128 &&
+        n_tile == 128 && !c.out_fp32 && !c.split_out && c.x_row_px == 0 && c.y_row_px == 0 && c.tail_out == nullptr &&
+        c.residual == nullptr && (c.y_pitch * elem_h) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0) {
+        const long t16 = (long)((c.OW + 15) / 16) * ((c.OH + 15) / 16) * c.B;
+        if (t16 >= device_sm_count() && t16 * 256 * 100 <= (long)c.OW * c.OH * c.B * 105) hstream = true;
+    }
+    if (halo || hstream) {
         halves = 2; split_b = 2;
         best_bw = 8; best_bh = 16; best_bb = 1;
     }
@@ -1262,6 +1375,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.bw = best_bw; p.bh = best_bh; p.bb = best_bb;
     p.halves = halves; p.split_b = split_b;
     p.halo = halo ? 1 : 0;
+    p.hstream = hstream ? 1 : 0;
     const int full_bh = p.bh * (split_b == 0 ? halves : 1), full_bb = p.bb * (split_b == 1 ? halves : 1);
     p.tiles_w = (c.OW + p.bw * (split_b == 2 ? halves : 1) - 1) / (p.bw * (split_b == 2 ? halves : 1));
     p.tiles_h = (c.OH + full_bh - 1) / full_bh;
@@ -1309,8 +1423,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                             (halves == 1 && n_tile == 256 && allow_cta2_n256 &&
                              (allow_cta2_n256 >= 2 || kblocks_all >= (cta2_min_kb < 16 ? cta2_min_kb : 16)));
     // split-precision inputs / outputs and fp32 outputs take the pair form of the generic epilogue (EPI = 0)
-    const bool cta2 = allow_cta2 && !first && !halo && swz == 128 && cta2_shape && c.tail_out == nullptr &&
-                      c.x_row_px == 0 && c.y_row_px == 0 && (long)p.tiles_w * p.tiles_h * tiles_b >= 2;
+    const bool cta2 = hstream || (allow_cta2 && !first && !halo && swz == 128 && cta2_shape && c.tail_out == nullptr &&
+                                  c.x_row_px == 0 && c.y_row_px == 0 && (long)p.tiles_w * p.tiles_h * tiles_b >= 2);
     (void)elem_c;
     const int n_load = cta2 ? n_tile / 2 : n_tile;      // weight rows each CTA stages per k-block
     p.num_pair_tiles = (int)((((long)p.tiles_w * p.tiles_h * tiles_b + 1) / 2) * p.tiles_n);
@@ -1320,6 +1434,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         p.a_stage_bytes = 18u * 24u * (uint32_t)swz;               // haloed patch
         p.b_stage_bytes = 9u * (uint32_t)(n_tile * swz) / 2u;      // x 2 "stages" = the nine resident tap slabs
     }
+    if (hstream) p.a_stage_bytes = 18u * 24u * 128u;               // one patch per 64-channel chunk; b = half slab (8 KB)
     size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     // epilogue staging: only when the output rows keep 16-byte alignment and the n-tile splits into whole chunks
     const int elem = c.out_fp32 ? 4 : 2;
@@ -1351,6 +1466,14 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         }
     }
     if (first && stages > 4) stages = 4;   // barrier slot kMaxStages - 1 belongs to the resident weights (like halo)
+    p.a_slots = stages;
+    if (hstream) {
+        // two patch slots in front of a weight ring of up to kMaxStages - 2 half slabs (the last two barrier slots
+        // belong to the patch ring)
+        p.a_slots = 2;
+        stages = (int)((227 * 1024 - 1024 - tail_bytes - 2 * (size_t)p.a_stage_bytes) / p.b_stage_bytes);
+        if (stages > kMaxStages - 2) stages = kMaxStages - 2;
+    }
     p.stages = stages;
     p.idesc = ptx::make_idesc_f16(c.dtype == ACT_BF16 ? 1 : 0, cta2 ? 2 * kTileM : kTileM, n_tile);
     p.pool = pool;
@@ -1402,7 +1525,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const cuuint64_t xw = (cuuint64_t)(c.x_row_px > 0 ? c.x_row_px : c.W);
         cuuint64_t strides[4] = {pb, pb * xw, pb * xw * S, pb * xw * c.H};
         cuuint32_t box[5] = {(cuuint32_t)block_k, (cuuint32_t)p.bw, 1u, (cuuint32_t)full_bh, (cuuint32_t)full_bb};
-        if (halo) { box[1] = 24; box[3] = 18; box[4] = 1; }
+        if (halo || hstream) { box[1] = 24; box[3] = 18; box[4] = 1; }
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&mx, dt, 5, const_cast<void*>(c.x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1482,7 +1605,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
             return cudaErrorInvalidValue;
         }
     }
-    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
+    const size_t smem = hstream ? 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)p.stages * p.b_stage_bytes + tail_bytes
+                                : 1024 + (size_t)p.stages * stage_bytes + tail_bytes;
     if (LOCR_CONV_EXPERIMENTS && getenv("LOCR_CONV_VERBOSE"))
         fprintf(stderr, "conv_tc: %dx%dx%d cin %d cout %d k%dx%d: swz %d halves %d split %d box %dx%dx%d n_tile %d stages %d "
                 "kblocks %d tiles %d halo %d pool %d smem %zu\n", c.B, c.OH, c.OW, c.Cin, c.Cout, c.KH, c.KW, swz, halves,

@@ -175,18 +175,45 @@ def test_conv_halo_mode_narrow_layers(shape, chan, act):
     assert err <= tol, "max abs err %g > tol %g" % (err, tol)
 
 
+@pytest.mark.parametrize("cin", [64, 128])
+@pytest.mark.parametrize("shape", [(2, 160, 128), (1, 336, 240), (4, 96, 112), (1, 330, 250)], ids=str)
+@pytest.mark.parametrize("pool", [False, True])
+def test_conv_hstream_pairs(shape, cin, pool):
+    """The N = 128 3x3 layers at high resolution (slice1.7 / slice1.10) run as CTA pairs over haloed patches (one per
+    64-channel chunk) against a streamed weight ring: even and odd tile counts, ragged edges within the 5 % waste limit,
+    with and without the fused 2x2 max-pool."""
+    from lightly_ocr_b200 import bridge
+    B, H, W = shape
+    rng = np.random.default_rng(B * 1000 + H * 10 + W + cin)
+    x = rng.standard_normal((B, H, W, cin)).astype(np.float32)
+    w = (rng.standard_normal((128, 3, 3, cin)) / np.sqrt(9 * cin)).astype(np.float32)
+    bias = rng.standard_normal(128).astype(np.float32)
+    ref = _ref(x, w, bias, None, (1, 1), (1, 1), 1, True, 0)
+    scale = float(np.abs(ref).max())
+    tol = 2e-3 * scale + scale * 2.0 ** -11
+    if pool:
+        y, yp = bridge.test_conv_pool(x, w, bias, pad=(1, 1), relu=True, act_dtype=0, want_full=True)
+        want = F.max_pool2d(torch.from_numpy(y).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()
+        assert np.array_equal(yp, want)
+    else:
+        y = bridge.test_conv(x, w, bias, None, pad=(1, 1), relu=True, out_fp32=False, act_dtype=0)
+    err = float(np.abs(y - ref).max())
+    assert err <= tol, "max abs err %g > tol %g" % (err, tol)
+
+
 def test_cta_pair_kernels_on_every_eligible_layer():
     """By default only the K >= 1152 layers with N = 128 take the CTA-pair kernels (cta_group::2).  The switch is read
     once per process, so the `cta2_*` cases above are re-run in a child process with LOCR_CONV_CTA2=2, where every
     eligible layer - small K, 1x1, residual, fused pools, odd tile counts, and (LOCR_CONV_CTA2_N256=2) the N = 256 tiles of
-    the 256- / 512- / 1024-channel layers - goes through them."""
+    the 256- / 512- / 1024-channel layers - goes through them; LOCR_CONV_HSTREAM=0 there, so the shapes that take the
+    haloed-patch pair form by default are covered in the generic pair form as well."""
     import os
     import subprocess
     import sys
     if os.environ.get("LOCR_CONV_CTA2") == "2":
         pytest.skip("already inside the child process")
-    env = dict(os.environ, LOCR_CONV_CTA2="2", LOCR_CONV_CTA2_N256="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "cta2 and not every_eligible"],
+    env = dict(os.environ, LOCR_CONV_CTA2="2", LOCR_CONV_CTA2_N256="2", LOCR_CONV_HSTREAM="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "(cta2 or hstream) and not every_eligible"],
                        env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     tail = (r.stdout + r.stderr)[-2000:]

@@ -20,9 +20,15 @@ print("targets: tools/prof_kernels.py tc (one launch per layer, LOCR_BENCH_WARMU
 print("sources: gpurun_out/prof_tc_%s.ncu-rep, gpurun_out/prof_mem_%s.ncu-rep (scratch); cold-cache replays: compare "
       "shares, not absolutes\n" % (tag, tag))
 labels_tc = ["slice1.0 16->64 @1280x960 x8, plain 9-tap form (first launch of the process: cold)",
-             "slice1.3 64->64 @1280x960 x8, haloed-patch path, only the 2x2 max-pooled tensor written (as in the pipeline)", "slice1.10 128->128 @640x480 x8", "slice3.27 512->512 @160x120 x8",
-             "conv_cls.0 32->32 @640x480 x8, plain 9-tap form", "CRNN 512->512 @4x26 x640 crops",
+             "slice1.3 64->64 @1280x960 x8, haloed-patch path, only the 2x2 max-pooled tensor written (as in the pipeline)",
+             "slice1.10 128->128 @640x480 x8 (CTA pairs, N = 128)", "slice3.27 512->512 @160x120 x8 (CTA pairs, N = 256)",
+             "conv_cls.0 32->32 @640x480 x8, haloed-patch form on 64-byte pixels",
+             "upconv4.3 64->32 @640x480 x8, haloed-patch form",
+             "slice2.17 256->256 @320x240 x8 (CTA pairs, N = 256)",
+             "CRNN 512->512 @4x26 x640 crops (CTA pairs, N = 256)",
              "BiLSTM recurrence, 650 crops x 26 steps x 2 directions"]
+if tag < "r02b":      # captures before the round-2 additions to tools/prof_kernels.py
+    labels_tc = labels_tc[:5] + labels_tc[7:]
 for rep, labels in (("%s/prof_tc_%s.ncu-rep" % (root, tag), labels_tc), ("%s/prof_mem_%s.ncu-rep" % (root, tag), None)):
     raw = rep.replace(".ncu-rep", "_raw.csv")
     if os.path.exists(rep):

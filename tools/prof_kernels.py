@@ -35,6 +35,8 @@ if mode == "tc":
     run("slice1.10", 8, 640, 480, 128, 128)
     run("slice3.27", 8, 160, 120, 512, 512)
     run("cls.0", 8, 640, 480, 32, 32)
+    run("upconv4.3", 8, 640, 480, 64, 32)
+    run("slice2.17", 8, 320, 240, 256, 256)
     run("crnn512", 640, 4, 26, 512, 512)
     rng = np.random.default_rng(0)
     xp = rng.normal(0, 1, (650, 26, 2048)).astype(np.float32)
