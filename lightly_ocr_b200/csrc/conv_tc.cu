@@ -1344,26 +1344,30 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                              ((c.Cin == 64 && c.Cout_pad == 32 && n_tile == 32 && c.tail_out == nullptr) ||
                               (c.Cin == 32 && (c.Cout_pad == 64 || c.Cout_pad == 32 || c.Cout_pad == 16) &&
                                n_tile == c.Cout_pad));
-    const bool halo = allow_halo && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
+    const bool halo_base = allow_halo && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
                       c.pad_w == 1 && c.stride_h == 1 && (halo_wide || halo_narrow) && c.cin_wrap == 0 &&
                       !c.out_fp32 && !c.split_out && c.x_row_px == 0 && (c.y_row_px == 0 || halo_narrow) &&
                       c.residual == nullptr &&
                       (c.tail_out != nullptr ||
                        ((c.y_pitch * elem_h) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0));
-    // hstream: the N = 128 3x3 layers at high resolution (slice1.7, slice1.10) as CTA pairs over haloed patches (one per
+    // hstream: the 128 -> 128 3x3 layers at high resolution (slice1.10) as CTA pairs over haloed patches (one per
     // 64-channel chunk, ring of two) against a streamed weight ring: per 256-pixel tile and CTA 55 KB of A per chunk
-    // instead of nine 32 KB boxes - these layers are bound by shared-memory traffic (fills + operand reads), and the
-    // fills drop from 40 KB to ~14 KB per k-block.  Only where 16 x 16 tiles waste <= 5 % of the pixels.
+    // instead of nine 32 KB boxes - that layer is bound by shared-memory traffic (fills + operand reads), and the fills
+    // drop from 40 KB to ~14 KB per k-block: 0.541 -> 0.430 ms per 8 canvases (1340 -> 1684 TFLOP/s).  Measured on the
+    // other candidates: slower with ONE chunk (64 input channels, slice1.7: 0.314 -> 0.333 ms - a two-deep patch ring is
+    // then only one tile of look-ahead), neutral with four (upconv2.conv.3, 256 channels at 160x120: 0.081 -> 0.084).
+    // Only where 16 x 16 tiles waste <= 5 % of the pixels.
     static int allow_hstream = -1;
     if (allow_hstream < 0) { const char* e = getenv("LOCR_CONV_HSTREAM"); allow_hstream = e ? atoi(e) : 1; }
     bool hstream = false;
-    if (allow_hstream && !halo && !first && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
-        c.pad_w == 1 && c.stride_h == 1 && (c.Cin == 64 || c.Cin == 128) && c.cin_wrap == 0 && c.Cout_pad == 128 &&
+    if (allow_hstream && !halo_base && !first && c.KH == 3 && c.KW == 3 && c.dil_h == 1 && c.dil_w == 1 && c.pad_h == 1 &&
+        c.pad_w == 1 && c.stride_h == 1 && c.Cin == 128 && c.cin_wrap == 0 && c.Cout_pad == 128 &&
         n_tile == 128 && !c.out_fp32 && !c.split_out && c.x_row_px == 0 && c.y_row_px == 0 && c.tail_out == nullptr &&
         c.residual == nullptr && (c.y_pitch * elem_h) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0) {
         const long t16 = (long)((c.OW + 15) / 16) * ((c.OH + 15) / 16) * c.B;
         if (t16 >= device_sm_count() && t16 * 256 * 100 <= (long)c.OW * c.OH * c.B * 105) hstream = true;
     }
+    const bool halo = halo_base;
     if (halo || hstream) {
         halves = 2; split_b = 2;
         best_bw = 8; best_bh = 16; best_bb = 1;
@@ -1432,7 +1436,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     p.b_stage_bytes = (uint32_t)((n_load * swz + 1023) / 1024 * 1024);
     if (halo) {
         p.a_stage_bytes = 18u * 24u * (uint32_t)swz;               // haloed patch
-        p.b_stage_bytes = 9u * (uint32_t)(n_tile * swz) / 2u;      // x 2 "stages" = the nine resident tap slabs
+        p.b_stage_bytes = 9u * (uint32_t)(n_load * swz) / 2u;      // x 2 "stages" = the nine resident tap slabs
     }
     if (hstream) p.a_stage_bytes = 18u * 24u * 128u;               // one patch per 64-channel chunk; b = half slab (8 KB)
     size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
@@ -1453,7 +1457,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     if (halo) {
         // patch ring as deep as the resident slabs leave room for (one barrier round per tile: the prefetch distance is
         // what hides the load latency); the slabs are spread over `stages` equal, 1024-byte-aligned shares
-        const size_t slabs = 9u * (size_t)(n_tile * swz);
+        const size_t slabs = 9u * (size_t)(n_load * swz);
         static int halo_stages_max = -1;
         if (halo_stages_max < 0) { const char* e = getenv("LOCR_CONV_HALO_STAGES"); halo_stages_max = e ? atoi(e) : 6; }
         int st = (int)((227 * 1024 - 1024 - tail_bytes - slabs - 6 * 1024) / p.a_stage_bytes);

@@ -109,6 +109,8 @@ POOL_CASES = [
     ("c32_sw64", 2, 16, 36, 32, 32, 0, 0),
     ("cta2_vgg_c128", 4, 160, 128, 128, 128, 0, 0),      # the slice1.10 pattern on the CTA-pair kernels
     ("cta2_crnn_conv1", 125, 16, 50, 128, 128, 0, 0),
+    ("halo_c64_large", 2, 160, 128, 64, 64, 0, 0),       # the slice1.3 pattern over more tiles than SMs
+    ("halo_c64_odd", 1, 336, 240, 64, 64, 1, 0),
     ("cta2_n256_vgg_c256", 2, 80, 60, 256, 256, 0, 0),   # the slice3.20 pattern (N = 256 tiles on CTA pairs)
     ("cta2_n256_vgg_c512", 2, 40, 30, 512, 512, 1, 0),
 ]
@@ -135,7 +137,8 @@ def test_conv_fused_maxpool(case, want_full):
         assert np.array_equal(y, plain)
 
 
-@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 160, 120), (3, 20, 100)], ids=str)
+@pytest.mark.parametrize("shape", [(1, 16, 16), (2, 33, 47), (1, 160, 120), (3, 20, 100), (2, 176, 128), (1, 330, 250)],
+                         ids=str)
 @pytest.mark.parametrize("act", [0, 1])
 def test_conv_halo_mode_64_to_64(shape, act):
     """3x3 / pad 1 / 64 -> 64 layers take the haloed-patch path (one TMA patch per 16 x 16 tile, the nine taps are
@@ -175,13 +178,14 @@ def test_conv_halo_mode_narrow_layers(shape, chan, act):
     assert err <= tol, "max abs err %g > tol %g" % (err, tol)
 
 
-@pytest.mark.parametrize("cin", [64, 128])
+@pytest.mark.parametrize("cin", [64, 128, 256])
 @pytest.mark.parametrize("shape", [(2, 160, 128), (1, 336, 240), (4, 96, 112), (1, 330, 250)], ids=str)
 @pytest.mark.parametrize("pool", [False, True])
 def test_conv_hstream_pairs(shape, cin, pool):
-    """The N = 128 3x3 layers at high resolution (slice1.7 / slice1.10) run as CTA pairs over haloed patches (one per
-    64-channel chunk) against a streamed weight ring: even and odd tile counts, ragged edges within the 5 % waste limit,
-    with and without the fused 2x2 max-pool."""
+    """The 128 -> 128 3x3 layers at high resolution (slice1.10) run as CTA pairs
+    over haloed patches (one per 64-channel chunk) against a streamed weight ring: even and odd tile counts, ragged
+    edges within the 5 % waste limit, with and without the fused 2x2 max-pool.  64 / 256 input channels: the generic pair
+    form, same shapes."""
     from lightly_ocr_b200 import bridge
     B, H, W = shape
     rng = np.random.default_rng(B * 1000 + H * 10 + W + cin)
