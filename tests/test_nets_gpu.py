@@ -92,6 +92,34 @@ def test_craft_score_maps_full_canvas(oracle_mods):
     eng.close()
 
 
+@pytest.mark.parametrize("shape", [(1, 480, 352), (3, 448, 352), (5, 352, 288), (2, 736, 416)], ids=str)
+def test_craft_score_maps_odd_shapes(oracle_mods, shape):
+    """Canvas sizes and batch sizes that give odd tile counts, ragged 16 x 16 tiles and last CTA pairs without a partner
+    in the pair / haloed-patch forms of the conv kernel (165, 462, 99 x 5 and 2 x 299 tiles at half resolution): score maps
+    within 1e-2 of the fp32 oracle, and within 2e-3 of the same image run alone."""
+    ocr_ref, receipts, weights = oracle_mods
+    from lightly_ocr_b200 import bridge
+    B, H, W = shape
+    sd = weights.craft_calibrated(0, ink=True)
+    eng = bridge.Engine(act_dtype=ACT["f16"])
+    eng.load_state_dict(bridge.MODEL_CRAFT, sd)
+    batch = np.stack([np.ascontiguousarray(receipts.receipt(10 + i)[60:60 + H, 40:40 + W]) for i in range(B)])
+    got = eng.craft_scores(batch)
+    assert got.shape == (B, H // 2, W // 2, 2) and np.isfinite(got).all()
+    with torch.no_grad():
+        x = torch.cat([ocr_ref.craft_preproc(i, canvas_size=10 ** 6, mag_ratio=1.0)[0] for i in batch], 0)
+        ref = ocr_ref.craft_forward(sd, x).numpy()
+    err = float(np.abs(got - ref).max())
+    print("%s: score max-abs err %.4g" % (shape, err))
+    assert err < 1e-2
+    if B > 1:
+        # (not bit-identical in general: below 148 tiles slice1.10 takes the generic pair form, whose fp32 summation
+        # order over the taps differs from the haloed-patch form's)
+        alone = eng.craft_scores(batch[B - 1:B])
+        assert float(np.abs(alone[0] - got[B - 1]).max()) < 2e-3
+    eng.close()
+
+
 @pytest.mark.parametrize("head", ["CTC", "Attention"])
 @pytest.mark.parametrize("act", ["f16", "bf16"])
 def test_crnn_logits_and_decode(oracle_mods, act, head):
