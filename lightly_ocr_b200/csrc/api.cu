@@ -42,6 +42,10 @@ LOCR_API void locr_destroy(locr_handle* h) {
     for (void* p : h->owned) cudaFree(p);
     for (auto& kv : h->buffers)
         if (kv.second.first) cudaFree(kv.second.first);
+    for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    if (h->timer0) cudaEventDestroy(h->timer0);
+    if (h->timer1) cudaEventDestroy(h->timer1);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -123,8 +127,8 @@ LOCR_API int locr_profile_read(locr_handle* h, double* conv_ms, double* conv_flo
         a.ms += t;
         a.flops += r.flops;
         a.n += 1;
-        cudaEventDestroy(r.e0);
-        cudaEventDestroy(r.e1);
+        h->event_pool.push_back(r.e0);      // reused by the next ProfScope: creating events per launch costs host time
+        h->event_pool.push_back(r.e1);      // that shows up as gaps between the kernels of a profiled pass
     }
     if (conv_ms) *conv_ms = ms;
     if (conv_flops) *conv_flops = fl;

@@ -67,6 +67,7 @@ struct locr_handle {
     bool profile = false;
     struct ProfRec { cudaEvent_t e0, e1; double flops; std::string name; bool is_conv; };
     std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;   // events of read-out records, reused
     struct ProfAgg { double ms = 0, flops = 0; int64_t n = 0; };
     std::map<std::string, ProfAgg> prof_layers;  // per-layer totals accumulated by locr_profile_read
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
@@ -100,8 +101,12 @@ struct ProfScope {
     ProfScope(locr_handle* h_, const std::string& name, double flops, bool is_conv) : h(h_), on(h_->profile) {
         if (!on) return;
         r.name = name; r.flops = flops; r.is_conv = is_conv;
-        cudaEventCreate(&r.e0);
-        cudaEventCreate(&r.e1);
+        auto take = [&](cudaEvent_t* e) {
+            if (!h->event_pool.empty()) { *e = h->event_pool.back(); h->event_pool.pop_back(); }
+            else cudaEventCreate(e);
+        };
+        take(&r.e0);
+        take(&r.e1);
         cudaEventRecord(r.e0, h->stream);
     }
     ~ProfScope() {

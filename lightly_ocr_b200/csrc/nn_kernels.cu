@@ -361,7 +361,7 @@ maxpool_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int
 // with weights 0.25 / 0.75 (dy = 0) or 0.75 / 0.25 (dy = 1), same for columns; rows / columns outside the tensor
 // clamp to the edge, which reproduces PyTorch's clamping of negative source coordinates and of the last index.  Nine
 // source loads feed four outputs (the plain per-output form needs sixteen) and the index arithmetic is shared.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, int W, int C,
                   uint16_t* __restrict__ out, long out_pitch, int f16) {
     const uint32_t groups = (uint32_t)C >> 3;
@@ -377,26 +377,43 @@ upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, 
         const int ks[3] = {k > 0 ? k - 1 : 0, k, k < H - 1 ? k + 1 : H - 1};
         const int ls[3] = {l > 0 ? l - 1 : 0, l, l < W - 1 ? l + 1 : W - 1};
         const uint16_t* base = in + (long)b * H * W * in_pitch + cg * 8;
-        float v[3][3][8];
+        // all nine loads first (memory-level parallelism), then row by row: horizontal lerps of a source row (output
+        // columns 2l and 2l + 1), then the vertical lerp with the previous row - PyTorch's own order of operations
+        // (value = hy * row(y0) + ly * row(y1) with row(y) = hx * p(x0) + lx * p(x1)); only two lerped rows stay live
+        uint4 raw[3][3];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j)
-                unpack8(__ldg(reinterpret_cast<const uint4*>(base + (long)(ks[i] * W + ls[j]) * in_pitch)), v[i][j], f16);
+                raw[i][j] = __ldg(reinterpret_cast<const uint4*>(base + (long)(ks[i] * W + ls[j]) * in_pitch));
         uint16_t* obase = out + ((long)b * 2 * H * OW) * out_pitch + cg * 8;
+        float hprev[2][8];
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            // PyTorch: y0 = floor(src), ly = src - y0, value = hy * row(y0) + ly * row(y1)
-            const float ly = dy == 0 ? 0.75f : 0.25f, hy = 1.f - ly;
+        for (int i = 0; i < 3; ++i) {
+            float a[8], m[8], c[8], hcur[2][8];
+            unpack8(raw[i][0], a, f16);
+            unpack8(raw[i][1], m, f16);
+            unpack8(raw[i][2], c, f16);
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const float lx = dx == 0 ? 0.75f : 0.25f, hx = 1.f - lx;
-                float r[8];
+            for (int q = 0; q < 8; ++q) {
+                hcur[0][q] = 0.25f * a[q] + 0.75f * m[q];
+                hcur[1][q] = 0.75f * m[q] + 0.25f * c[q];
+            }
+            if (i > 0) {
+                const int dy = i - 1;
+                const float ly = dy == 0 ? 0.75f : 0.25f, hy = 1.f - ly;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)   // four constant weights (9/16, 3/16, 3/16, 1/16): one multiply + three FMAs
-                    r[c] = fmaf(ly * lx, v[dy + 1][dx + 1][c], fmaf(ly * hx, v[dy + 1][dx][c],
-                                fmaf(hy * lx, v[dy][dx + 1][c], (hy * hx) * v[dy][dx][c])));
-                *reinterpret_cast<uint4*>(obase + ((long)(2 * k + dy) * OW + 2 * l + dx) * out_pitch) = pack8(r, f16);
+                for (int dx = 0; dx < 2; ++dx) {
+                    float r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) r[q] = hy * hprev[dx][q] + ly * hcur[dx][q];
+                    *reinterpret_cast<uint4*>(obase + ((long)(2 * k + dy) * OW + 2 * l + dx) * out_pitch) = pack8(r, f16);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                hprev[0][q] = hcur[0][q];
+                hprev[1][q] = hcur[1][q];
             }
         }
     }

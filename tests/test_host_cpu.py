@@ -46,6 +46,30 @@ def test_compare_rects_and_sort_match_oracle_restatement():
         assert hostops.sort_rects(rects) == ocr_ref.sort_rects(rects)
 
 
+def test_overlapped_sort_permutation_equals_sorting_the_rects():
+    """OcrRunner recognises the crops in label order while a helper thread sorts `rect + [position]` lists with the same
+    comparator (it only reads elements 0..3) and permutes the outputs afterwards: the permutation must reproduce
+    sorted(rects, key=cmp_to_key(compare_rects)) exactly, duplicates and degenerate rects included - also on the live
+    reference's golden rects."""
+    from lightly_ocr_b200 import hostops
+    rng = np.random.default_rng(1)
+    sets = []
+    for trial in range(200):
+        k = int(rng.integers(0, 120))
+        ys, xs = rng.integers(0, 1200, k), rng.integers(0, 900, k)
+        r = np.stack([ys, xs, ys + rng.integers(-2, 40, k), xs + rng.integers(-2, 200, k)], 1).astype(np.int32)
+        if trial % 3 == 0 and k > 4:
+            r[k // 2] = r[k // 3]
+        sets.append(r.tolist())
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ctc.npz"))
+    sets += [g["maps1_rects"].tolist(), g["maps2_rects"].tolist()]
+    for flat in sets:
+        want = hostops.sort_rects([list(x) for x in flat])
+        perm = [t[4] for t in hostops.sort_rects([flat[j] + [j] for j in range(len(flat))])]
+        assert [flat[q] for q in perm] == want
+        assert sorted(perm) == list(range(len(flat)))
+
+
 def test_sorted_rects_match_reference_golden():
     from lightly_ocr_b200 import hostops
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_ctc.npz"))
