@@ -708,10 +708,11 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "precision": args.precision,
-            "config": {"workload": "end-to-end CRAFT+CRNN(%s) over synthetic 1280x960 receipts, %d receipts per "
-                                   "step per GPU in %d passes of %d (BASELINE config %d; ~%d crops per receipt)"
-                                   % (head, RECEIPTS_PER_STEP, PASSES, PER_PASS, 4 if head == "CTC" else 5,
-                                      total_crops // max(receipts_total, 1)),
+            # `workload` is the same string in both arms (--impl reference); how each arm batches it is its own key
+            "config": {"workload": "end-to-end CRAFT+CRNN(%s) over synthetic 1280x960 receipts (BASELINE config %d)"
+                                   % (head, 4 if head == "CTC" else 5),
+                       "batching": "%d receipts per step per GPU in %d passes of %d; ~%d crops per receipt"
+                                   % (RECEIPTS_PER_STEP, PASSES, PER_PASS, total_crops // max(receipts_total, 1)),
                        "l2": "inputs + activations per pass (~0.6 GB per receipt) far exceed the 126 MB L2",
                        "weights": "synthetic checkpoints (lightly_ocr_b200/synth: seed-generated, read-out trained on synthetic receipts), fp16 storage, fp32 accumulate",
                        "parallelism": "replicas x%d, receipts sharded, no collective; %d host lanes (handles/streams) per GPU" % (world, LANES)},
