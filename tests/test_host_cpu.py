@@ -244,3 +244,40 @@ def test_installed_reference_copy_is_unmodified():
     for name in ("pipeline.py", "net.py", "server.py", "tools/det_utils.py"):
         with open(os.path.join(ref_env.INSTALLED, name), "rb") as a, open(os.path.join(ref_env.UPSTREAM, name), "rb") as b:
             assert a.read() == b.read(), name
+
+
+def test_evaluation_loop_host_logic():
+    """lightly_ocr_b200.evaluate.evaluation (the reference's validation loop, ocr/train/crnn.py:142-240) with a stand-in
+    engine: targets reach the engine exactly as the reference's converters encode them, the loss is the Averager's mean
+    of the batch costs, the accuracy counts the engine's flags, `max_iter` bounds the loop, and the returned preds_ /
+    confidence_ / label are those of the last batch (the reference overwrites them per batch)."""
+    from lightly_ocr_b200 import evaluate
+
+    class Fake:
+        head = 0          # bridge.HEAD_CTC
+
+        def __init__(self):
+            self.calls = []
+
+        def evaluate(self, crops, targets, target_len):
+            self.calls.append((len(crops), np.array(targets), np.array(target_len)))
+            n = len(crops)
+            return dict(cost=0.5 * len(self.calls), loss=np.ones(n, np.float32), correct=np.array([1] + [0] * (n - 1), np.int32),
+                        ids=np.zeros((n, 26), np.int32), text=["t%d" % i for i in range(n)], conf=np.linspace(0.1, 0.9, n))
+
+    eng = Fake()
+    batches = [([np.zeros((8, 8), np.uint8)] * 3, ["ab", "c", "0z9"]), ([np.zeros((8, 8), np.uint8)] * 2, ["q", "rs"]),
+               ([np.zeros((8, 8), np.uint8)], ["never"])]
+    loss, acc, preds_, conf_, label, infer_, n = evaluate.evaluation(eng, batches, {"batch_max_len": 25, "max_iter": 2})
+    assert len(eng.calls) == 2 and n == 5
+    assert abs(loss - (0.5 + 1.0) / 2) < 1e-9 and abs(acc - 2 / 5 * 100) < 1e-9
+    assert preds_ == ["t0", "t1"] and label == ["q", "rs"] and len(conf_) == 2 and infer_ >= 0
+    # CTC targets: blank = 0, '0' -> 1 ... 'z' -> 36, concatenated, with the lengths
+    assert eng.calls[0][1].tolist() == [11, 12, 13, 1, 36, 10] and eng.calls[0][2].tolist() == [2, 1, 3]
+    eng2 = Fake()
+    eng2.head = 1         # attention: [GO] = 0, [s] = 1, rows of batch_max_len + 2
+    evaluate.evaluation(eng2, batches[:1], {"batch_max_len": 25})
+    tg = eng2.calls[0][1]
+    assert tg.shape == (3, 27) and tg[0, :4].tolist() == [0, 12, 13, 1] and tg[2, :5].tolist() == [0, 2, 37, 11, 1]
+    assert eng2.calls[0][2].tolist() == [3, 2, 4]
+
