@@ -37,7 +37,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LANES = int(os.environ.get("LOCR_BENCH_LANES", "2"))   # host threads per GPU, each with its own liblocr handle/stream:
+LANES = int(os.environ.get("LOCR_BENCH_LANES", "3"))   # host threads per GPU, each with its own liblocr handle/stream:
                                # while one lane sorts rects / copies results on the host, the other lanes' kernels
                                # keep the GPU busy
 PER_LANE = int(os.environ.get("LOCR_BENCH_PER_LANE", "8"))   # receipts per lane and pass (one CRAFT launch sequence)

@@ -10,10 +10,11 @@ case $ST in
 list)
     BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin --no-other-precision"
     export LOCR_BENCH_PASSES=1
+    export LOCR_BENCH_LANES=2     # the skip / count below are for two lanes
     # launches 0..515 are the three warm-up passes of the e2e leg (2 lanes x 86 launches per pass); the next 344 are its timed region
     $BENCH > gpurun_out/plain_${TAG}.log 2>&1 &&
     ncu --metrics gpu__time_duration.sum --clock-control none -s 520 -c 340 --csv --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_launch_${TAG}.log 2>&1
-    unset LOCR_BENCH_PASSES
+    unset LOCR_BENCH_PASSES LOCR_BENCH_LANES
     ;;
 tc)
     export LOCR_BENCH_WARMUP=0
