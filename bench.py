@@ -625,11 +625,13 @@ def main():
     r0 = runners[0]
     r0.profile(True)
     r0.profile_read()
+    r0.profile_layers()        # clears the per-kernel totals
     r0.timer_start()
     for k in range(args.steps):
         r0.ocr_resident(PER_LANE)
     prof_ms = r0.timer_stop()
     conv_ms, conv_flops, conv_launches = r0.profile_read()
+    all_kernels_ms = sum(row[1] for row in r0.profile_layers())      # every launch of the pass, conv or not
     r0.profile(False)
     barrier()
     if rank == 0:
@@ -734,6 +736,9 @@ def main():
                                          "steps (per-launch CUDA events on the launching stream)" % (args.steps, PER_LANE),
                          "kernel_ms": conv_ms, "pass_ms": prof_ms,
                          "kernel_share_of_step": conv_ms / prof_ms if prof_ms > 0 else None,
+                         # share of the GPU's busy time (what an ncu launch list measures: no host gaps in it)
+                         "all_kernels_ms": all_kernels_ms,
+                         "kernel_share_of_gpu_time": conv_ms / all_kernels_ms if all_kernels_ms > 0 else None,
                          "algorithmic_flops": conv_flops,
                          "whole_step_tensor_frac": ((CRAFT_FLOPS * receipts_total + CRNN_FLOPS_PER_CROP * total_crops)
                                                     / elapsed / 1e12 / world / peak_tf) if peak_tf else None},
