@@ -14,7 +14,9 @@ times the path with the receipts already resident in HBM; `e2e` times the same p
 Receipts are independent units: no collective on the data path, torch.distributed only provides the barrier and the
 max-over-ranks reduction of the elapsed time.
 
---head Attention (or --config 5) runs the same legs with the attention decoder (BASELINE config 5).
+--head Attention (or --config 5) runs the same legs with the attention decoder (BASELINE config 5).  Every run of
+config 4 also times the e2e leg once more with the attention decoder (`other_head`; the CTC head when the main legs are
+config 5), at whatever N it was launched with, so a 1 / 2 / 4 / 8-GPU sweep of the default command carries both heads.
 --config 1 / 2 / 3 time the other BASELINE configurations on one lane and print the same JSON shape:
   1  CRNN (CTC) on a single 32x100 gray crop          (ms per crop, lower is better)
   2  CRAFT forward + getDetBoxes on one 1280x960 receipt (ms per receipt, lower is better)
@@ -492,6 +494,9 @@ def main():
                     help="arithmetic of the recogniser for the main legs (include/locr.h LOCR_PREC_*); the other mode is "
                          "timed as an extra e2e leg (`other_precision`) unless --no-other-precision")
     ap.add_argument("--no-other-precision", action="store_true")
+    ap.add_argument("--no-other-head", action="store_true",
+                    help="skip the `other_head` leg (the e2e leg once more with the other prediction head: the attention "
+                         "decoder of BASELINE config 5 when the main legs run config 4)")
     ap.add_argument("--jpeg", action="store_true",
                     help="extra leg: the same receipts handed over as JPEG files (q90, 4:2:0) through locr_detect_encoded; "
                          "adds an `e2e_jpeg` object to the JSON line (BASELINE's metric itself excludes the image decode)")
@@ -525,13 +530,14 @@ def main():
 
     from concurrent.futures import ThreadPoolExecutor
     craft_sd, crnn_sd = weights.craft_calibrated(0, ink=True), weights.crnn_calibrated(1, head)
-    def make_runners(precision):
+    def make_runners(precision, head_=None):
+        sd = crnn_sd if head_ in (None, head) else weights.crnn_calibrated(1, head_)
         out = []
         for _ in range(LANES):
-            r = bridge.OcrRunner(device_id=local_rank, act_dtype=bridge.ACT_F16, head=head,
+            r = bridge.OcrRunner(device_id=local_rank, act_dtype=bridge.ACT_F16, head=head_ or head,
                                  precision=bridge.PREC_EXACT if precision == "exact" else bridge.PREC_FAST)
             r.load_state_dict(bridge.MODEL_CRAFT, craft_sd)
-            r.load_state_dict(bridge.MODEL_CRNN, crnn_sd)
+            r.load_state_dict(bridge.MODEL_CRNN, sd)
             out.append(r)
         return out
 
@@ -669,11 +675,12 @@ def main():
         total_crops, crops_e2e = int(t[0].item()), int(t[1].item())
     for r in runners:
         r.close()
-    # ---------------- the other arithmetic of the recogniser through the same e2e leg (host buffers in, results out)
-    other = None
-    if not args.no_other_precision:
-        other_name = "exact" if args.precision == "fast" else "fast"
-        runners = make_runners(other_name)
+    # ---------------- two more e2e legs (host buffers in, host results out) at every N, so that the driver's 1 -> 8 sweep
+    # carries them too: the other arithmetic of the recogniser, and the other prediction head (BASELINE config 5 when
+    # the main legs are config 4 and vice versa)
+    def extra_leg(precision, head_):
+        nonlocal runners
+        runners = make_runners(precision, head_)
         n_pass = max(args.steps // 2, 2) * PASSES
         for w in range(3):
             e2e_pass(w)
@@ -693,11 +700,26 @@ def main():
             t = torch.tensor([oc], dtype=torch.float64, device=dev)
             dist.all_reduce(t)
             oc = int(t[0].item())
-        other = {"precision": other_name, "value": world * PER_PASS * n_pass / o_s, "unit": UNIT,
-                 "crops_per_sec": oc / o_s, "passes": n_pass,
-                 "leg": "e2e (host buffers in, host results out), same receipts and lanes as `e2e`"}
         for r in runners:
             r.close()
+        runners = []
+        return {"precision": precision, "head": head_, "value": world * PER_PASS * n_pass / o_s, "unit": UNIT,
+                "crops_per_sec": oc / o_s, "passes": n_pass, "n_gpus": world,
+                "leg": "e2e (host buffers in, host results out), same receipts and lanes as `e2e`"}
+
+    other = None
+    if not args.no_other_precision:
+        other = extra_leg("exact" if args.precision == "fast" else "fast", head)
+    other_head = None
+    if not args.no_other_head:
+        head2 = "Attention" if head == "CTC" else "CTC"
+        try:
+            other_head = extra_leg(args.precision, head2)
+            other_head["metric"] = metric_name(head2)
+            other_head["workload"] = ("end-to-end CRAFT+CRNN(%s) over synthetic 1280x960 receipts (BASELINE config %d)"
+                                      % (head2, 4 if head2 == "CTC" else 5))
+        except Exception as e:        # an extra leg must not cost the run its headline line (same on every rank)
+            other_head = {"head": head2, "error": "%s: %s" % (type(e).__name__, e)}
     runners = []
 
     if rank == 0:
@@ -746,6 +768,8 @@ def main():
         }
         if other is not None:
             line["other_precision"] = other
+        if other_head is not None:
+            line["other_head"] = other_head
         if e2e_jpeg is not None:
             line["e2e_jpeg"] = e2e_jpeg
         if world == 1 and not args.no_dropin:
