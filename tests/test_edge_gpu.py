@@ -115,3 +115,49 @@ def test_unfinalized_model_is_an_error():
     with pytest.raises(bridge.LocrError):
         e.load_state_dict(bridge.MODEL_CRNN, {"Prediction.weight": np.zeros((37, 256), np.float32)})
     e.close()
+
+
+def test_baseline_config4_full_size_lanes_equal_one_at_a_time(runner):
+    """BASELINE config 4 at its full size - 256 distinct 1280x960 receipts - the way bench.py issues them (three host
+    lanes with their own handle / stream on one GPU, 8 receipts per call, all lanes in flight at once) against the
+    one-image-at-a-time order of the reference (ocr/pipeline.py:65-87): rects, their order and every string must be
+    identical, confidences equal to float rounding; and a second run of the lanes reproduces the first bit for bit."""
+    from concurrent.futures import ThreadPoolExecutor
+    from lightly_ocr_b200 import bridge
+    from lightly_ocr_b200.synth import receipts, weights
+    images = [receipts.receipt(2000 + i) for i in range(256)]
+    craft_sd, crnn_sd = weights.craft_calibrated(0, ink=True), weights.crnn_calibrated(1, "CTC")
+    lanes = []
+    for _ in range(3):
+        r = bridge.OcrRunner(device_id=0, act_dtype=bridge.ACT_F16, head="CTC")
+        r.load_state_dict(bridge.MODEL_CRAFT, craft_sd)
+        r.load_state_dict(bridge.MODEL_CRNN, crnn_sd)
+        lanes.append(r)
+    batches = [images[i:i + 8] for i in range(0, len(images), 8)]
+
+    def run_lanes():
+        def work(k):
+            return [lanes[k].ocr(b) for b in batches[k::3]]
+        with ThreadPoolExecutor(max_workers=3) as ex:
+            parts = list(ex.map(work, range(3)))
+        outs = [None] * len(batches)
+        for k in range(3):
+            outs[k::3] = parts[k]
+        return outs
+
+    first, second = run_lanes(), run_lanes()
+    n_crops = 0
+    for bi, ((per_image, out), (per_image2, out2)) in enumerate(zip(first, second)):
+        assert per_image == per_image2 and out["text"] == out2["text"] and np.array_equal(out["conf"], out2["conf"])
+        k = 0
+        for img, rects in zip(batches[bi], per_image):
+            one_rects, one = runner.ocr([img])
+            assert one_rects[0] == rects
+            assert one["text"] == out["text"][k:k + len(rects)]
+            np.testing.assert_allclose(one["conf"], out["conf"][k:k + len(rects)], rtol=1e-4, atol=1e-6)
+            k += len(rects)
+        assert k == len(out["text"])
+        n_crops += k
+    assert n_crops > 256 * 50
+    for r in lanes:
+        r.close()
