@@ -249,6 +249,12 @@ LOCR_API int locr_test_jpeg_coefficients(const uint8_t* data, int64_t nbytes, in
  * out may be NULL to query *need (bytes) only. */
 LOCR_API int locr_test_png_scanlines(const uint8_t* data, int64_t nbytes, uint8_t* out, int64_t capacity, int64_t* need);
 
+/* Number of convolutions this process has run in the split-K form (few output pixels, deep K: the K range is cut into
+ * slices that run as separate CTAs, a second kernel adds the partial sums; lightly_ocr_b200/csrc/conv_tc.cuh).  Tests
+ * use it to prove that the path under test was taken.  LOCR_TEST_SPLITK=0 makes the two conv harnesses above run
+ * unsplit, LOCR_CONV_SPLITK=0 switches the form off everywhere. */
+LOCR_API int64_t locr_test_splitk_calls(void);
+
 /* Times one conv layer in isolation (zero-filled device buffers, CUDA events, `iters` launches after 3 warm-ups). */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter);
 /* In-kernel timeline of the conv kernel (tools/conv_trace.py): only a library built with -DLOCR_CONV_EXPERIMENTS=1 and

@@ -24,6 +24,8 @@
 
 #include "ptx.cuh"
 
+#include <atomic>
+
 namespace locr {
 
 namespace {
@@ -91,6 +93,11 @@ struct ConvParams {
     int img_h, img_w;
     long img_row_stride, img_stride;
     int dbg;            // experiments only (LOCR_CONV_DBG): 1 = skip MMAs, 2 = skip A loads, 4 = skip B loads, 8 = skip epilogue math
+    // Split-K (ConvCall::ksplit, generic kernel only): the input-channel chunks of every tap are cut into ksplit slices and
+    // the tile walk covers ksplit * base_tiles tiles; tile q works on slice q / base_tiles of tile q % base_tiles
+    // (cin_chunks and num_kblocks are those of ONE slice) and stores its fp32 partial sums at output channel
+    // slice * ks_out_stride + n of the workspace.  cin_total = elements per tap of a weight row.
+    int ksplit, base_tiles, cin_total, ks_out_stride;
 };
 
 struct TileCoord {
@@ -187,7 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int t_end = CTA2 ? p.num_pair_tiles : p.num_tiles;
     // pair tile q -> this CTA's tile: same n-tile, m-tile 2 * (q / tiles_n) + rank (may lie past the end: its loads
     // are zero-filled and its stores clipped by the TMA unit)
-    auto tile_of = [&](int q) { return CTA2 ? ((2 * (q / p.tiles_n) + (int)rank) * p.tiles_n + q % p.tiles_n) : q; };
+    auto tile_of = [&](int q) {
+        if (p.ksplit > 1) q %= p.base_tiles;       // split-K: the same tiles once per K slice
+        return CTA2 ? ((2 * (q / p.tiles_n) + (int)rank) * p.tiles_n + q % p.tiles_n) : q;
+    };
 
     if (warp == 0 && lane == 0) {
         if (!FIRST) ptx::tma_prefetch_desc(&tmap_x);
@@ -386,6 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const TileCoord t = decode_tile(p, tile_of(tile));
                 LOCR_TRACE(0, 0);
                 int kcoord = 0;
+                const int ks_c0 = p.ksplit > 1 ? (tile / p.base_tiles) * p.cin_chunks * BLOCK_K : 0;   // split-K: first channel of the slice
                 for (int kh = 0; kh < KH; ++kh) {
                     const int c2 = p.stride2 ? kh : 0;
                     const int c3 = p.stride2 ? t.oh0 : t.oh0 + kh * p.dil_h - p.pad_h;
@@ -396,19 +407,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             LOCR_TRACE(0, 1);
                             int cch = cc * BLOCK_K;
                             if (cch >= p.cin_wrap) cch -= p.cin_wrap;   // [hi | lo | hi] of a split-precision input
+                            int kc = kcoord;
+                            if (p.ksplit > 1) {
+                                cch += ks_c0;
+                                kc = (kh * p.KW + kw) * p.cin_total + cch;
+                            }
                             if (ptx::elect_one()) {
                                 if (CTA2) {
                                     const uint32_t lead = full_lead0 + (full_s - full0);
                                     if (rank == 0) ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
                                     ptx::tma_load_5d_2sm(a_s, &tmap_x, lead, cch, iw0, c2, c3, t.b0);
-                                    ptx::tma_load_2d_2sm(b_s, &tmap_w, lead, kcoord, t.n0 + n_half);
+                                    ptx::tma_load_2d_2sm(b_s, &tmap_w, lead, kc, t.n0 + n_half);
                                 } else {
                                 if (LOCR_CONV_EXPERIMENTS && tx_bytes == 0) ptx::mbar_arrive(&full_bar[(full_s - full0) >> 3]);
                                 else ptx::mbar_arrive_expect_tx_a(full_s, tx_bytes);
                                 if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 2)))
                                     ptx::tma_load_5d_a(a_s, &tmap_x, full_s, cch, iw0, c2, c3, t.b0);
                                 if (!(LOCR_CONV_EXPERIMENTS && (p.dbg & 4)))
-                                    ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kcoord, t.n0);
+                                    ptx::tma_load_2d_a(b_s, &tmap_w, full_s, kc, t.n0);
                                 }
                             }
                             LOCR_TRACE(0, 2);
@@ -808,13 +824,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             }
             // one n-tile: the bias slice is the same for every tile of this CTA (the first chunk's barrier publishes it)
             const bool bias_once = p.tiles_n == 1;
+            const bool no_bias = EPI == 0 && p.bias == nullptr;     // split-K partial sums: the reduction adds the bias
             if (bias_once)
-                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[i]);
+                for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = no_bias ? 0.f : __ldg(&p.bias[i]);
             for (int tile = t_begin; tile < t_end; tile += t_step) {
                 const TileCoord t = decode_tile(p, tile_of(tile));
+                // split-K: slice s of the K range writes its partial sums at channel s * ks_out_stride + n
+                const int n_out = t.n0 + ((EPI == 0 && p.ksplit > 1) ? (tile / p.base_tiles) * p.ks_out_stride : 0);
                 if (etid == 0) LOCR_TRACE(2, 0);
                 if (!bias_once)
-                    for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = __ldg(&p.bias[t.n0 + i]);
+                    for (int i = etid; i < p.n_tile; i += 256) bias_s[i] = no_bias ? 0.f : __ldg(&p.bias[t.n0 + i]);
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
                 if (etid == 0) LOCR_TRACE(2, 1);
                 ptx::tc_fence_after();
@@ -1054,7 +1073,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (etid == 0) LOCR_TRACE(2, 7);
                     if (etid == 0) {
                         if (!e_skip_full && !(LOCR_CONV_EXPERIMENTS && (p.dbg & 8))) {
-                            ptx::tma_store_4d(&tmap_y, sbuf, t.n0 + c * stage_cols, ow0, oh0, b0);
+                            ptx::tma_store_4d(&tmap_y, sbuf, n_out + c * stage_cols, ow0, oh0, b0);
                             if (e_split)
                                 ptx::tma_store_4d(&tmap_y, sbuf_lo, p.Cout + t.n0 + c * stage_cols, ow0, oh0, b0);
                         }
@@ -1217,7 +1236,53 @@ cudaError_t launch_swz(const CUtensorMap& mx, const CUtensorMap& mw, const CUten
     return cudaGetLastError();
 }
 
+// Second half of a split-K call: y = act(sum over slices of the fp32 partial sums + bias [+ residual]) rounded to 16 bits.
+// One thread per pixel and 8 output channels; ws is [pixels][slices * Cp] fp32.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int slices, int Cp, long pixels,
+                                     const float* __restrict__ bias, const uint16_t* __restrict__ res, long res_pitch,
+                                     uint16_t* __restrict__ y, long y_pitch, int relu, int is_f16) {
+    const int groups = Cp >> 3;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= pixels * groups) return;
+    const long pix = idx / groups;
+    const int n = (int)(idx - pix * groups) << 3;
+    float v[8];
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    const float* q = ws + pix * ((long)slices * Cp) + n;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < slices; ++s, q += Cp) {
+        const float4 a = *reinterpret_cast<const float4*>(q);
+        const float4 b = *reinterpret_cast<const float4*>(q + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += acc[j];      // same order as the unsplit epilogue: accumulator + bias
+    if (res != nullptr) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(res + pix * res_pitch + n));
+        const float2 f0 = unpack2(u.x, is_f16), f1 = unpack2(u.y, is_f16);
+        const float2 f2 = unpack2(u.z, is_f16), f3 = unpack2(u.w, is_f16);
+        v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+        v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+    }
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+    uint4 o;
+    o.x = pack2(v[0], v[1], is_f16); o.y = pack2(v[2], v[3], is_f16);
+    o.z = pack2(v[4], v[5], is_f16); o.w = pack2(v[6], v[7], is_f16);
+    *reinterpret_cast<uint4*>(y + pix * y_pitch + n) = o;
+}
+
 }  // namespace
+
+static std::atomic<long long> g_splitk_calls{0};
+long long conv_tc_splitk_calls() { return g_splitk_calls.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
     static int n = 0;
@@ -1265,6 +1330,55 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         set_err(err, errlen, "conv_tc: split-precision output needs a 16-bit output with Cout a multiple of 64");
         return cudaErrorInvalidValue;
     }
+    // ---- split-K (see ConvCall::splitk_ws): few output pixels, many k-blocks
+    static int allow_splitk = -1;
+    if (allow_splitk < 0) { const char* e = getenv("LOCR_CONV_SPLITK"); allow_splitk = e ? atoi(e) : 1; }
+    if (allow_splitk && c.ksplit == 0 && c.splitk_ws != nullptr && !first && swz == 128 && c.n_tile == 0 &&
+        c.cin_wrap == 0 && !c.split_out && !c.out_fp32 && c.pool_y == nullptr && c.tail_out == nullptr &&
+        c.x_row_px == 0 && c.y_row_px == 0 && c.res_lo_off == 0 && c.Cout == c.Cout_pad && c.Cout_pad % 64 == 0 &&
+        c.y_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
+        (c.residual == nullptr || (c.res_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(c.residual) % 16) == 0))) {
+        const long pixels = (long)c.B * c.OH * c.OW;
+        const int chunks = c.Cin / 64;
+        // m-tiles of 128 pixels the generic kernel would walk (its box search below finds the same or fewer)
+        long m_tiles = -1;
+        for (int bw = 128; bw >= 1; bw >>= 1)
+            for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+                const int bb = 128 / (bw * bh);
+                const long t = (long)((c.OW + bw - 1) / bw) * ((c.OH + bh - 1) / bh) * ((c.B + bb - 1) / bb);
+                if (m_tiles < 0 || t < m_tiles) m_tiles = t;
+            }
+        int slices = 1;
+        if (m_tiles <= 8 && c.KH * c.KW * chunks >= 8) {
+            const long units = m_tiles * (c.Cout_pad / 64);
+            for (int cand = 8; cand >= 2; cand >>= 1)
+                if (chunks % cand == 0 && units * cand <= (long)device_sm_count() + units / 2) { slices = cand; break; }
+        }
+        if (slices > 1 && (size_t)pixels * slices * c.Cout_pad * 4 <= c.splitk_ws_bytes) {
+            ConvCall part = c;
+            part.ksplit = slices;
+            part.n_tile = 64;
+            part.y = c.splitk_ws;
+            part.y_pitch = (long)slices * c.Cout_pad;
+            part.out_fp32 = 1;
+            part.bias = nullptr;
+            part.residual = nullptr;
+            part.relu = 0;
+            part.splitk_ws = nullptr;
+            cudaError_t e = conv_tc_launch(part, stream, err, errlen);
+            if (e != cudaSuccess) return e;
+            const long work = pixels * (c.Cout_pad / 8);
+            splitk_reduce_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
+                reinterpret_cast<const float*>(c.splitk_ws), slices, c.Cout_pad, pixels, c.bias,
+                reinterpret_cast<const uint16_t*>(c.residual), c.res_pitch, reinterpret_cast<uint16_t*>(c.y), c.y_pitch,
+                c.relu, c.dtype == ACT_F16 ? 1 : 0);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) set_err(err, errlen, cudaGetErrorString(e));
+            else g_splitk_calls.fetch_add(1, std::memory_order_relaxed);
+            return e;
+        }
+    }
+    const int ksplit = c.ksplit > 1 ? c.ksplit : 1;
     int n_tile = c.n_tile;
     if (n_tile == 0) {
         if (c.Cout_pad % 256 == 0) n_tile = 256;
@@ -1317,7 +1431,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
         const bool aligned_out = (c.y_pitch * elem_) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.y) % 16) == 0 &&
                                  n_tile % sc_ == 0 && (rb_ == 32 || rb_ == 64 || rb_ == 128);
         int w2 = 0, h2 = 0, b2 = 0;
-        if ((allow256 || first) && n_tile <= 128 && aligned_out) {
+        if ((allow256 || first) && n_tile <= 128 && aligned_out && ksplit == 1) {
             const long tiles256 = search(256, w2, h2, b2);
             const long n_tiles_n = c.Cout_pad / n_tile;
             // worthwhile when it wastes no more pixels than the 128-row tiling and still fills the machine
@@ -1396,7 +1510,12 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     int cols = 32;
     while (cols < 2 * halves * p.n_tile_alloc) cols <<= 1;
     p.tmem_cols = cols;
-    p.cin_chunks = c.Cin / block_k;
+    p.cin_chunks = c.Cin / block_k / ksplit;     // per K slice
+    p.ksplit = ksplit;
+    p.base_tiles = p.num_tiles;
+    p.cin_total = c.Cin;
+    p.ks_out_stride = c.Cout_pad;
+    if (ksplit > 1) p.num_tiles *= ksplit;
     p.KW = c.KW; p.dil_h = c.dil_h; p.dil_w = c.dil_w; p.pad_h = c.pad_h; p.pad_w = c.pad_w;
     p.stride2 = (c.stride_h == 2) ? 1 : 0;
     p.num_kblocks = c.KH * c.KW * p.cin_chunks;
@@ -1427,7 +1546,7 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
                             (halves == 1 && n_tile == 256 && allow_cta2_n256 &&
                              (allow_cta2_n256 >= 2 || kblocks_all >= (cta2_min_kb < 16 ? cta2_min_kb : 16)));
     // split-precision inputs / outputs and fp32 outputs take the pair form of the generic epilogue (EPI = 0)
-    const bool cta2 = hstream || (allow_cta2 && !first && !halo && swz == 128 && cta2_shape && c.tail_out == nullptr &&
+    const bool cta2 = hstream || (allow_cta2 && ksplit == 1 && !first && !halo && swz == 128 && cta2_shape && c.tail_out == nullptr &&
                                   c.x_row_px == 0 && c.y_row_px == 0 && (long)p.tiles_w * p.tiles_h * tiles_b >= 2);
     (void)elem_c;
     const int n_load = cta2 ? n_tile / 2 : n_tile;      // weight rows each CTA stages per k-block
@@ -1562,8 +1681,8 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
     memset(&my, 0, sizeof(my));
     if (p.tma_store && !p.skip_full && c.tail_out == nullptr) {
         const cuuint64_t eb = (cuuint64_t)elem;
-        cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : c.Cout), (cuuint64_t)c.OW, (cuuint64_t)c.OH,
-                              (cuuint64_t)c.B};
+        cuuint64_t dims[4] = {(cuuint64_t)(c.split_out ? 2 * c.Cout : (ksplit > 1 ? ksplit * c.Cout_pad : c.Cout)),
+                              (cuuint64_t)c.OW, (cuuint64_t)c.OH, (cuuint64_t)c.B};
         const cuuint64_t pb = (cuuint64_t)c.y_pitch * eb;
         const cuuint64_t yw = (cuuint64_t)(c.y_row_px > 0 ? c.y_row_px : c.OW);
         cuuint64_t strides[3] = {pb, pb * yw, pb * yw * c.OH};

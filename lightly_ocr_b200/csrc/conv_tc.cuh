@@ -61,6 +61,14 @@ struct ConvCall {
     const uint8_t* first_u8 = nullptr;
     int img_h = 0, img_w = 0;
     long img_row_stride = 0, img_stride = 0;   // bytes per image row / per image
+    // Split-K for calls with very few output pixels (one crop or a handful: M <= 8 tiles of 128 pixels), where a deep
+    // layer (e.g. 512 -> 512, 3x3: 72 k-blocks) would otherwise run as one or two CTAs walking the whole K range while
+    // 146 SMs idle: with a workspace the launcher cuts the input channels into up to 8 slices, runs slices x n-tiles
+    // (N = 64) CTAs that store fp32 partial sums, and a second small kernel adds the slices, the bias and the residual,
+    // applies the ReLU and rounds to 16 bits.  Plain 16-bit-output layers only (no pooling, split precision, fused tail).
+    void* splitk_ws = nullptr;       // fp32 workspace, >= B * OH * OW * slices * Cout_pad * 4 bytes; null = never split
+    size_t splitk_ws_bytes = 0;
+    int ksplit = 0;                  // internal: set by conv_tc_launch on the partial-sum call it issues
 };
 
 // Returns cudaSuccess or the launch/encode error; writes a human-readable reason into err (if non-null).
@@ -69,6 +77,9 @@ cudaError_t conv_tc_launch(const ConvCall& c, cudaStream_t stream, char* err, in
 // Experiments build (-DLOCR_CONV_EXPERIMENTS=1, LOCR_CONV_DBG bit 32): clock64 stamps of block 0's producer / MMA issuer /
 // first epilogue warp, [3][8192] entries of (clock << 4 | event); counts[3] entries are valid.  Resets the counters.
 int conv_tc_trace_read(unsigned long long* out, int* counts);
+
+// Split-K convolutions launched by this process so far (tests: proves that the path under test was taken).
+long long conv_tc_splitk_calls();
 
 // Number of SMs used for the persistent grid (queried once).
 int device_sm_count();

@@ -190,6 +190,10 @@ void dbg(locr_handle* h, const std::string& name, const void* p, int kind, std::
     h->dbg[name] = d;
 }
 
+// split-K workspace: 1024 pixels x 8 slices x 1024 channels of fp32 partial sums at most
+constexpr long kSplitKMaxPixels = 1024;
+constexpr size_t kSplitKWorkspace = (size_t)kSplitKMaxPixels * 8 * 1024 * 4;
+
 struct Ctx {
     locr_handle* h;
     int rc = LOCR_OK;
@@ -246,6 +250,12 @@ struct Ctx {
         tail_w = nullptr; tail_out = nullptr;
         c.x_row_px = x_row_px; c.y_row_px = y_row_px;
         x_row_px = 0; y_row_px = 0;
+        // single crops / a handful of them: deep layers split their K range over the machine (conv_tc.cuh splitk_ws)
+        if ((long)B * c.OH * c.OW <= kSplitKMaxPixels && !out_fp32 && !split_out && cw.cin_wrap == 0 && c.pool_y == nullptr &&
+            c.tail_out == nullptr && cw.cin % 64 == 0 && cw.kh * cw.kw * (cw.cin / 64) >= 8) {
+            c.splitk_ws = engine_buffer(h, "splitk.ws", kSplitKWorkspace);     // null: the call simply runs unsplit
+            c.splitk_ws_bytes = c.splitk_ws != nullptr ? kSplitKWorkspace : 0;
+        }
         char err[256] = {0};
         cudaError_t e;
         const std::string shown = layer.substr(0, layer.find('#'));   // "layer#variant" is reported under the layer's name

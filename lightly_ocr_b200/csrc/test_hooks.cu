@@ -89,6 +89,17 @@ static int test_conv_impl(const locr_conv_desc* d, const float* x, const float* 
         c.skip_full = y == nullptr ? 1 : 0;
         if (y == nullptr) c.y = nullptr;
     }
+    // like the engine: calls with at most 1024 output pixels get a split-K workspace (LOCR_TEST_SPLITK=0, read per call,
+    // runs the same call unsplit)
+    DevBuf dws;
+    const char* sk = getenv("LOCR_TEST_SPLITK");
+    if (npix <= 1024 && !(sk && atoi(sk) == 0)) {
+        const size_t wsb = npix * 8 * (size_t)cout_pad * 4;
+        LOCR_CUDA_OK(dws.alloc(wsb));
+        LOCR_CUDA_OK(cudaMemset(dws.p, 0xff, wsb));      // NaN pattern: a partial sum that was never written shows
+        c.splitk_ws = dws.p;
+        c.splitk_ws_bytes = wsb;
+    }
     char err[256] = {0};
     cudaError_t e = conv_tc_launch(c, 0, err, sizeof(err));
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? LOCR_ERR_INVALID : LOCR_ERR_CUDA, err);
@@ -121,6 +132,9 @@ LOCR_API int locr_test_conv_pool(const locr_conv_desc* d, const float* x, const 
     if (y_pool == nullptr) return fail(LOCR_ERR_INVALID, "null argument");
     return test_conv_impl(d, x, w, bias, nullptr, y, y_pool);
 }
+
+/* Split-K convolutions (conv_tc.cuh splitk_ws) launched by this process so far. */
+LOCR_API int64_t locr_test_splitk_calls(void) { return (int64_t)conv_tc_splitk_calls(); }
 
 /* Times `iters` back-to-back launches of one conv layer on uninitialised (zeroed) device buffers. */
 LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_iter) {
@@ -155,6 +169,14 @@ LOCR_API int locr_bench_conv(const locr_conv_desc* d, int iters, float* ms_per_i
         c.pool_y = dp.p;
         c.pool_pitch = d->Cout;
         c.skip_full = atoi(penv) == 2 ? 1 : 0;
+    }
+    DevBuf dws;
+    const char* sk = getenv("LOCR_TEST_SPLITK");
+    if ((size_t)d->B * OH * OW <= 1024 && !(sk && atoi(sk) == 0)) {
+        const size_t wsb = (size_t)d->B * OH * OW * 8 * (size_t)cout_pad * 4;
+        LOCR_CUDA_OK(dws.alloc(wsb));
+        c.splitk_ws = dws.p;
+        c.splitk_ws_bytes = wsb;
     }
     char err[256] = {0};
     const char* wenv = getenv("LOCR_BENCH_WARMUP");   // profiler runs: 0 warm-ups keep the capture to one launch per layer

@@ -224,3 +224,58 @@ def test_cta_pair_kernels_on_every_eligible_layer():
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
 
+
+
+SPLITK_CASES = [
+    # name, B, H, W, Cin, Cout, KH, KW, pad, stride_h, residual, act   (16-bit outputs, ReLU; <= 1024 output pixels)
+    ("one_crop_c512", 1, 4, 26, 512, 512, 3, 3, (1, 1), 1, True, 0),          # 24 of the recogniser's 29 convs at B = 1
+    ("three_crops_c512", 3, 4, 26, 512, 512, 3, 3, (1, 1), 1, True, 0),       # three m-tiles: four slices
+    ("eight_crops_c512_bf16", 8, 4, 26, 512, 512, 3, 3, (1, 1), 1, False, 1),  # 7 m-tiles: two slices
+    ("one_crop_c256", 1, 8, 25, 256, 256, 3, 3, (1, 1), 1, True, 0),          # layer2: four chunks -> four slices
+    ("one_crop_c128", 1, 16, 50, 128, 128, 3, 3, (1, 1), 1, True, 0),         # layer1: two chunks -> two slices
+    ("one_crop_c256_c512", 1, 4, 26, 256, 512, 3, 3, (1, 1), 1, False, 0),    # layer3.0.conv1
+    ("conv4_1_k2_s21", 1, 4, 26, 512, 512, 2, 2, (0, 1), 2, False, 0),        # k2 s(2,1) p(0,1)
+    ("conv4_2_k2", 2, 2, 27, 512, 512, 2, 2, (0, 0), 1, False, 0),            # k2 s1 p0
+    ("downsample_1x1_c512", 1, 4, 26, 512, 512, 1, 1, (0, 0), 1, False, 0),   # 8 k-blocks
+    ("views_c64_of_c192", 2, 10, 20, 128, 64, 3, 3, (1, 1), 1, True, 0),      # channel-slice input / output views
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES, ids=[c[0] for c in SPLITK_CASES])
+def test_conv_split_k(case, monkeypatch):
+    """Split-K form of the deep layers on single crops / a handful of them (conv_tc.cuh splitk_ws): the K range runs as
+    up to 8 slices x n-tiles CTAs that store fp32 partial sums, a second kernel adds slices + bias + residual, applies
+    the ReLU and rounds.  Against torch's fp32 conv2d on the same rounded operands (tolerance of test_conv_parity), and
+    against the unsplit kernel: the two only differ in the order of fp32 additions, i.e. by at most one 16-bit
+    rounding step of a value that sat on a rounding boundary."""
+    from lightly_ocr_b200 import bridge
+    name, B, H, W, Cin, Cout, KH, KW, pad, stride_h, use_res, act = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    x_extra, y_extra = (64, 32) if name.startswith("views") else (0, 0)
+    x = rng.standard_normal((B, H, W, Cin + x_extra)).astype(np.float32)
+    w = (rng.standard_normal((Cout, KH, KW, Cin)) / np.sqrt(KH * KW * Cin)).astype(np.float32)
+    bias = rng.standard_normal(Cout).astype(np.float32)
+    OH = (H + 2 * pad[0] - (KH - 1) - 1) // stride_h + 1
+    OW = W + 2 * pad[1] - (KW - 1)
+    residual = rng.standard_normal((B, OH, OW, Cout)).astype(np.float32) if use_res else None
+    L = bridge.lib()
+    L.locr_test_splitk_calls.restype = __import__("ctypes").c_int64
+    kw = dict(pad=pad, stride_h=stride_h, relu=True, out_fp32=False, act_dtype=act, y_pitch=Cout + y_extra)
+    monkeypatch.setenv("LOCR_TEST_SPLITK", "1")
+    n0 = L.locr_test_splitk_calls()
+    y = bridge.test_conv(x, w, bias, residual, **kw)
+    assert L.locr_test_splitk_calls() == n0 + 1, "%s did not take the split-K form" % name
+    monkeypatch.setenv("LOCR_TEST_SPLITK", "0")
+    plain = bridge.test_conv(x, w, bias, residual, **kw)
+    assert L.locr_test_splitk_calls() == n0 + 1
+    ref = _ref(x[..., :Cin], w, bias, residual, (1, 1), pad, stride_h, True, act)
+    scale = float(np.abs(ref).max())
+    ulp = scale * (2.0 ** -8 if act == 1 else 2.0 ** -11)
+    err = float(np.abs(y[..., :Cout] - ref).max())
+    assert err <= 2e-3 * scale + ulp, "%s: max abs err %g (scale %g)" % (name, err, scale)
+    diff = np.abs(y - plain)
+    assert float(diff.max()) <= 2 * ulp, "%s: split and unsplit results differ by %g" % (name, float(diff.max()))
+    assert float((diff > 0).mean()) < 0.02
+    if y_extra:
+        assert np.all(y[..., Cout:] == 0), "kernel wrote outside its channel view"
