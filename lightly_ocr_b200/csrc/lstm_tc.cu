@@ -19,6 +19,7 @@
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = gate math.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "nn_kernels.cuh"
@@ -306,6 +307,196 @@ lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     ptx::cluster_wait_acquire();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Push form of the hand-over (fast arithmetic; LOCR_LSTM_MCAST=0 switches back to the pull form above).  In the pull
+// form every step pays: 8 remote arrivals per epilogue warp, a wait for all 64 warps of the cluster, and a 64 KB
+// pull-back of h per CTA - 2/3 of the step.  Here the K range is cut into EIGHT 32-unit chunks ([128 rows][64 B],
+// 64-byte swizzle), i.e. exactly one chunk per CTA of the cluster: as soon as the 8 epilogue warps of CTA r have stored
+// their 32 units of h_t (one CTA-local mbarrier), its producer issues ONE multicast TMA load of that 8 KB slice, which
+// lands as chunk r of the A buffer in all 8 CTAs and completes chunk r's barrier in each of them.  No cluster-wide
+// arrival round, every CTA reads 8 KB instead of 64 KB per step, and the MMAs of a chunk start when that chunk lands.
+// The A buffer is double buffered; a slice for step s + 1 can only be sent after the sender's epilogue of step s, which
+// needed every peer's slice of step s - 1, which each peer published after its own MMAs of step s - 1 had retired: the
+// buffer a multicast writes (last read at step s - 1) is free in every CTA, and barrier phases cannot alias.
+constexpr int kSliceBytes = 128 * 64;           // [128 crops][32 units] 16-bit = one CTA's share of h_t
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreadsLstm, 1)
+lstm_mcast_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                  const LstmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* w_buf = smem;                              // 8 chunks x kSliceBytes
+    uint8_t* a_buf = smem + kWBytes;                    // 2 x (8 chunks x kSliceBytes)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_buf + 2 * kABytes);
+    uint64_t* wfull_bar = bars;                         // [1]  W slice landed
+    uint64_t* afull_bar = bars + 1;                     // [2][8]  chunk kc of h landed (sent by CTA kc)
+    uint64_t* hlocal_bar = bars + 17;                   // [1]  this CTA's 8 epilogue warps stored their h slice
+    uint64_t* tfull_bar = bars + 18;                    // [1]  accumulator complete
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)ptx::cluster_ctarank();
+    const int dir = blockIdx.y;
+    const int crop0 = (blockIdx.x / kCluster) * 128;
+    const int T = p.T;
+
+    if (warp == 0 && lane == 0) {
+        ptx::tma_prefetch_desc(&tmap_w);
+        ptx::tma_prefetch_desc(&tmap_h);
+    }
+    if (warp == 1 && lane == 0) {
+        ptx::mbar_init(wfull_bar, 1);
+        for (int i = 0; i < 16; ++i) ptx::mbar_init(&afull_bar[i], 1);
+        ptx::mbar_init(hlocal_bar, kEpiWarps);
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr_smem, 128);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    // every CTA's barriers exist before a peer's multicast can signal them
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(wfull_bar, kWBytes);
+            for (int kc = 0; kc < 8; ++kc)
+                ptx::tma_load_2d(w_buf + kc * kSliceBytes, &tmap_w, wfull_bar, kc * 32, dir * 1024 + rank * 128);
+        }
+        for (int step = 1; step < T; ++step) {
+            const int b = step & 1;
+            const int t_prev = dir == 0 ? step - 1 : T - step;
+            // arm this step's eight chunk barriers (their previous phase, step - 2, was consumed before this CTA's
+            // epilogue of step - 2 could publish, which the previous iteration waited for)
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) ptx::mbar_arrive_expect_tx(&afull_bar[b * 8 + kc], kSliceBytes);
+            }
+            __syncwarp();
+            ptx::mbar_wait(hlocal_bar, (uint32_t)((step - 1) & 1), 500);     // h_{step-1}: this CTA's 32 units are in global memory
+            LSTM_STAMP(step, 0);
+            if (ptx::elect_one()) {
+                ptx::fence_proxy_async_all();
+                ptx::tma_load_3d_mcast(a_buf + b * kABytes + rank * kSliceBytes, &tmap_h, &afull_bar[b * 8 + rank],
+                                       dir * 256 + rank * 32, t_prev, crop0, (uint16_t)0xFF);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t desc_hi = (uint32_t)(ptx::make_kmajor_desc(0, 64) >> 32);
+        const uint32_t a_lo0 = ((ptx::smem_u32(a_buf) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t w_lo0 = ((ptx::smem_u32(w_buf) & 0x3FFFFu) >> 4) | (1u << 16);
+        ptx::mbar_wait(wfull_bar, 0, 600);
+        for (int step = 1; step < T; ++step) {
+            const int b = step & 1;
+            const uint32_t par = (uint32_t)(((step - 1) >> 1) & 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // own chunk last: it is the one this CTA sends itself, i.e. the one that leaves latest
+                const int kc = (rank + 1 + i) & 7;
+                ptx::mbar_wait(&afull_bar[b * 8 + kc], par, 610);
+                ptx::tc_fence_after();
+                const uint32_t a_lo = a_lo0 + (uint32_t)((b * kABytes + kc * kSliceBytes) >> 4);
+                const uint32_t w_lo = w_lo0 + (uint32_t)((kc * kSliceBytes) >> 4);
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        ptx::umma_f16_lohi(tmem_base, a_lo + k * 2, desc_hi, w_lo + k * 2, desc_hi, p.idesc, (i | k) ? 1u : 0u);
+                    if (i == 7) ptx::umma_commit(tfull_bar);
+                }
+                if (i == 0) LSTM_STAMP(step, 1);
+                if (i == 7) LSTM_STAMP(step, 2);
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;                 // TMEM lane quarter
+        const int chalf = (warp - 4) >> 2;            // which 64 of the CTA's 128 gate columns (16 units)
+        const int row = quarter * 32 + lane;          // crop within the cluster's block
+        const int crop = crop0 + row;
+        const bool valid = crop < p.B;
+        const int ucol = rank * 32 + chalf * 16;      // first hidden unit of this thread
+        const float* xp_base = p.xproj + (size_t)(valid ? crop : 0) * T * 2048 + dir * 1024 + ucol * 4;
+        uint16_t* out_base = p.out + (size_t)(valid ? crop : 0) * T * p.pitch + dir * 256 + ucol;
+        float cc[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cc[u] = 0.f;
+        float4 x[16];
+        {
+            const int t0 = dir == 0 ? 0 : T - 1;
+            const float4* xp4 = reinterpret_cast<const float4*>(xp_base + (size_t)t0 * 2048);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) x[u] = valid ? __ldg(xp4 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int step = 0; step < T; ++step) {
+            const int t = dir == 0 ? step : T - 1 - step;
+            if (step > 0) {
+                ptx::mbar_wait(tfull_bar, (uint32_t)((step - 1) & 1), 700);
+                ptx::tc_fence_after();
+            }
+            if (warp == 4) LSTM_STAMP(step, 3);       // accumulator complete
+            uint32_t hp[8];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t r[32];
+                if (step > 0) {
+                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * 64 + hf * 32), r);
+                    ptx::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                float hv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 xv = x[hf * 8 + u];
+                    const float gi = sigmoid_f(__uint_as_float(r[u * 4 + 0]) + xv.x);
+                    const float gf = sigmoid_f(__uint_as_float(r[u * 4 + 1]) + xv.y);
+                    const float gg = tanh_f(__uint_as_float(r[u * 4 + 2]) + xv.z);
+                    const float go = sigmoid_f(__uint_as_float(r[u * 4 + 3]) + xv.w);
+                    const float c = gf * cc[hf * 8 + u] + gi * gg;
+                    cc[hf * 8 + u] = c;
+                    hv[u] = go * tanh_f(c);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hp[hf * 4 + q] = pack2h(hv[q * 2], hv[q * 2 + 1], p.is_f16);
+            }
+            if (warp == 4) LSTM_STAMP(step, 4);       // gate math done
+            if (valid) {
+                uint4* o = reinterpret_cast<uint4*>(out_base + (size_t)t * p.pitch);
+                o[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                o[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+            }
+            if (step + 1 < T) {
+                // h_t is in global memory (generic proxy); this CTA's producer reads it back through TMA (async proxy)
+                ptx::fence_proxy_async_all();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(hlocal_bar);
+                if (warp == 4) LSTM_STAMP(step, 5);   // h stored, producer signalled
+                const int tn = dir == 0 ? step + 1 : T - 2 - step;
+                const float4* xp4 = reinterpret_cast<const float4*>(xp_base + (size_t)tn * 2048);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) x[u] = valid ? __ldg(xp4 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 128);
+    }
+    // no CTA leaves while a peer's multicast could still be writing into it
+    ptx::cluster_arrive_release();
+    ptx::cluster_wait_acquire();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -327,6 +518,44 @@ cudaError_t launch_lstm_tc(const float* xproj, const void* whh_perm, void* out, 
     const CUtensorMapDataType dt = is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUtensorMap mw, mh, mhlo;
     const int pitch = split ? 1024 : 512;
+    static int allow_mcast = -1;
+    if (allow_mcast < 0) { const char* e = getenv("LOCR_LSTM_MCAST"); allow_mcast = e ? atoi(e) : 1; }
+    if (allow_mcast && !split) {
+        // push form: 32-unit chunks ([128 rows][64 B], 64-byte swizzle), one per CTA of the cluster
+        {
+            cuuint64_t dims[2] = {256, 2048};
+            cuuint64_t strides[1] = {512};
+            cuuint32_t box[2] = {32, 128};
+            cuuint32_t estr[2] = {1, 1};
+            if (encode(&mw, dt, 2, const_cast<void*>(whh_perm), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaErrorInvalidValue;
+        }
+        {
+            cuuint64_t dims[3] = {512, (cuuint64_t)T, (cuuint64_t)B};
+            cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)T * pitch * 2};
+            cuuint32_t box[3] = {32, 1, 128};
+            cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&mh, dt, 3, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaErrorInvalidValue;
+        }
+        static bool attr_m = false;
+        const size_t smem_m = 1024 + kWBytes + 2 * kABytes + 24 * 8;
+        if (!attr_m) {
+            cudaError_t e = cudaFuncSetAttribute(lstm_mcast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+            if (e != cudaSuccess) return e;
+            attr_m = true;
+        }
+        LstmParams pm;
+        pm.xproj = xproj; pm.out = (uint16_t*)out; pm.B = B; pm.T = T; pm.is_f16 = is_f16; pm.pitch = pitch;
+        pm.idesc = ptx::make_idesc_f16(is_f16 ? 0 : 1, 128, 128);
+        dim3 grid_m(kCluster * ((B + 127) / 128), 2);
+        lstm_mcast_kernel<<<grid_m, kThreadsLstm, smem_m, s>>>(mw, mh, pm);
+        return cudaGetLastError();
+    }
     {
         cuuint64_t dims[2] = {256, 2048};
         cuuint64_t strides[1] = {512};

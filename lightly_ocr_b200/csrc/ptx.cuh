@@ -124,6 +124,16 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, ui
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Multicast form: the box lands at the same CTA-relative shared-memory offset in every CTA of the cluster whose bit is
+// set in cta_mask, and each of those CTAs' mbarriers (same CTA-relative offset as bar) receives the complete_tx.
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+        "[%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
