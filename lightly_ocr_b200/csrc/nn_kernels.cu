@@ -420,36 +420,110 @@ upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, 
 }
 
 // ------------------------------------------------------------------------------------------- TPS localisation head
-__global__ void __launch_bounds__(256)
-loc_head_kernel(const uint16_t* __restrict__ feat, int hw, const float* __restrict__ w1t, const float* __restrict__ b1,
-                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ fid, int f16, int split) {
-    __shared__ float pooled[512];
-    __shared__ float hid[256];
-    const int b = blockIdx.x;
+// AdaptiveAvgPool2d(1) + Linear(512, 256) + ReLU + Linear(256, 40) in fp32 (TPS_STN.py:48-51, :73-76).  Four crops per
+// CTA share every weight load (one CTA per crop re-read the 512 KB of fc1 once per crop: L2-bound at 635 crops), and
+// the two dot products are cut over the threads (fc1: two K halves x 256 outputs, fc2: 16 K slices x 40 outputs) with
+// the partial sums added in a fixed order, so a single crop is no longer one 512-long dependent chain per thread
+// (46 us whatever the batch -> a few us).  A crop's result does not depend on which other crops share its CTA.
+constexpr int kLocG = 4;
+
+__global__ void __launch_bounds__(512)
+loc_head_kernel(const uint16_t* __restrict__ feat, int B, int hw, const float* __restrict__ w1t,
+                const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                float* __restrict__ fid, int f16, int split) {
+    __shared__ float pooled[kLocG][512];
+    __shared__ float part1[2][kLocG][256];
+    __shared__ float hid[kLocG][256];
+    __shared__ float part2[16][kLocG][40];
+    const int b0 = blockIdx.x * kLocG;
+    const int ng = B - b0 < kLocG ? B - b0 : kLocG;
     const int pitch = split ? 1024 : 512;
-    const uint16_t* f = feat + (long)b * hw * pitch;
-    for (int c = threadIdx.x; c < 512; c += blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < hw; ++p) {
-            float v = act2f(f[(long)p * pitch + c], f16);
-            if (split) v += act2f(f[(long)p * pitch + 512 + c], f16);
-            s += v;
+    {
+        const int c = threadIdx.x;      // 512 threads = 512 channels
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) {
+            float s = 0.f;
+            if (g < ng) {
+                const uint16_t* f = feat + (long)(b0 + g) * hw * pitch;
+                // eight positions' loads in flight at a time; the sum keeps its order (position by position, hi + lo first)
+                for (int p0 = 0; p0 < hw; p0 += 8) {
+                    uint16_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int pp = p0 + i < hw ? p0 + i : hw - 1;
+                        hi[i] = __ldg(&f[(long)pp * pitch + c]);
+                        lo[i] = split ? __ldg(&f[(long)pp * pitch + 512 + c]) : (uint16_t)0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (p0 + i < hw) {
+                            float v = act2f(hi[i], f16);
+                            if (split) v += act2f(lo[i], f16);
+                            s += v;
+                        }
+                    }
+                }
+                s = s / (float)hw;
+            }
+            pooled[g][c] = s;
         }
-        pooled[c] = s / (float)hw;
     }
     __syncthreads();
     {
-        const int j = threadIdx.x;  // 256 threads
-        float s = b1[j];
-        for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], w1t[k * 256 + j], s);
-        hid[j] = fmaxf(s, 0.f);
+        const int j = threadIdx.x & 255, kh = threadIdx.x >> 8;
+        const float* w = w1t + (long)(kh * 256) * 256 + j;
+        float s[kLocG];
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) s[g] = 0.f;
+#pragma unroll 32
+        for (int k = 0; k < 256; ++k) {
+            const float wv = __ldg(w + (long)k * 256);
+#pragma unroll
+            for (int g = 0; g < kLocG; ++g) s[g] = fmaf(pooled[g][kh * 256 + k], wv, s[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) part1[kh][g][j] = s[g];
     }
     __syncthreads();
-    if (threadIdx.x < 40) {
+    if (threadIdx.x < 256) {
         const int j = threadIdx.x;
-        float s = b2[j];
-        for (int k = 0; k < 256; ++k) s = fmaf(hid[k], w2t[k * 40 + j], s);
-        fid[b * 40 + j] = s;
+        const float bj = b1[j];
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) hid[g][j] = fmaxf((bj + part1[0][g][j]) + part1[1][g][j], 0.f);
+    }
+    __syncthreads();
+    {
+        const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // 16 warps = 16 K slices of 16
+        float s0[kLocG], s1[kLocG];
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) { s0[g] = 0.f; s1[g] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = wp * 16 + kk;
+            const float wa = __ldg(&w2t[k * 40 + lane]);
+            const float wb = lane < 8 ? __ldg(&w2t[k * 40 + 32 + lane]) : 0.f;
+#pragma unroll
+            for (int g = 0; g < kLocG; ++g) {
+                const float hv = hid[g][k];
+                s0[g] = fmaf(hv, wa, s0[g]);
+                s1[g] = fmaf(hv, wb, s1[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < kLocG; ++g) {
+            part2[wp][g][lane] = s0[g];
+            if (lane < 8) part2[wp][g][32 + lane] = s1[g];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kLocG * 40) {
+        const int g = threadIdx.x / 40, j = threadIdx.x - g * 40;
+        if (g < ng) {
+            float s = b2[j];
+#pragma unroll
+            for (int wq = 0; wq < 16; ++wq) s += part2[wq][g][j];
+            fid[(long)(b0 + g) * 40 + j] = s;
+        }
     }
 }
 
@@ -697,6 +771,52 @@ attention_kernel(const uint16_t* __restrict__ feats, const float* __restrict__ f
 }
 
 // ------------------------------------------------------------------------------------------- token decode
+// decode_kernel below walks the 26 steps one after the other (two dependent passes over global memory and two shuffle
+// reductions per step: ~33 us whatever the batch).  decode_smem_kernel (C <= 64, i.e. both heads of the reference) loads
+// a crop's 26 x C logits into shared memory with independent coalesced loads and lets lane t handle step t on its own:
+// arg-max (first maximum, like torch) and soft-max probability of all 26 steps in one pass.
+constexpr int kDecodeMaxC = 64;
+
+__device__ __forceinline__ void decode_tail(const int* idv, const float* pv, int head_attn, char* out, int text_stride,
+                                            int32_t* has_eos, float* conf);
+
+__global__ void __launch_bounds__(128)
+decode_smem_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int32_t* __restrict__ ids,
+                   char* __restrict__ text, int text_stride, int32_t* __restrict__ has_eos, float* __restrict__ conf) {
+    constexpr int T = 26;
+    __shared__ float s_lg[4][T * kDecodeMaxC];
+    __shared__ int s_id[4][32];
+    __shared__ float s_p[4][32];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crop = blockIdx.x * 4 + wib;
+    if (crop >= B) return;
+    const float* lg = logits + (long)crop * T * C;
+    float* sl = s_lg[wib];
+    const int n_el = T * C;
+    for (int i = lane; i < n_el; i += 32) sl[i] = lg[i];
+    __syncwarp();
+    if (lane < T) {
+        const float* row = sl + lane * C;
+        float best = row[0];
+        int bi = 0;
+        for (int v = 1; v < C; ++v) {
+            const float x = row[v];
+            if (x > best) {
+                best = x;
+                bi = v;
+            }
+        }
+        float sum = 0.f;
+        for (int v = 0; v < C; ++v) sum += expf(row[v] - best);
+        s_id[wib][lane] = bi;
+        s_p[wib][lane] = 1.f / sum;
+        ids[crop * T + lane] = bi;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    decode_tail(s_id[wib], s_p[wib], head_attn, text + (long)crop * text_stride, text_stride, has_eos + crop, conf + crop);
+}
+
 __global__ void __launch_bounds__(128)
 decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int32_t* __restrict__ ids,
               char* __restrict__ text, int text_stride, int32_t* __restrict__ has_eos, float* __restrict__ conf) {
@@ -745,8 +865,15 @@ decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int
         pv[t] = __shfl_sync(0xffffffffu, my_p, t);
     }
     if (lane != 0) return;
+    decode_tail(idv, pv, head_attn, text + (long)warp * text_stride, text_stride, has_eos + warp, conf + warp);
+}
+
+// The sequential part (one lane per crop): collapse / cut the token sequence into the string and multiply the step
+// probabilities in step order (the reference's cumprod, net.py:177-190).
+__device__ __forceinline__ void decode_tail(const int* idv, const float* pv, int head_attn, char* out, int text_stride,
+                                            int32_t* has_eos, float* conf) {
+    constexpr int T = 26;
     const char* alphabet = "0123456789abcdefghijklmnopqrstuvwxyz";
-    char* out = text + (long)warp * text_stride;
     int n = 0;
     if (!head_attn) {
         float p = 1.f;
@@ -756,8 +883,8 @@ decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int
             p *= pv[t];
         }
         out[n] = 0;
-        has_eos[warp] = 1;
-        conf[warp] = p;
+        *has_eos = 1;
+        *conf = p;
     } else {
         // tokens: 0 = "[GO]", 1 = "[s]", 2.. = alphabet.  The reference cuts string and probabilities at the CHARACTER
         // index of the first "[s]" (net.py:184-186).
@@ -779,17 +906,17 @@ decode_kernel(const float* __restrict__ logits, int B, int C, int head_attn, int
         }
         out[n] = 0;
         if (eos_tok < 0) {
-            has_eos[warp] = 0;
-            conf[warp] = 0.f;
+            *has_eos = 0;
+            *conf = 0.f;
         } else if (n == 0) {
-            has_eos[warp] = -1;  // reference: cumprod of an empty tensor, [-1] raises IndexError
-            conf[warp] = 0.f;
+            *has_eos = -1;  // reference: cumprod of an empty tensor, [-1] raises IndexError
+            *conf = 0.f;
         } else {
             const int m = n < T ? n : T;  // n = character index of "[s]"
             float p = 1.f;
             for (int t = 0; t < m; ++t) p *= pv[t];
-            has_eos[warp] = 1;
-            conf[warp] = p;
+            *has_eos = 1;
+            *conf = p;
         }
     }
 }
@@ -1030,7 +1157,7 @@ void launch_upsample2x(const void* in, long in_pitch, int B, int H, int W, int C
 
 void launch_loc_head(const void* feat, int B, int hw, const float* w1t, const float* b1, const float* w2t,
                      const float* b2, float* fid, int is_f16, cudaStream_t s, int split) {
-    loc_head_kernel<<<B, 256, 0, s>>>((const uint16_t*)feat, hw, w1t, b1, w2t, b2, fid, is_f16, split);
+    loc_head_kernel<<<(B + kLocG - 1) / kLocG, 512, 0, s>>>((const uint16_t*)feat, B, hw, w1t, b1, w2t, b2, fid, is_f16, split);
 }
 
 void launch_tps_sample(const float* fid, const float* inv_delta_c, const float* p_hat_t, const float* x, float* out,
@@ -1072,8 +1199,12 @@ void launch_attn_ce(const float* logits, int B, int C, const int32_t* targets, i
 void launch_decode(const float* logits, int B, int C, int head_attn, int32_t* ids, char* text, int text_stride,
                    int32_t* has_eos, float* conf, cudaStream_t s) {
     const int warps_per_block = 4;
-    decode_kernel<<<(B + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(logits, B, C, head_attn, ids, text,
-                                                                              text_stride, has_eos, conf);
+    if (C <= kDecodeMaxC)
+        decode_smem_kernel<<<(B + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(logits, B, C, head_attn, ids, text,
+                                                                                       text_stride, has_eos, conf);
+    else
+        decode_kernel<<<(B + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(logits, B, C, head_attn, ids, text,
+                                                                                  text_stride, has_eos, conf);
 }
 
 }  // namespace locr

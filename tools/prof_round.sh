@@ -8,7 +8,7 @@ set -x
 for ST in $STAGES; do
 case $ST in
 list)
-    BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin --no-other-precision"
+    BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dropin --no-other-precision --no-other-head"
     export LOCR_BENCH_PASSES=1
     export LOCR_BENCH_LANES=2     # the skip / count below are for two lanes
     # launches 0..515 are the three warm-up passes of the e2e leg (2 lanes x 86 launches per pass); the next 344 are its timed region
