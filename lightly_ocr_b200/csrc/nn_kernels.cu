@@ -420,80 +420,100 @@ upsample2x_kernel(const uint16_t* __restrict__ in, long in_pitch, int B, int H, 
 }
 
 // ------------------------------------------------------------------------------------------- TPS localisation head
-// AdaptiveAvgPool2d(1) + Linear(512, 256) + ReLU + Linear(256, 40) in fp32 (TPS_STN.py:48-51, :73-76).  Four crops per
-// CTA share every weight load (one CTA per crop re-read the 512 KB of fc1 once per crop: L2-bound at 635 crops), and
-// the two dot products are cut over the threads (fc1: two K halves x 256 outputs, fc2: 16 K slices x 40 outputs) with
-// the partial sums added in a fixed order, so a single crop is no longer one 512-long dependent chain per thread
-// (46 us whatever the batch -> a few us).  A crop's result does not depend on which other crops share its CTA.
-constexpr int kLocG = 4;
+// AdaptiveAvgPool2d(1) + Linear(512, 256) + ReLU + Linear(256, 40) in fp32 (TPS_STN.py:48-51, :73-76).  Eight crops per
+// CTA share every weight load (one CTA per crop re-read the 512 KB of fc1 once per crop: L2-bound at 635 crops, and a
+// single 512-long dependent chain per thread).  Pooling: thread = (8 channels, one of 8 position groups), 16-byte
+// loads, all of a crop's loads in flight at once, the position groups added in a fixed order.  fc1: two K halves x 256
+// outputs, the eight crops' inputs of one k as two 16-byte shared-memory reads; fc2: 16 K slices x 40 outputs; partial
+// sums added in a fixed order.  A crop's result does not depend on which other crops share its CTA.
+constexpr int kLocG = 8;
 
 __global__ void __launch_bounds__(512)
 loc_head_kernel(const uint16_t* __restrict__ feat, int B, int hw, const float* __restrict__ w1t,
                 const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                 float* __restrict__ fid, int f16, int split) {
-    __shared__ float pooled[kLocG][512];
-    __shared__ float part1[2][kLocG][256];
-    __shared__ float hid[kLocG][256];
-    __shared__ float part2[16][kLocG][40];
+    __shared__ __align__(16) float pooled_t[512][kLocG];          // [k][crop]
+    __shared__ __align__(16) float scratch[16 * kLocG * 40];      // pooling partials [8][512] / fc1 partials [2][256][G] / fc2 partials [16][G][40]
+    __shared__ __align__(16) float hid_t[256][kLocG];             // [k][crop]
+    const int tid = threadIdx.x;
     const int b0 = blockIdx.x * kLocG;
     const int ng = B - b0 < kLocG ? B - b0 : kLocG;
     const int pitch = split ? 1024 : 512;
     {
-        const int c = threadIdx.x;      // 512 threads = 512 channels
-#pragma unroll
+        const int cg = tid & 63, pg = tid >> 6;
         for (int g = 0; g < kLocG; ++g) {
-            float s = 0.f;
-            if (g < ng) {
-                const uint16_t* f = feat + (long)(b0 + g) * hw * pitch;
-                // eight positions' loads in flight at a time; the sum keeps its order (position by position, hi + lo first)
-                for (int p0 = 0; p0 < hw; p0 += 8) {
-                    uint16_t hi[8], lo[8];
+            float acc[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pp = p0 + i < hw ? p0 + i : hw - 1;
-                        hi[i] = __ldg(&f[(long)pp * pitch + c]);
-                        lo[i] = split ? __ldg(&f[(long)pp * pitch + 512 + c]) : (uint16_t)0;
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            if (g < ng) {
+                const uint16_t* f = feat + (long)(b0 + g) * hw * pitch + cg * 8;
+                for (int p0 = pg; p0 < hw; p0 += 64) {
+                    uint4 hv[8], lv[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int pp = p0 + 8 * it;
+                        hv[it] = make_uint4(0u, 0u, 0u, 0u);
+                        lv[it] = make_uint4(0u, 0u, 0u, 0u);
+                        if (pp < hw) {
+                            hv[it] = __ldg(reinterpret_cast<const uint4*>(f + (long)pp * pitch));
+                            if (split) lv[it] = __ldg(reinterpret_cast<const uint4*>(f + (long)pp * pitch + 512));
+                        }
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (p0 + i < hw) {
-                            float v = act2f(hi[i], f16);
-                            if (split) v += act2f(lo[i], f16);
-                            s += v;
+                    for (int it = 0; it < 8; ++it) {
+                        if (p0 + 8 * it < hw) {
+                            float a[8], l[8];
+                            unpack8(hv[it], a, f16);
+                            unpack8(lv[it], l, f16);     // zeros when the tensor is not split
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i] += a[i] + l[i];
                         }
                     }
                 }
-                s = s / (float)hw;
             }
-            pooled[g][c] = s;
+            float4* dst = reinterpret_cast<float4*>(&scratch[pg * 512 + cg * 8]);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            __syncthreads();
+            {
+                float sum = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sum += scratch[q * 512 + tid];
+                pooled_t[tid][g] = sum / (float)hw;
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
     {
-        const int j = threadIdx.x & 255, kh = threadIdx.x >> 8;
+        const int j = tid & 255, kh = tid >> 8;
         const float* w = w1t + (long)(kh * 256) * 256 + j;
-        float s[kLocG];
+        float sacc[kLocG];
 #pragma unroll
-        for (int g = 0; g < kLocG; ++g) s[g] = 0.f;
-#pragma unroll 32
+        for (int g = 0; g < kLocG; ++g) sacc[g] = 0.f;
+#pragma unroll 16
         for (int k = 0; k < 256; ++k) {
             const float wv = __ldg(w + (long)k * 256);
-#pragma unroll
-            for (int g = 0; g < kLocG; ++g) s[g] = fmaf(pooled[g][kh * 256 + k], wv, s[g]);
+            const float4 pa = *reinterpret_cast<const float4*>(&pooled_t[kh * 256 + k][0]);
+            const float4 pb = *reinterpret_cast<const float4*>(&pooled_t[kh * 256 + k][4]);
+            sacc[0] = fmaf(pa.x, wv, sacc[0]); sacc[1] = fmaf(pa.y, wv, sacc[1]);
+            sacc[2] = fmaf(pa.z, wv, sacc[2]); sacc[3] = fmaf(pa.w, wv, sacc[3]);
+            sacc[4] = fmaf(pb.x, wv, sacc[4]); sacc[5] = fmaf(pb.y, wv, sacc[5]);
+            sacc[6] = fmaf(pb.z, wv, sacc[6]); sacc[7] = fmaf(pb.w, wv, sacc[7]);
         }
-#pragma unroll
-        for (int g = 0; g < kLocG; ++g) part1[kh][g][j] = s[g];
+        float4* dst = reinterpret_cast<float4*>(&scratch[(kh * 256 + j) * kLocG]);
+        dst[0] = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+        dst[1] = make_float4(sacc[4], sacc[5], sacc[6], sacc[7]);
     }
     __syncthreads();
-    if (threadIdx.x < 256) {
-        const int j = threadIdx.x;
-        const float bj = b1[j];
+    if (tid < 256) {
+        const float bj = b1[tid];
 #pragma unroll
-        for (int g = 0; g < kLocG; ++g) hid[g][j] = fmaxf((bj + part1[0][g][j]) + part1[1][g][j], 0.f);
+        for (int g = 0; g < kLocG; ++g)
+            hid_t[tid][g] = fmaxf((bj + scratch[tid * kLocG + g]) + scratch[(256 + tid) * kLocG + g], 0.f);
     }
     __syncthreads();
     {
-        const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // 16 warps = 16 K slices of 16
+        const int wp = tid >> 5, lane = tid & 31;     // 16 warps = 16 K slices of 16
         float s0[kLocG], s1[kLocG];
 #pragma unroll
         for (int g = 0; g < kLocG; ++g) { s0[g] = 0.f; s1[g] = 0.f; }
@@ -502,27 +522,30 @@ loc_head_kernel(const uint16_t* __restrict__ feat, int B, int hw, const float* _
             const int k = wp * 16 + kk;
             const float wa = __ldg(&w2t[k * 40 + lane]);
             const float wb = lane < 8 ? __ldg(&w2t[k * 40 + 32 + lane]) : 0.f;
+            const float4 ha = *reinterpret_cast<const float4*>(&hid_t[k][0]);
+            const float4 hb = *reinterpret_cast<const float4*>(&hid_t[k][4]);
+            const float hv8[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
             for (int g = 0; g < kLocG; ++g) {
-                const float hv = hid[g][k];
-                s0[g] = fmaf(hv, wa, s0[g]);
-                s1[g] = fmaf(hv, wb, s1[g]);
+                s0[g] = fmaf(hv8[g], wa, s0[g]);
+                s1[g] = fmaf(hv8[g], wb, s1[g]);
             }
         }
+        // (the fc1 partials in `scratch` were consumed before the barrier above)
 #pragma unroll
         for (int g = 0; g < kLocG; ++g) {
-            part2[wp][g][lane] = s0[g];
-            if (lane < 8) part2[wp][g][32 + lane] = s1[g];
+            scratch[(wp * kLocG + g) * 40 + lane] = s0[g];
+            if (lane < 8) scratch[(wp * kLocG + g) * 40 + 32 + lane] = s1[g];
         }
     }
     __syncthreads();
-    if (threadIdx.x < kLocG * 40) {
-        const int g = threadIdx.x / 40, j = threadIdx.x - g * 40;
+    if (tid < kLocG * 40) {
+        const int g = tid / 40, j = tid - g * 40;
         if (g < ng) {
-            float s = b2[j];
+            float sum = b2[j];
 #pragma unroll
-            for (int wq = 0; wq < 16; ++wq) s += part2[wq][g][j];
-            fid[(long)(b0 + g) * 40 + j] = s;
+            for (int wq = 0; wq < 16; ++wq) sum += scratch[(wq * kLocG + g) * 40 + j];
+            fid[(long)(b0 + g) * 40 + j] = sum;
         }
     }
 }
