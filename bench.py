@@ -520,12 +520,20 @@ def main():
     import torch.distributed as dist
     from lightly_ocr_b200 import bridge, shard
     from lightly_ocr_b200.synth import weights
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    # LOCR_BENCH_BACKEND=gloo exists for tests/test_bench_cpu.py only: the bench's multi-rank bookkeeping (barriers, per-rank
+    # times, reductions, the one JSON line) run on CPU tensors against a stand-in engine.  The product path stays CUDA-only.
+    backend = os.environ.get("LOCR_BENCH_BACKEND", "nccl")
+    if backend == "nccl":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        if world > 1:
+            dist.init_process_group(backend)
     head = args.head
 
     from concurrent.futures import ThreadPoolExecutor
@@ -553,7 +561,8 @@ def main():
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if backend == "nccl":
+            torch.cuda.synchronize()
 
     def launches():
         return sum(r.launch_count() for r in runners)

@@ -100,3 +100,46 @@ def test_bench_line_shape_with_a_stand_in_engine(monkeypatch, argv):
         # main legs, exact leg, other-head leg: LANES runners each, every one closed again
         assert [m.head for m in _Runner.made] == [head] * (2 * bench.LANES) + [other] * bench.LANES
     assert all(m.closed for m in _Runner.made)
+
+
+_WORKER = r"""
+import io, json, os, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+import bench
+from lightly_ocr_b200 import bridge
+from lightly_ocr_b200.synth import weights
+from test_bench_cpu import _Runner
+bridge.OcrRunner = _Runner
+weights.craft_calibrated = lambda *a, **k: {"head": None}
+weights.crnn_calibrated = lambda seed, head: {"head": head}
+bench.make_receipts = lambda rank, n: [np.zeros((8, 8, 3), np.uint8) for _ in range(n)]
+sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3"]
+bench.main()
+"""
+
+
+def test_bench_two_ranks_gloo(tmp_path):
+    """The launch the driver uses for N > 1 (one process per GPU, RANK / WORLD_SIZE / MASTER_* from the environment), two
+    ranks over gloo with the stand-in engine: every leg's barriers and reductions line up on both ranks, rank 0 alone
+    prints the one JSON line, whole-job values count both ranks, per-rank times are reported."""
+    import subprocess
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % (ROOT, ROOT))
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29719", LOCR_BENCH_BACKEND="gloo",
+               LOCR_BENCH_SAMPLER="0")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert outs[1][0].strip() == "", "rank 1 printed: %r" % outs[1][0]
+    line = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert len(line["ranks"]["per_rank_dev_s"]) == 2 and len(line["e2e"]["ranks"]["per_rank_wall_s"]) == 2
+    # the stand-in reports 3 crops per receipt on every rank: whole-job crops / receipts = 3
+    assert abs(line["crops_per_sec"] / line["value"] - 3.0) < 1e-9
+    assert line["other_head"]["n_gpus"] == 2 and line["other_head"]["head"] == "Attention" and line["other_head"]["value"] > 0
+    assert abs(line["other_head"]["crops_per_sec"] / line["other_head"]["value"] - 3.0) < 1e-9
+    assert line["other_precision"]["precision"] == "exact"
+    assert "e2e_dropin" not in line and "cpu_baseline" not in line     # rank 0 at N = 1 only
