@@ -282,7 +282,9 @@ class CRNN(Placeholder):
             if r["has_eos"] == -1:
                 raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
             raw_pred = r["text"]
-        confidence = torch.tensor(float(r["conf"]), dtype=torch.float32)
-        print(f"results: {raw_pred}\tconfidence score: {confidence:.4f}\n")
+        conf = float(r["conf"])
+        confidence = torch.tensor(conf, dtype=torch.float32)
+        # the reference formats the 0-d tensor (net.py:192), i.e. tensor.item(): the same double as the fp32 value here
+        print(f"results: {raw_pred}\tconfidence score: {conf:.4f}\n")
         result[confidence] = raw_pred
         return raw_pred, result

@@ -281,3 +281,15 @@ def test_evaluation_loop_host_logic():
     assert tg.shape == (3, 27) and tg[0, :4].tolist() == [0, 12, 13, 1] and tg[2, :5].tolist() == [0, 2, 37, 11, 1]
     assert eng2.calls[0][2].tolist() == [3, 2, 4]
 
+
+
+def test_confidence_line_formats_like_the_reference_tensor():
+    """net.CRNN.process prints `confidence score: {confidence:.4f}` of a 0-d fp32 tensor (reference ocr/net.py:192); the
+    drop-in formats the Python float it built the tensor from - the same characters for every fp32 value."""
+    import torch
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.random(5000).astype(np.float32),
+                           np.float32([0, 1, 0.99995, 0.00005, 1e-8, 0.12345, 0.5, 0.99999994, 0.00015, 0.99985])])
+    for v in vals:
+        conf = float(v)
+        assert f"{torch.tensor(conf, dtype=torch.float32):.4f}" == f"{conf:.4f}"
