@@ -283,22 +283,27 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ the drop-in leg
-def dropin_leg(head, device_index, images):
+def dropin_leg(head, device_index, images, via_reference=False):
     """receipts/s through the reference-facing classes exactly as ocr/pipeline.py:65-87 drives them: one image at a
     time, `net.CRAFT.process(image)` then one `net.CRNN.process(result, gray)` per crop with cv2.cvtColor on the host
-    (decoded images in, result dicts out).  When baseline/_ref/ocr is installed the loop is the reference's own
-    `pipeline.getText` on PNG files (cv2.imread included)."""
+    (decoded images in, result dicts out).  Nothing under oracle/ is touched.  via_reference (--dropin-via-reference,
+    needs baseline/_ref/ocr): additionally the unmodified reference's own `pipeline.getText` on PNG files (cv2.imread
+    included) with the drop-in classes behind it, staged by the same helper the reference arm uses."""
     import cv2
     import torch
+    import yaml
     from lightly_ocr_b200.synth import weights
-    from oracle import ref_env
     tmp = tempfile.mkdtemp(prefix="locr_dropin_")
     craft_sd, crnn_sd = weights.craft_calibrated(0, ink=True), weights.crnn_calibrated(1, head)
     out = {}
-    if ref_env.source() is not None:
+    ref_env = None
+    if via_reference:
+        from oracle import ref_env as _ref_env
+        if _ref_env.source() is not None:
+            ref_env = _ref_env
+    if ref_env is not None:
         dst = ref_env.stage(head, craft_sd, crnn_sd, tmp)
     else:
-        import yaml
         dst = os.path.join(tmp, "ocr_" + head)
         os.makedirs(os.path.join(dst, "save_models"))
         with open(os.path.join(ROOT, "lightly_ocr_b200", "config.yml")) as f:
@@ -342,7 +347,7 @@ def dropin_leg(head, device_index, images):
            "ms_per_receipt_median": 1e3 * statistics.median(lat), "crops_per_sec": crops / dt, "receipts": len(images),
            "path": "net.CRAFT.process(image) + net.CRNN.process(result, gray) per crop, one image at a time "
                    "(ocr/pipeline.py:70-79); decoded BGR arrays in, result dict out"}
-    if ref_env.source() is not None:
+    if ref_env is not None:
         paths = []
         for i, im in enumerate(images):
             p = os.path.join(tmp, "r%d.png" % i)
@@ -490,6 +495,9 @@ def main():
     ap.add_argument("--head", default=None, choices=["CTC", "Attention"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (one image at a time through net.py)")
+    ap.add_argument("--dropin-via-reference", action="store_true",
+                    help="e2e_dropin additionally times the unmodified reference's pipeline.getText(path) over the drop-in "
+                         "classes (needs baseline/_ref/ocr)")
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
                     help="arithmetic of the recogniser for the main legs (include/locr.h LOCR_PREC_*); the other mode is "
                          "timed as an extra e2e leg (`other_precision`) unless --no-other-precision")
@@ -783,7 +791,7 @@ def main():
             line["e2e_jpeg"] = e2e_jpeg
         if world == 1 and not args.no_dropin:
             try:
-                line["e2e_dropin"] = dropin_leg(head, local_rank, pool[:8])
+                line["e2e_dropin"] = dropin_leg(head, local_rank, pool[:8], args.dropin_via_reference)
             except Exception as e:
                 line["e2e_dropin"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if not args.no_cpu_baseline and world == 1:     # rank 0 at N = 1 only
